@@ -1,0 +1,36 @@
+// Operator base class behind the C ABI: one virtual per ArrowOperator trait method
+// (arroyo-operator/src/operator.rs:1143-1257).
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "arrow_io.h"
+#include "common.cuh"
+
+namespace ab {
+
+class OpBase {
+ public:
+  ArroyoB200OpConfig cfg{};
+  std::string last_error;
+  std::string name;
+
+  virtual ~OpBase() {}
+  virtual void on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, int64_t watermark, int64_t table_min) = 0;
+  virtual void process_batch(uint32_t index, uint32_t in_partitions, ArrowArray* batch, const ArrowSchema* schema) = 0;
+  virtual void process_device_batch(uint32_t index, uint32_t in_partitions, const uint64_t* cols, int32_t n_cols,
+                                    int64_t n_rows) = 0;
+  // exactly one of out_host / out_dev is non-null
+  virtual void handle_watermark(int64_t watermark, BatchesPriv* out_host, std::vector<ArroyoB200DeviceBatch>* out_dev) = 0;
+  virtual void handle_checkpoint(int64_t watermark, BatchesPriv* out) = 0;
+  virtual void on_close(int end_of_data, BatchesPriv* out) = 0;
+  virtual void flush() = 0;
+  virtual void stats(ArroyoB200Stats* out) = 0;
+};
+
+OpBase* make_window_agg_op(const ArroyoB200OpConfig& cfg);
+OpBase* make_instant_join_op(const ArroyoB200OpConfig& cfg);
+OpBase* make_session_op(const ArroyoB200OpConfig& cfg);
+
+}  // namespace ab

@@ -1,0 +1,1917 @@
+// Tumbling / sliding window keyed aggregate on sm_100a.
+//
+// Replaces, behind the ArrowOperator surface:
+//   TumblingAggregatingWindowFunc  arroyo-worker/src/arrow/tumbling_aggregating_window.rs:250-392
+//   SlidingAggregatingWindowFunc   arroyo-worker/src/arrow/sliding_aggregating_window.rs:102-210, :598-737
+// and the DataFusion / arrow-rs work they call per batch:
+//   K1 date_bin  K2 sort_to_indices+take+partition  K3 AggregateExec(Partial)
+//   K4 AggregateExec(Final)  K5 final projection (window struct, _timestamp)  K7 late-row filter
+//
+// Design:
+//   * one persistent key dictionary per operator: open addressing, 16-byte slots {key, dense id};
+//     keys recur in every pane, so after warm-up a row costs one read-only 16-byte probe (L2 hit).
+//   * one accumulator block per pane: dense SoA arrays indexed by id (rows, then one 64-bit
+//     accumulator per SUM / AVG / MIN / MAX).  A row = date_bin (one mulhi) + late test + probe +
+//     one RED per accumulator.  Nothing is sorted, gathered or materialised per batch.
+//   * panes live in a ring indexed by (ts / slide) & (R - 1); the device table pane_bins[] says
+//     which bin a slot holds.  Rows whose pane is not resident (far future / before the ring) or
+//     whose key cannot get an id (dictionary full) are copied to a deferred buffer; the host grows
+//     the ring / dictionary at the next sync point and re-ingests them.  No row is lost.
+//   * emission merges the panes of a window element-wise over the dense id space, finalises
+//     (AVG = sum / count), compacts ids with rows > 0 and writes the output columns including
+//     window.start / window.end / _timestamp.  Invertible aggregates (COUNT/SUM/AVG) keep a running
+//     window block W += entering pane, W -= leaving pane instead of re-merging width/slide panes.
+#include <algorithm>
+#include <climits>
+#include <deque>
+#include <map>
+#include <memory>
+#include <set>
+
+#include "op.h"
+#include "planner.h"
+
+namespace ab {
+namespace {
+
+constexpr int MAX_VALS = 4;
+constexpr int MAX_ACC = ARROYO_B200_MAX_AGGS + 1;
+constexpr int MAX_SEGS = 512;
+constexpr int MAX_RING = 4096;
+constexpr int MAX_MERGE = 4096;
+constexpr uint32_t ID_UNSET = 0xFFFFFFFFu;
+constexpr uint32_t ID_OVERFLOW = 0xFFFFFFFEu;
+constexpr long long EMPTY_KEY = LLONG_MIN;
+constexpr long long FREE_BIN = LLONG_MIN;
+constexpr int MAX_PROBE = 4096;
+
+constexpr int THREADS = 256;
+constexpr int PAIRS = 2;
+constexpr int TILE = THREADS * PAIRS * 2;  // rows per tile
+
+struct alignas(16) Slot {
+  long long key;
+  uint32_t id;
+  uint32_t pad;
+};
+
+enum AccKind : int { ACC_ROWS = 0, ACC_SUM_I64 = 1, ACC_SUM_F64 = 2, ACC_MIN_I64 = 3, ACC_MAX_I64 = 4 };
+
+struct Counters {
+  unsigned long long late_rows;
+  unsigned long long deferred;
+  unsigned long long lost;
+  unsigned long long ontime_rows;
+  long long max_bin;
+  long long min_bin;
+  unsigned int n_keys;
+  unsigned int pad;
+};
+
+struct Segment {
+  const long long* key;
+  const long long* ts;
+  const long long* val[MAX_VALS];
+  long long n;
+  long long tile_start;
+  int vec_ok;
+  int pad;
+};
+
+struct DictView {
+  Slot* slots;
+  long long* id_keys;
+  unsigned int* n_keys;
+  uint32_t mask;
+  uint32_t id_cap;
+};
+
+struct IngestParams {
+  const Segment* segs;
+  int n_segs;
+  int keyed;
+  long long n_tiles;
+  DictView dict;
+  FastDivU64 slide_div;
+  long long slide;
+  long long late_bin;
+  uint32_t ring_mask;
+  int n_acc;
+  const long long* pane_bins;
+  unsigned long long* const* pane_ptrs;
+  unsigned long long id_cap;
+  int acc_kind[MAX_ACC];
+  int acc_val[MAX_ACC];
+  Counters* counters;
+  unsigned int* touched;
+  long long* d_key;
+  long long* d_ts;
+  long long* d_val[MAX_VALS];
+  unsigned long long defer_cap;
+};
+
+// -------------------------------------------------------------------------------------------
+// dictionary
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t wait_id(const Slot* s) {
+  uint32_t id;
+  do {
+    __nanosleep(20);
+    id = *(volatile const uint32_t*)&s->id;
+  } while (id == ID_UNSET);
+  return id;
+}
+
+// Returns the dense id of `key`, inserting it if absent; ID_OVERFLOW if no id / slot is available.
+__device__ __forceinline__ uint32_t dict_lookup_insert(const DictView& d, long long key) {
+  if (key == EMPTY_KEY) return 0;  // id 0 is reserved for the one key that equals the sentinel
+  uint32_t pos = (uint32_t)mix64((uint64_t)key) & d.mask;
+#pragma unroll 1
+  for (int probe = 0; probe < MAX_PROBE; ++probe) {
+    Slot* sp = d.slots + pos;
+    ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(sp));
+    long long k = (long long)raw.x;
+    uint32_t id = (uint32_t)raw.y;
+    if (k == key) {
+      if (id == ID_UNSET) id = wait_id(sp);
+      return id;
+    }
+    if (k == EMPTY_KEY) {
+      unsigned long long old =
+          atomicCAS(reinterpret_cast<unsigned long long*>(&sp->key), (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+      if (old == (unsigned long long)EMPTY_KEY) {
+        uint32_t nid = atomicAdd(d.n_keys, 1u);
+        if (nid >= d.id_cap) {
+          nid = ID_OVERFLOW;
+        } else {
+          d.id_keys[nid] = key;
+        }
+        __threadfence();
+        atomicExch(&sp->id, nid);
+        return nid;
+      }
+      if ((long long)old == key) return wait_id(sp);
+      // another key claimed the slot: keep probing
+    }
+    pos = (pos + 1) & d.mask;
+  }
+  return ID_OVERFLOW;
+}
+
+__global__ void dict_init_kernel(Slot* slots, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    slots[i].key = EMPTY_KEY;
+    slots[i].id = ID_UNSET;
+    slots[i].pad = 0;
+  }
+}
+
+// re-insert ids [1, n) after the slot array was replaced
+__global__ void dict_rebuild_kernel(Slot* slots, uint32_t mask, const long long* id_keys, uint32_t n) {
+  uint32_t id = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  uint32_t stride = gridDim.x * blockDim.x;
+  for (; id < n; id += stride) {
+    long long key = id_keys[id];
+    uint32_t pos = (uint32_t)mix64((uint64_t)key) & mask;
+    while (true) {
+      unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&slots[pos].key),
+                                         (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+      if (old == (unsigned long long)EMPTY_KEY) {
+        slots[pos].id = id;
+        break;
+      }
+      pos = (pos + 1) & mask;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// pane blocks
+// -------------------------------------------------------------------------------------------
+struct InitParams {
+  unsigned long long* pane;
+  unsigned long long id_cap;
+  unsigned long long n;  // ids [0, n) to reset
+  int n_acc;
+  int acc_kind[MAX_ACC];
+};
+
+__global__ void pane_init_kernel(const __grid_constant__ InitParams p) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < p.n; i += stride) {
+    for (int a = 0; a < p.n_acc; ++a) {
+      unsigned long long v = 0;
+      if (p.acc_kind[a] == ACC_MIN_I64) v = (unsigned long long)LLONG_MAX;
+      if (p.acc_kind[a] == ACC_MAX_I64) v = (unsigned long long)LLONG_MIN;
+      p.pane[a * p.id_cap + i] = v;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// ingest: window-assign + keyed partial aggregate
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ const long long* ldg_ptr(const long long* const* pp) {
+  return reinterpret_cast<const long long*>(__ldg(reinterpret_cast<const unsigned long long*>(pp)));
+}
+
+template <int NV>
+struct Row {
+  long long key;
+  long long ts;
+  long long val[NV > 0 ? NV : 1];
+};
+
+template <int NV>
+__device__ __forceinline__ void defer_row(const IngestParams& p, const Row<NV>& r) {
+  unsigned long long idx = atomicAdd(&p.counters->deferred, 1ull);
+  if (idx < p.defer_cap) {
+    p.d_key[idx] = r.key;
+    p.d_ts[idx] = r.ts;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) p.d_val[v][idx] = r.val[v];
+  } else {
+    atomicAdd(&p.counters->lost, 1ull);
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void process_row(const IngestParams& p, const Row<NV>& r, unsigned char* s_touched,
+                                            unsigned long long& late, unsigned long long& ontime, long long& maxb,
+                                            long long& minb) {
+  // K1: bin = ts - ts % slide (tumbling_aggregating_window.rs:65-73)
+  uint64_t q = p.slide_div.div((uint64_t)r.ts);
+  long long bin = (long long)(q * (uint64_t)p.slide);
+  // K7: late bins are dropped (tumbling :282-291, sliding :631-633)
+  if (bin < p.late_bin) {
+    ++late;
+    return;
+  }
+  maxb = max(maxb, bin);
+  minb = min(minb, bin);
+  uint32_t slot = (uint32_t)q & p.ring_mask;
+  if (__ldg(p.pane_bins + slot) != bin) {
+    defer_row<NV>(p, r);
+    return;
+  }
+  uint32_t id = 0;
+  if (p.keyed) {
+    id = dict_lookup_insert(p.dict, r.key);
+    if (id >= ID_OVERFLOW) {
+      defer_row<NV>(p, r);
+      return;
+    }
+  }
+  ++ontime;
+  s_touched[slot] = 1;
+  unsigned long long* pane = reinterpret_cast<unsigned long long*>(__ldg(reinterpret_cast<const unsigned long long*>(p.pane_ptrs + slot)));
+  // K3: partial aggregate.  Results are unused => the compiler emits RED (no return trip).
+  atomicAdd(pane + id, 1ull);
+#pragma unroll
+  for (int a = 1; a < MAX_ACC; ++a) {
+    if (a < p.n_acc) {
+      unsigned long long* dst = pane + (unsigned long long)a * p.id_cap + id;
+      long long v = 0;
+#pragma unroll
+      for (int x = 0; x < NV; ++x)
+        if (p.acc_val[a] == x) v = r.val[x];
+      switch (p.acc_kind[a]) {
+        case ACC_SUM_I64:
+          atomicAdd(dst, (unsigned long long)v);
+          break;
+        case ACC_SUM_F64:
+          atomicAdd(reinterpret_cast<double*>(dst), (double)v);
+          break;
+        case ACC_MIN_I64:
+          atomicMin(reinterpret_cast<long long*>(dst), v);
+          break;
+        case ACC_MAX_I64:
+          atomicMax(reinterpret_cast<long long*>(dst), v);
+          break;
+        default:
+          break;
+      }
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(THREADS) ingest_kernel(const __grid_constant__ IngestParams p) {
+  __shared__ unsigned char s_touched[MAX_RING];
+  __shared__ unsigned long long s_red[4][THREADS / 32];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < MAX_RING; i += THREADS) s_touched[i] = 0;
+  __syncthreads();
+
+  unsigned long long late = 0, ontime = 0;
+  long long maxb = LLONG_MIN, minb = LLONG_MAX;
+
+  for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    int lo = 0, hi = p.n_segs - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&p.segs[mid].tile_start) <= tile) lo = mid; else hi = mid - 1;
+    }
+    const Segment* sg = p.segs + lo;
+    const long long base = (tile - __ldg(&sg->tile_start)) * TILE;
+    const long long nrem = __ldg(&sg->n) - base;
+    const int cnt = nrem < TILE ? (int)nrem : TILE;
+    const long long* kcol = ldg_ptr(&sg->key);
+    const long long* tcol = ldg_ptr(&sg->ts);
+    const long long* vcol[NV > 0 ? NV : 1];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) vcol[v] = ldg_ptr(&sg->val[v]);
+
+    if (cnt == TILE && __ldg(&sg->vec_ok)) {
+      // 128-bit streaming loads: a warp instruction covers 512 contiguous bytes per column
+      Row<NV> rows[PAIRS * 2];
+#pragma unroll
+      for (int j = 0; j < PAIRS; ++j) {
+        const long long r0 = base + 2ll * (j * THREADS + tid);
+        longlong2 t2 = __ldcs(reinterpret_cast<const longlong2*>(tcol + r0));
+        rows[2 * j].ts = t2.x;
+        rows[2 * j + 1].ts = t2.y;
+        if (p.keyed) {
+          longlong2 k2 = __ldcs(reinterpret_cast<const longlong2*>(kcol + r0));
+          rows[2 * j].key = k2.x;
+          rows[2 * j + 1].key = k2.y;
+        } else {
+          rows[2 * j].key = 0;
+          rows[2 * j + 1].key = 0;
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          longlong2 v2 = __ldcs(reinterpret_cast<const longlong2*>(vcol[v] + r0));
+          rows[2 * j].val[v] = v2.x;
+          rows[2 * j + 1].val[v] = v2.y;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < PAIRS * 2; ++j) process_row<NV>(p, rows[j], s_touched, late, ontime, maxb, minb);
+    } else {
+      for (int i = tid; i < cnt; i += THREADS) {
+        Row<NV> r;
+        r.ts = __ldcs(tcol + base + i);
+        r.key = p.keyed ? __ldcs(kcol + base + i) : 0;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) r.val[v] = __ldcs(vcol[v] + base + i);
+        process_row<NV>(p, r, s_touched, late, ontime, maxb, minb);
+      }
+    }
+  }
+
+  // block-level reductions of the bookkeeping counters: a handful of atomics per CTA
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    late += __shfl_xor_sync(0xffffffffu, late, o);
+    ontime += __shfl_xor_sync(0xffffffffu, ontime, o);
+    maxb = max(maxb, __shfl_xor_sync(0xffffffffu, maxb, o));
+    minb = min(minb, __shfl_xor_sync(0xffffffffu, minb, o));
+  }
+  const int w = tid >> 5;
+  if ((tid & 31) == 0) {
+    s_red[0][w] = late;
+    s_red[1][w] = ontime;
+    s_red[2][w] = (unsigned long long)maxb;
+    s_red[3][w] = (unsigned long long)minb;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 1; i < THREADS / 32; ++i) {
+      late += s_red[0][i];
+      ontime += s_red[1][i];
+      maxb = max(maxb, (long long)s_red[2][i]);
+      minb = min(minb, (long long)s_red[3][i]);
+    }
+    if (late) atomicAdd(&p.counters->late_rows, late);
+    if (ontime) atomicAdd(&p.counters->ontime_rows, ontime);
+    if (maxb != LLONG_MIN) atomicMax(&p.counters->max_bin, maxb);
+    if (minb != LLONG_MAX) atomicMin(&p.counters->min_bin, minb);
+  }
+  for (int i = tid; i <= (int)p.ring_mask; i += THREADS)
+    if (s_touched[i]) p.touched[i] = 1u;
+}
+
+// Restore: merge a partial-state batch (AggregateExec(Partial) output written at a checkpoint,
+// sliding_aggregating_window.rs:725-733) into one pane block.
+struct PartialParams {
+  const long long* key;
+  const unsigned long long* state[MAX_ACC];  // state[0] = rows
+  long long n;
+  int keyed;
+  int n_acc;
+  int acc_kind[MAX_ACC];
+  DictView dict;
+  unsigned long long* pane;
+  unsigned long long id_cap;
+  Counters* counters;
+};
+
+__global__ void ingest_partial_kernel(const __grid_constant__ PartialParams p) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < p.n; i += stride) {
+    uint32_t id = 0;
+    if (p.keyed) {
+      id = dict_lookup_insert(p.dict, p.key[i]);
+      if (id >= ID_OVERFLOW) {
+        atomicAdd(&p.counters->lost, 1ull);
+        continue;
+      }
+    }
+    for (int a = 0; a < p.n_acc; ++a) {
+      unsigned long long* dst = p.pane + (unsigned long long)a * p.id_cap + id;
+      unsigned long long v = p.state[a][i];
+      switch (p.acc_kind[a]) {
+        case ACC_ROWS:
+        case ACC_SUM_I64:
+          atomicAdd(dst, v);
+          break;
+        case ACC_SUM_F64:
+          atomicAdd(reinterpret_cast<double*>(dst), __longlong_as_double((long long)v));
+          break;
+        case ACC_MIN_I64:
+          atomicMin(reinterpret_cast<long long*>(dst), (long long)v);
+          break;
+        case ACC_MAX_I64:
+          atomicMax(reinterpret_cast<long long*>(dst), (long long)v);
+          break;
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// emission: pane merge (K4) + finalise + projection (K5) + compaction
+// -------------------------------------------------------------------------------------------
+struct EmitParams {
+  const unsigned long long* const* panes;  // device array of n_panes block pointers
+  int n_panes;
+  int n_acc;
+  unsigned long long id_cap;
+  uint32_t n_ids;
+  int keyed;
+  int acc_kind[MAX_ACC];
+  int n_aggs;
+  int agg_kind[ARROYO_B200_MAX_AGGS];
+  int agg_acc[ARROYO_B200_MAX_AGGS];
+  const long long* id_keys;
+  long long* out_key;
+  unsigned long long* out_agg[ARROYO_B200_MAX_AGGS];
+  long long* out_wstart;
+  long long* out_wend;
+  long long* out_ts;
+  long long wstart, wend, ts;
+  unsigned int* out_count;
+  // running-window mode: W (same layout as a pane) is updated in place with
+  // W += add panes, W -= sub panes and the output is produced from W.
+  unsigned long long* running;
+  int n_add;  // panes[0 .. n_add) enter, panes[n_add .. n_panes) leave
+  // partial-state mode (checkpoint): emit raw accumulator columns instead of finalised aggregates
+  int partial;
+  unsigned long long* out_state[MAX_ACC];
+};
+
+constexpr int EMIT_THREADS = 256;
+
+__global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(const __grid_constant__ EmitParams p) {
+  __shared__ unsigned int s_warp[EMIT_THREADS / 32];
+  __shared__ unsigned int s_base;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, w = tid >> 5;
+  const uint32_t n_iter = (p.n_ids + EMIT_THREADS - 1) / EMIT_THREADS;
+  for (uint32_t it = blockIdx.x; it < n_iter; it += gridDim.x) {
+    const uint32_t id = it * EMIT_THREADS + tid;
+    unsigned long long acc[MAX_ACC];
+    unsigned long long rows = 0;
+    if (id < p.n_ids) {
+      if (p.running) {
+#pragma unroll
+        for (int a = 0; a < MAX_ACC; ++a)
+          if (a < p.n_acc) acc[a] = p.running[(unsigned long long)a * p.id_cap + id];
+        for (int k = 0; k < p.n_panes; ++k) {
+          const unsigned long long* pane = p.panes[k];
+          const bool add = k < p.n_add;
+#pragma unroll
+          for (int a = 0; a < MAX_ACC; ++a) {
+            if (a < p.n_acc) {
+              unsigned long long v = __ldcs(pane + (unsigned long long)a * p.id_cap + id);
+              if (p.acc_kind[a] == ACC_SUM_F64) {
+                double d = __longlong_as_double((long long)acc[a]);
+                double x = __longlong_as_double((long long)v);
+                acc[a] = (unsigned long long)__double_as_longlong(add ? d + x : d - x);
+              } else {
+                acc[a] = add ? acc[a] + v : acc[a] - v;
+              }
+            }
+          }
+        }
+        rows = acc[0];
+        // a key that left the window restarts from exactly zero (no f64 drift carried over)
+#pragma unroll
+        for (int a = 0; a < MAX_ACC; ++a) {
+          if (a < p.n_acc) {
+            if (rows == 0) acc[a] = 0;
+            p.running[(unsigned long long)a * p.id_cap + id] = acc[a];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int a = 0; a < MAX_ACC; ++a) {
+          if (a < p.n_acc) {
+            acc[a] = 0;
+            if (p.acc_kind[a] == ACC_MIN_I64) acc[a] = (unsigned long long)LLONG_MAX;
+            if (p.acc_kind[a] == ACC_MAX_I64) acc[a] = (unsigned long long)LLONG_MIN;
+          }
+        }
+        for (int k = 0; k < p.n_panes; ++k) {
+          const unsigned long long* pane = p.panes[k];
+#pragma unroll
+          for (int a = 0; a < MAX_ACC; ++a) {
+            if (a < p.n_acc) {
+              unsigned long long v = __ldcs(pane + (unsigned long long)a * p.id_cap + id);
+              switch (p.acc_kind[a]) {
+                case ACC_ROWS:
+                case ACC_SUM_I64:
+                  acc[a] += v;
+                  break;
+                case ACC_SUM_F64:
+                  acc[a] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)acc[a]) +
+                                                                    __longlong_as_double((long long)v));
+                  break;
+                case ACC_MIN_I64:
+                  acc[a] = (unsigned long long)min((long long)acc[a], (long long)v);
+                  break;
+                case ACC_MAX_I64:
+                  acc[a] = (unsigned long long)max((long long)acc[a], (long long)v);
+                  break;
+              }
+            }
+          }
+        }
+        rows = acc[0];
+      }
+    }
+    const bool valid = rows != 0;
+    const unsigned int ballot = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) s_warp[w] = __popc(ballot);
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int total = 0;
+      for (int i = 0; i < EMIT_THREADS / 32; ++i) {
+        unsigned int c = s_warp[i];
+        s_warp[i] = total;
+        total += c;
+      }
+      s_base = total ? atomicAdd(p.out_count, total) : 0u;
+    }
+    __syncthreads();
+    if (valid) {
+      const unsigned int o = s_base + s_warp[w] + __popc(ballot & ((1u << lane) - 1u));
+      if (p.keyed) p.out_key[o] = p.id_keys[id];
+      if (p.partial) {
+#pragma unroll
+        for (int a = 0; a < MAX_ACC; ++a)
+          if (a < p.n_acc) p.out_state[a][o] = acc[a];
+        p.out_ts[o] = p.ts;
+      } else {
+#pragma unroll
+        for (int g = 0; g < ARROYO_B200_MAX_AGGS; ++g) {
+          if (g < p.n_aggs) {
+            unsigned long long v;
+            switch (p.agg_kind[g]) {
+              case ARROYO_B200_AGG_COUNT_STAR:
+                v = rows;
+                break;
+              case ARROYO_B200_AGG_AVG_I64:
+                v = (unsigned long long)__double_as_longlong(
+                    __longlong_as_double((long long)acc[p.agg_acc[g]]) / (double)rows);
+                break;
+              default:
+                v = acc[p.agg_acc[g]];
+                break;
+            }
+            p.out_agg[g][o] = v;
+          }
+        }
+        if (p.out_wstart) {
+          p.out_wstart[o] = p.wstart;
+          p.out_wend[o] = p.wend;
+        }
+        p.out_ts[o] = p.ts;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// checkpoint fold: frozen += active; active = identity  (see Pane::frozen)
+struct FoldParams {
+  unsigned long long* active;
+  unsigned long long* frozen;
+  unsigned long long id_cap;
+  uint32_t n_ids;
+  int n_acc;
+  int acc_kind[MAX_ACC];
+};
+__global__ void fold_kernel(const __grid_constant__ FoldParams p) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t stride = gridDim.x * blockDim.x;
+  for (; i < p.n_ids; i += stride) {
+    for (int a = 0; a < p.n_acc; ++a) {
+      unsigned long long* fa = p.frozen + (unsigned long long)a * p.id_cap + i;
+      unsigned long long* aa = p.active + (unsigned long long)a * p.id_cap + i;
+      unsigned long long f = *fa, v = *aa, ident = 0;
+      switch (p.acc_kind[a]) {
+        case ACC_ROWS:
+        case ACC_SUM_I64:
+          f += v;
+          break;
+        case ACC_SUM_F64:
+          f = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)f) +
+                                                       __longlong_as_double((long long)v));
+          break;
+        case ACC_MIN_I64:
+          f = (unsigned long long)min((long long)f, (long long)v);
+          ident = (unsigned long long)LLONG_MAX;
+          break;
+        case ACC_MAX_I64:
+          f = (unsigned long long)max((long long)f, (long long)v);
+          ident = (unsigned long long)LLONG_MIN;
+          break;
+      }
+      *fa = f;
+      *aa = ident;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------
+struct Pane {
+  int64_t bin = 0;
+  unsigned long long* dev = nullptr;     // active accumulators (receives REDs)
+  unsigned long long* frozen = nullptr;  // state already written to a checkpoint / restored
+  int slot = -1;
+  bool in_tier = false;
+};
+
+struct LaunchRec {
+  cudaEvent_t done = nullptr;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  Counters* h_counters = nullptr;  // pinned
+  unsigned int* h_touched = nullptr;  // pinned [MAX_RING]
+  uint64_t rows = 0;
+  bool in_flight = false;
+  int chunk = -1;  // staging chunk read by this launch (-1: none)
+};
+
+struct PendingRelease {
+  cudaEvent_t ev;
+  ArrowArray arr;  // moved-in copy; released when ev completes
+};
+
+class WindowAggOp final : public OpBase {
+ public:
+  explicit WindowAggOp(const ArroyoB200OpConfig& c);
+  ~WindowAggOp() override;
+
+  void on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, int64_t watermark, int64_t table_min) override;
+  void process_batch(uint32_t, uint32_t, ArrowArray* batch, const ArrowSchema* schema) override;
+  void process_device_batch(uint32_t, uint32_t, const uint64_t* cols, int32_t n_cols, int64_t n_rows) override;
+  void handle_watermark(int64_t wm, BatchesPriv* out_host, std::vector<ArroyoB200DeviceBatch>* out_dev) override;
+  void handle_checkpoint(int64_t wm, BatchesPriv* out) override;
+  void on_close(int, BatchesPriv*) override { flush(); }
+  void flush() override;
+  void stats(ArroyoB200Stats* out) override;
+
+ private:
+  // config-derived
+  bool sliding_;
+  int64_t width_, slide_;  // slide_ == width_ for tumbling
+  bool keyed_;
+  int key_col_, ts_col_;
+  int n_vals_ = 0;
+  int val_cols_[MAX_VALS];
+  int n_acc_ = 1;
+  int acc_kind_[MAX_ACC];
+  int acc_val_[MAX_ACC];
+  int n_aggs_;
+  int agg_kind_[ARROYO_B200_MAX_AGGS];
+  int agg_acc_[ARROYO_B200_MAX_AGGS];
+  bool invertible_ = true;
+  bool running_mode_ = false;
+  bool profile_;
+  std::string key_format_ = "l";
+  std::vector<std::string> agg_format_;
+
+  int device_;
+  cudaStream_t stream_ = nullptr;
+  bool own_stream_ = false;
+  int num_sms_ = 148;
+
+  // dictionary
+  uint64_t id_cap_ = 0;
+  uint64_t dict_cap_ = 0;
+  DevBuf slots_, id_keys_, counters_, touched_;
+  uint32_t n_keys_host_ = 1;
+
+  // ring
+  uint32_t ring_ = 16;
+  std::vector<long long> h_pane_bins_;
+  std::vector<unsigned long long*> h_pane_ptrs_;
+  DevBuf d_pane_bins_, d_pane_ptrs_;
+  bool ring_dirty_ = true;
+  std::map<int64_t, Pane> panes_;
+  std::vector<std::pair<unsigned long long*, uint64_t>> free_panes_;  // (block, dirty ids)
+  std::vector<DevBuf> pane_storage_;
+  int64_t late_bin_ = LLONG_MIN;
+  int64_t max_bin_seen_ = LLONG_MIN;
+
+  // running window block
+  unsigned long long* running_ = nullptr;
+  std::set<int64_t> in_running_;
+  std::map<int64_t, Pane> zombies_;  // left the store; blocks kept until the next emit subtracts them
+
+  // planners
+  std::unique_ptr<TumblingPlanner> tumbling_;
+  std::unique_ptr<SlidingPlanner> sliding_planner_;
+
+  // staging
+  static constexpr int NCHUNK = 3;
+  static constexpr int NLAUNCH = 3;
+  int64_t chunk_rows_ = 1 << 22;
+  DevBuf chunk_[NCHUNK];
+  cudaEvent_t chunk_free_[NCHUNK] = {nullptr, nullptr, nullptr};
+  int cur_chunk_ = 0;
+  int64_t cur_rows_ = 0;
+  std::vector<Segment> segs_;
+  int64_t pending_rows_ = 0;
+  bool pending_uses_chunk_ = false;
+  PinnedBuf h_segs_[NLAUNCH];
+  DevBuf d_segs_[NLAUNCH];
+  LaunchRec launches_[NLAUNCH];
+  PinnedBuf h_counters_[NLAUNCH], h_touched_[NLAUNCH];
+  int next_launch_ = 0;
+  std::deque<int> in_flight_;
+  std::deque<PendingRelease> releases_;
+
+  // deferred rows (two sets: one being filled, one being re-ingested)
+  uint64_t defer_cap_ = 0;
+  DevBuf defer_[2][2 + MAX_VALS];
+  int defer_cur_ = 0;
+  Counters last_counters_{};
+  bool have_counters_ = false;
+  bool draining_ = false;
+
+  // emission output
+  struct OutSet {
+    DevBuf key, wstart, wend, ts;
+    DevBuf agg[ARROYO_B200_MAX_AGGS];
+    DevBuf state[MAX_ACC];
+    uint64_t cap = 0;
+  };
+  std::vector<std::unique_ptr<OutSet>> out_sets_;
+  DevBuf d_emit_panes_, d_out_count_;
+  PinnedBuf h_out_count_;
+
+  ArroyoB200Stats st_{};
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> emit_events_;
+
+  // helpers
+  void set_device() { AB_CUDA(cudaSetDevice(device_)); }
+  void alloc_dictionary(uint64_t id_cap);
+  void grow_ids();
+  unsigned long long* acquire_block();
+  void release_block(unsigned long long* blk);
+  void init_block(unsigned long long* blk, uint64_t n_ids);
+  void ensure_pane(int64_t bin);
+  void drop_pane(int64_t bin);
+  void upload_ring();
+  void add_segment(const long long* key, const long long* ts, const long long* const* vals, int64_t n);
+  void launch_pending();
+  void launch_segments(const std::vector<Segment>& segs, int chunk);
+  void absorb(int li);
+  void sync_all();
+  void drain_deferred();
+  void poll_releases(bool wait);
+  void rotate_chunk();
+  void touch(int64_t bin);
+  OutSet* out_set(size_t i, uint64_t cap);
+  int64_t run_emit(const std::vector<const unsigned long long*>& blocks, int n_add, bool use_running, bool partial,
+                   int64_t wstart, int64_t wend, int64_t ts, OutSet* os);
+  void emit_window(int64_t a, int64_t b, size_t out_index, BatchesPriv* out_host,
+                   std::vector<ArroyoB200DeviceBatch>* out_dev);
+  void export_window(OutSet* os, int64_t n, BatchesPriv* out_host);
+  void export_partial(OutSet* os, int64_t n, BatchesPriv* out);
+  void lookahead();
+};
+
+WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
+  cfg = c;
+  sliding_ = c.kind == ARROYO_B200_SLIDING_AGGREGATE;
+  name = sliding_ ? "sliding_window" : "tumbling_window";
+  AB_REQUIRE(c.width_ns > 0, ARROYO_B200_UNSUPPORTED, "width_micros == 0 (instant window) is not supported");
+  width_ = c.width_ns;
+  slide_ = sliding_ ? c.slide_ns : c.width_ns;
+  AB_REQUIRE(slide_ >= 2, ARROYO_B200_INVALID_ARGUMENT, "slide must be >= 2 ns");
+  if (sliding_)
+    AB_REQUIRE(width_ % slide_ == 0, ARROYO_B200_INVALID_ARGUMENT,
+               "hop width must be a multiple of the slide (arroyo-planner/src/lib.rs:640-655)");
+  AB_REQUIRE(c.n_key_cols == 0 || c.n_key_cols == 1, ARROYO_B200_UNSUPPORTED,
+             "only 0 or 1 group-by key columns are supported");
+  keyed_ = c.n_key_cols == 1;
+  key_col_ = c.key_col;
+  ts_col_ = c.timestamp_col;
+  AB_REQUIRE(c.n_cols >= 1 && c.n_cols <= ARROYO_B200_MAX_COLS, ARROYO_B200_INVALID_ARGUMENT, "bad n_cols");
+  AB_REQUIRE(ts_col_ >= 0 && ts_col_ < c.n_cols, ARROYO_B200_INVALID_ARGUMENT, "bad timestamp_col");
+  AB_REQUIRE(!keyed_ || (key_col_ >= 0 && key_col_ < c.n_cols), ARROYO_B200_INVALID_ARGUMENT, "bad key_col");
+  AB_REQUIRE(c.n_aggs >= 1 && c.n_aggs <= ARROYO_B200_MAX_AGGS, ARROYO_B200_INVALID_ARGUMENT, "bad n_aggs");
+  n_aggs_ = c.n_aggs;
+  acc_kind_[0] = ACC_ROWS;
+  acc_val_[0] = 0;
+  for (int g = 0; g < n_aggs_; ++g) {
+    int kind = c.aggs[g].kind;
+    agg_kind_[g] = kind;
+    agg_acc_[g] = 0;
+    if (kind == ARROYO_B200_AGG_COUNT_STAR) {
+      agg_format_.push_back("l");
+      continue;
+    }
+    int col = c.aggs[g].input_col;
+    AB_REQUIRE(col >= 0 && col < c.n_cols, ARROYO_B200_INVALID_ARGUMENT, "aggregate input column out of range");
+    int vs = -1;
+    for (int v = 0; v < n_vals_; ++v)
+      if (val_cols_[v] == col) vs = v;
+    if (vs < 0) {
+      AB_REQUIRE(n_vals_ < MAX_VALS, ARROYO_B200_UNSUPPORTED, "more than 4 distinct aggregate input columns");
+      vs = n_vals_;
+      val_cols_[n_vals_++] = col;
+    }
+    int ak;
+    switch (kind) {
+      case ARROYO_B200_AGG_SUM_I64: ak = ACC_SUM_I64; agg_format_.push_back("l"); break;
+      case ARROYO_B200_AGG_AVG_I64: ak = ACC_SUM_F64; agg_format_.push_back("g"); break;
+      case ARROYO_B200_AGG_MIN_I64: ak = ACC_MIN_I64; agg_format_.push_back("l"); invertible_ = false; break;
+      case ARROYO_B200_AGG_MAX_I64: ak = ACC_MAX_I64; agg_format_.push_back("l"); invertible_ = false; break;
+      default:
+        throw Error(ARROYO_B200_UNSUPPORTED, "unsupported aggregate kind");
+    }
+    // share accumulators between identical (kind, column) pairs
+    int found = -1;
+    for (int a = 1; a < n_acc_; ++a)
+      if (acc_kind_[a] == ak && acc_val_[a] == vs) found = a;
+    if (found < 0) {
+      found = n_acc_;
+      acc_kind_[n_acc_] = ak;
+      acc_val_[n_acc_] = vs;
+      ++n_acc_;
+    }
+    agg_acc_[g] = found;
+  }
+  profile_ = (c.flags & ARROYO_B200_FLAG_PROFILE) != 0;
+  running_mode_ = sliding_ && invertible_ && !(c.flags & ARROYO_B200_FLAG_REMERGE_ONLY) && width_ > slide_;
+
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    throw Error(ARROYO_B200_FATAL, "no CUDA device available: libarroyo_b200 has no CPU fallback");
+  device_ = c.device;
+  AB_REQUIRE(device_ >= 0 && device_ < count, ARROYO_B200_INVALID_ARGUMENT, "bad device ordinal");
+  set_device();
+  cudaDeviceProp prop{};
+  AB_CUDA(cudaGetDeviceProperties(&prop, device_));
+  num_sms_ = prop.multiProcessorCount;
+  if (c.stream) {
+    stream_ = (cudaStream_t)c.stream;
+  } else {
+    AB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    own_stream_ = true;
+  }
+
+  if (sliding_) sliding_planner_.reset(new SlidingPlanner(width_, slide_));
+  else tumbling_.reset(new TumblingPlanner(width_));
+
+  counters_.alloc(sizeof(Counters));
+  touched_.alloc(MAX_RING * sizeof(unsigned int));
+  Counters init{};
+  init.max_bin = LLONG_MIN;
+  init.min_bin = LLONG_MAX;
+  init.n_keys = 1;
+  AB_CUDA(cudaMemcpyAsync(counters_.p, &init, sizeof init, cudaMemcpyHostToDevice, stream_));
+  last_counters_ = init;
+
+  uint64_t want = c.expected_keys ? c.expected_keys : (1ull << 16);
+  uint64_t cap = 1024;
+  while (cap < 2 * want + 2) cap <<= 1;
+  if (!keyed_) cap = 1024;
+  alloc_dictionary(cap);
+
+  h_pane_bins_.assign(MAX_RING, FREE_BIN);
+  h_pane_ptrs_.assign(MAX_RING, nullptr);
+  d_pane_bins_.alloc(MAX_RING * sizeof(long long));
+  d_pane_ptrs_.alloc(MAX_RING * sizeof(void*));
+  if (sliding_) {
+    uint64_t need = (uint64_t)(width_ / slide_) + 8;
+    while (ring_ < need && ring_ < MAX_RING) ring_ <<= 1;
+  }
+
+  const int n_used = 2 + n_vals_;
+  for (int i = 0; i < NCHUNK; ++i) {
+    AB_CUDA(cudaEventCreateWithFlags(&chunk_free_[i], cudaEventDisableTiming));
+  }
+  (void)n_used;
+  for (int i = 0; i < NLAUNCH; ++i) {
+    h_segs_[i].alloc(MAX_SEGS * sizeof(Segment));
+    d_segs_[i].alloc(MAX_SEGS * sizeof(Segment));
+    h_counters_[i].alloc(sizeof(Counters));
+    h_touched_[i].alloc(MAX_RING * sizeof(unsigned int));
+    launches_[i].h_counters = h_counters_[i].as<Counters>();
+    launches_[i].h_touched = h_touched_[i].as<unsigned int>();
+    AB_CUDA(cudaEventCreateWithFlags(&launches_[i].done, cudaEventDisableTiming));
+    if (profile_) {
+      AB_CUDA(cudaEventCreate(&launches_[i].t0));
+      AB_CUDA(cudaEventCreate(&launches_[i].t1));
+    }
+  }
+  defer_cap_ = (uint64_t)chunk_rows_ * 2;
+  d_emit_panes_.alloc(MAX_MERGE * sizeof(void*));
+  d_out_count_.alloc(sizeof(unsigned int));
+  h_out_count_.alloc(sizeof(unsigned int));
+  AB_CUDA(cudaStreamSynchronize(stream_));
+}
+
+WindowAggOp::~WindowAggOp() {
+  cudaSetDevice(device_);
+  cudaStreamSynchronize(stream_);
+  for (auto& r : releases_) {
+    if (r.arr.release) r.arr.release(&r.arr);
+    cudaEventDestroy(r.ev);
+  }
+  for (int i = 0; i < NCHUNK; ++i)
+    if (chunk_free_[i]) cudaEventDestroy(chunk_free_[i]);
+  for (int i = 0; i < NLAUNCH; ++i) {
+    if (launches_[i].done) cudaEventDestroy(launches_[i].done);
+    if (launches_[i].t0) cudaEventDestroy(launches_[i].t0);
+    if (launches_[i].t1) cudaEventDestroy(launches_[i].t1);
+  }
+  for (auto& e : emit_events_) {
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+  if (own_stream_ && stream_) cudaStreamDestroy(stream_);
+}
+
+void WindowAggOp::alloc_dictionary(uint64_t id_cap) {
+  id_cap_ = id_cap;
+  id_keys_.alloc(id_cap_ * sizeof(long long));
+  long long k0 = EMPTY_KEY;
+  AB_CUDA(cudaMemcpyAsync(id_keys_.p, &k0, sizeof k0, cudaMemcpyHostToDevice, stream_));
+  if (keyed_) {
+    dict_cap_ = id_cap_ * 2;
+    AB_REQUIRE(dict_cap_ <= (1ull << 31), ARROYO_B200_RUNTIME, "key dictionary too large");
+    slots_.alloc(dict_cap_ * sizeof(Slot));
+    dict_init_kernel<<<num_sms_ * 4, 256, 0, stream_>>>(slots_.as<Slot>(), dict_cap_);
+    AB_CUDA(cudaGetLastError());
+    ++st_.kernel_launches;
+  }
+}
+
+void WindowAggOp::init_block(unsigned long long* blk, uint64_t n_ids) {
+  if (n_ids == 0) return;
+  InitParams ip{};
+  ip.pane = blk;
+  ip.id_cap = id_cap_;
+  ip.n = n_ids;
+  ip.n_acc = n_acc_;
+  for (int a = 0; a < n_acc_; ++a) ip.acc_kind[a] = acc_kind_[a];
+  int blocks = (int)std::min<uint64_t>((n_ids + 255) / 256, (uint64_t)num_sms_ * 8);
+  pane_init_kernel<<<blocks, 256, 0, stream_>>>(ip);
+  AB_CUDA(cudaGetLastError());
+  ++st_.kernel_launches;
+}
+
+unsigned long long* WindowAggOp::acquire_block() {
+  if (!free_panes_.empty()) {
+    auto pr = free_panes_.back();
+    free_panes_.pop_back();
+    init_block(pr.first, pr.second);
+    return pr.first;
+  }
+  pane_storage_.emplace_back((size_t)n_acc_ * id_cap_ * sizeof(unsigned long long));
+  auto* blk = pane_storage_.back().as<unsigned long long>();
+  init_block(blk, id_cap_);
+  return blk;
+}
+
+void WindowAggOp::release_block(unsigned long long* blk) {
+  if (!blk) return;
+  free_panes_.emplace_back(blk, std::min<uint64_t>(id_cap_, (uint64_t)n_keys_host_ + 1));
+}
+
+// Doubles the dense id space: id_keys, every live pane block and the slot array are re-created.
+void WindowAggOp::grow_ids() {
+  const uint64_t old_cap = id_cap_;
+  const uint64_t new_cap = old_cap * 2;
+  const uint32_t n_valid = (uint32_t)std::min<uint64_t>(n_keys_host_, old_cap);
+  DevBuf new_keys(new_cap * sizeof(long long));
+  AB_CUDA(cudaMemcpyAsync(new_keys.p, id_keys_.p, (size_t)n_valid * sizeof(long long), cudaMemcpyDeviceToDevice, stream_));
+  // pane blocks
+  std::vector<DevBuf> new_storage;
+  id_cap_ = new_cap;
+  auto migrate = [&](unsigned long long* old_blk) -> unsigned long long* {
+    if (!old_blk) return nullptr;
+    new_storage.emplace_back((size_t)n_acc_ * new_cap * sizeof(unsigned long long));
+    auto* nb = new_storage.back().as<unsigned long long>();
+    init_block(nb, new_cap);
+    for (int a = 0; a < n_acc_; ++a)
+      AB_CUDA(cudaMemcpyAsync(nb + (size_t)a * new_cap, old_blk + (size_t)a * old_cap,
+                              (size_t)n_valid * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream_));
+    return nb;
+  };
+  for (auto& kv : panes_) {
+    kv.second.dev = migrate(kv.second.dev);
+    kv.second.frozen = migrate(kv.second.frozen);
+    if (kv.second.slot >= 0) h_pane_ptrs_[kv.second.slot] = kv.second.dev;
+  }
+  for (auto& kv : zombies_) {
+    kv.second.dev = migrate(kv.second.dev);
+    kv.second.frozen = migrate(kv.second.frozen);
+  }
+  running_ = migrate(running_);
+  AB_CUDA(cudaStreamSynchronize(stream_));
+  free_panes_.clear();
+  pane_storage_ = std::move(new_storage);
+  id_keys_ = std::move(new_keys);
+  ring_dirty_ = true;
+  if (keyed_) {
+    dict_cap_ = new_cap * 2;
+    AB_REQUIRE(dict_cap_ <= (1ull << 31), ARROYO_B200_RUNTIME, "key dictionary too large");
+    slots_.alloc(dict_cap_ * sizeof(Slot));
+    dict_init_kernel<<<num_sms_ * 4, 256, 0, stream_>>>(slots_.as<Slot>(), dict_cap_);
+    AB_CUDA(cudaGetLastError());
+    if (n_valid > 1) {
+      int blocks = (int)std::min<uint32_t>((n_valid + 255) / 256, (uint32_t)num_sms_ * 8);
+      dict_rebuild_kernel<<<blocks, 256, 0, stream_>>>(slots_.as<Slot>(), (uint32_t)(dict_cap_ - 1),
+                                                       id_keys_.as<long long>(), n_valid);
+      AB_CUDA(cudaGetLastError());
+    }
+    st_.kernel_launches += 2;
+  }
+  // ids handed out beyond the old capacity were never usable: clamp the device counter
+  unsigned int nk = n_valid;
+  AB_CUDA(cudaMemcpyAsync((char*)counters_.p + offsetof(Counters, n_keys), &nk, sizeof nk, cudaMemcpyHostToDevice, stream_));
+  n_keys_host_ = n_valid;
+  AB_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void WindowAggOp::ensure_pane(int64_t bin) {
+  if (panes_.count(bin)) return;
+  const uint64_t q = (uint64_t)bin / (uint64_t)slide_;
+  while (true) {
+    uint32_t slot = (uint32_t)q & (ring_ - 1);
+    if (h_pane_bins_[slot] == FREE_BIN) break;
+    // slot conflict: double the ring and re-place every live pane
+    AB_REQUIRE(ring_ * 2 <= MAX_RING, ARROYO_B200_RUNTIME,
+               "event-time spread of live panes exceeds the pane ring (4096 panes)");
+    ring_ *= 2;
+    std::fill(h_pane_bins_.begin(), h_pane_bins_.end(), FREE_BIN);
+    std::fill(h_pane_ptrs_.begin(), h_pane_ptrs_.end(), nullptr);
+    for (auto& kv : panes_) {
+      if (kv.second.slot < 0) continue;
+      uint32_t s = (uint32_t)((uint64_t)kv.first / (uint64_t)slide_) & (ring_ - 1);
+      kv.second.slot = (int)s;
+      h_pane_bins_[s] = kv.first;
+      h_pane_ptrs_[s] = kv.second.dev;
+    }
+    ring_dirty_ = true;
+  }
+  Pane p;
+  p.bin = bin;
+  p.dev = acquire_block();
+  p.slot = (int)((uint32_t)q & (ring_ - 1));
+  h_pane_bins_[p.slot] = bin;
+  h_pane_ptrs_[p.slot] = p.dev;
+  panes_[bin] = p;
+  ring_dirty_ = true;
+}
+
+void WindowAggOp::drop_pane(int64_t bin) {
+  auto it = panes_.find(bin);
+  if (it == panes_.end()) return;
+  Pane& p = it->second;
+  if (p.slot >= 0) {
+    h_pane_bins_[p.slot] = FREE_BIN;
+    h_pane_ptrs_[p.slot] = nullptr;
+    ring_dirty_ = true;
+  }
+  release_block(p.dev);
+  release_block(p.frozen);
+  panes_.erase(it);
+}
+
+void WindowAggOp::upload_ring() {
+  if (!ring_dirty_) return;
+  // pageable sources: the runtime stages them before returning, so the vectors may change afterwards
+  AB_CUDA(cudaMemcpyAsync(d_pane_bins_.p, h_pane_bins_.data(), ring_ * sizeof(long long), cudaMemcpyHostToDevice, stream_));
+  AB_CUDA(cudaMemcpyAsync(d_pane_ptrs_.p, h_pane_ptrs_.data(), ring_ * sizeof(void*), cudaMemcpyHostToDevice, stream_));
+  ring_dirty_ = false;
+}
+
+void WindowAggOp::poll_releases(bool wait) {
+  while (!releases_.empty()) {
+    PendingRelease& r = releases_.front();
+    if (wait) {
+      AB_CUDA(cudaEventSynchronize(r.ev));
+    } else {
+      cudaError_t e = cudaEventQuery(r.ev);
+      if (e == cudaErrorNotReady) break;
+      AB_CUDA(e);
+    }
+    if (r.arr.release) r.arr.release(&r.arr);
+    cudaEventDestroy(r.ev);
+    releases_.pop_front();
+  }
+}
+
+void WindowAggOp::add_segment(const long long* key, const long long* ts, const long long* const* vals, int64_t n) {
+  if (n <= 0) return;
+  if (!segs_.empty()) {
+    Segment& l = segs_.back();
+    bool contig = l.ts + l.n == ts && (!keyed_ || l.key + l.n == key);
+    for (int v = 0; v < n_vals_; ++v) contig = contig && (l.val[v] + l.n == vals[v]);
+    if (contig) {
+      l.n += n;
+      pending_rows_ += n;
+      return;
+    }
+  }
+  if ((int)segs_.size() == MAX_SEGS) launch_pending();
+  Segment s{};
+  s.key = key;
+  s.ts = ts;
+  for (int v = 0; v < n_vals_; ++v) s.val[v] = vals[v];
+  s.n = n;
+  segs_.push_back(s);
+  pending_rows_ += n;
+}
+
+void WindowAggOp::rotate_chunk() {
+  cur_chunk_ = (cur_chunk_ + 1) % NCHUNK;
+  cur_rows_ = 0;
+  // the launch that last read this chunk must have finished
+  AB_CUDA(cudaEventSynchronize(chunk_free_[cur_chunk_]));
+}
+
+void WindowAggOp::process_batch(uint32_t, uint32_t, ArrowArray* batch, const ArrowSchema* schema) {
+  set_device();
+  int64_t n = 0;
+  std::vector<InColumn> cols = import_batch(batch, schema, &n);
+  AB_REQUIRE((int)cols.size() == cfg.n_cols, ARROYO_B200_INVALID_ARGUMENT, "batch has the wrong number of columns");
+  if (keyed_) key_format_ = cols[key_col_].format;
+  for (int g = 0; g < n_aggs_; ++g)
+    if (agg_kind_[g] == ARROYO_B200_AGG_MIN_I64 || agg_kind_[g] == ARROYO_B200_AGG_MAX_I64 ||
+        agg_kind_[g] == ARROYO_B200_AGG_SUM_I64) {
+      const std::string& f = cols[cfg.aggs[g].input_col].format;
+      AB_REQUIRE(f != "g", ARROYO_B200_UNSUPPORTED, "float64 aggregate inputs are not supported");
+      if (agg_kind_[g] != ARROYO_B200_AGG_SUM_I64) agg_format_[g] = f;
+    }
+  poll_releases(false);
+  st_.rows_in += (uint64_t)n;
+  if (n > 0 && panes_.empty() && max_bin_seen_ == LLONG_MIN) {
+    // residency hint only (no semantics): make the first row's pane resident so a cold start does
+    // not have to go through the deferred path
+    int64_t b0 = bin_start((int64_t)cols[ts_col_].data[0], slide_);
+    if (b0 >= late_bin_) {
+      ensure_pane(b0);
+      max_bin_seen_ = b0;
+      lookahead();
+    }
+  }
+  const int n_used = 2 + n_vals_;
+  int64_t done = 0;
+  while (done < n) {
+    if (!chunk_[cur_chunk_].p) chunk_[cur_chunk_].alloc((size_t)n_used * chunk_rows_ * 8);
+    int64_t room = chunk_rows_ - cur_rows_;
+    if (room == 0) {
+      launch_pending();
+      rotate_chunk();
+      continue;
+    }
+    int64_t take = std::min(room, n - done);
+    long long* base = chunk_[cur_chunk_].as<long long>();
+    long long* d_key = base + 0 * chunk_rows_ + cur_rows_;
+    long long* d_ts = base + 1 * chunk_rows_ + cur_rows_;
+    const long long* d_vals[MAX_VALS];
+    if (keyed_)
+      AB_CUDA(cudaMemcpyAsync(d_key, cols[key_col_].data + done, (size_t)take * 8, cudaMemcpyHostToDevice, stream_));
+    AB_CUDA(cudaMemcpyAsync(d_ts, cols[ts_col_].data + done, (size_t)take * 8, cudaMemcpyHostToDevice, stream_));
+    for (int v = 0; v < n_vals_; ++v) {
+      long long* dv = base + (size_t)(2 + v) * chunk_rows_ + cur_rows_;
+      AB_CUDA(cudaMemcpyAsync(dv, cols[val_cols_[v]].data + done, (size_t)take * 8, cudaMemcpyHostToDevice, stream_));
+      d_vals[v] = dv;
+    }
+    st_.h2d_bytes += (uint64_t)take * 8 * (uint64_t)((keyed_ ? 1 : 0) + 1 + n_vals_);
+    add_segment(d_key, d_ts, d_vals, take);
+    pending_uses_chunk_ = true;
+    cur_rows_ += take;
+    done += take;
+  }
+  // ownership of the input moves to the library; release once the copies have completed
+  PendingRelease r;
+  AB_CUDA(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
+  AB_CUDA(cudaEventRecord(r.ev, stream_));
+  r.arr = *batch;
+  batch->release = nullptr;
+  releases_.push_back(r);
+  if (cur_rows_ == chunk_rows_) {
+    launch_pending();
+    rotate_chunk();
+  }
+}
+
+void WindowAggOp::process_device_batch(uint32_t, uint32_t, const uint64_t* cols, int32_t n_cols, int64_t n_rows) {
+  set_device();
+  AB_REQUIRE(n_cols == cfg.n_cols, ARROYO_B200_INVALID_ARGUMENT, "batch has the wrong number of columns");
+  if (n_rows <= 0) return;
+  st_.rows_in += (uint64_t)n_rows;
+  int64_t done = 0;
+  while (done < n_rows) {
+    int64_t take = std::min<int64_t>(n_rows - done, chunk_rows_ - pending_rows_);
+    const long long* vals[MAX_VALS];
+    for (int v = 0; v < n_vals_; ++v) vals[v] = (const long long*)cols[val_cols_[v]] + done;
+    add_segment(keyed_ ? (const long long*)cols[key_col_] + done : nullptr, (const long long*)cols[ts_col_] + done, vals,
+                take);
+    done += take;
+    if (pending_rows_ >= chunk_rows_) launch_pending();
+  }
+}
+
+void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk) {
+  // At most two launches (each <= chunk_rows_ rows) are ever in flight, so the deferred buffer
+  // (2 * chunk_rows_ rows) cannot overflow; as soon as a finished launch reports deferrals they are
+  // drained before anything else is queued.
+  while (in_flight_.size() >= 2) absorb(in_flight_.front());
+  if (!draining_ && have_counters_ && last_counters_.deferred > 0) {
+    while (!in_flight_.empty()) absorb(in_flight_.front());
+    drain_deferred();
+  }
+  const int li = next_launch_;
+  next_launch_ = (next_launch_ + 1) % NLAUNCH;
+  LaunchRec& L = launches_[li];
+  AB_REQUIRE(!L.in_flight, ARROYO_B200_RUNTIME, "launch record still in flight");
+  Segment* hs = h_segs_[li].as<Segment>();
+  long long tiles = 0;
+  uint64_t rows = 0;
+  for (size_t i = 0; i < segs_in.size(); ++i) {
+    hs[i] = segs_in[i];
+    hs[i].tile_start = tiles;
+    uintptr_t al = (uintptr_t)hs[i].ts;
+    if (keyed_) al |= (uintptr_t)hs[i].key;
+    for (int v = 0; v < n_vals_; ++v) al |= (uintptr_t)hs[i].val[v];
+    hs[i].vec_ok = (al & 15) == 0;
+    tiles += (hs[i].n + TILE - 1) / TILE;
+    rows += (uint64_t)hs[i].n;
+  }
+  AB_CUDA(cudaMemcpyAsync(d_segs_[li].p, hs, segs_in.size() * sizeof(Segment), cudaMemcpyHostToDevice, stream_));
+  upload_ring();
+  AB_CUDA(cudaMemsetAsync(touched_.p, 0, ring_ * sizeof(unsigned int), stream_));
+  if (!defer_[defer_cur_][0].p) {
+    for (int c = 0; c < 2 + n_vals_; ++c) defer_[defer_cur_][c].alloc(defer_cap_ * 8);
+  }
+
+  IngestParams p{};
+  p.segs = d_segs_[li].as<Segment>();
+  p.n_segs = (int)segs_in.size();
+  p.keyed = keyed_ ? 1 : 0;
+  p.n_tiles = tiles;
+  p.dict.slots = slots_.as<Slot>();
+  p.dict.id_keys = id_keys_.as<long long>();
+  p.dict.n_keys = (unsigned int*)((char*)counters_.p + offsetof(Counters, n_keys));
+  p.dict.mask = keyed_ ? (uint32_t)(dict_cap_ - 1) : 0;
+  p.dict.id_cap = (uint32_t)std::min<uint64_t>(id_cap_, 0xFFFFFFF0ull);
+  p.slide_div = FastDivU64::make((uint64_t)slide_);
+  p.slide = slide_;
+  p.late_bin = late_bin_;
+  p.ring_mask = ring_ - 1;
+  p.n_acc = n_acc_;
+  p.pane_bins = d_pane_bins_.as<long long>();
+  p.pane_ptrs = d_pane_ptrs_.as<unsigned long long*>();
+  p.id_cap = id_cap_;
+  for (int a = 0; a < n_acc_; ++a) {
+    p.acc_kind[a] = acc_kind_[a];
+    p.acc_val[a] = acc_val_[a];
+  }
+  p.counters = counters_.as<Counters>();
+  p.touched = touched_.as<unsigned int>();
+  p.d_key = defer_[defer_cur_][0].as<long long>();
+  p.d_ts = defer_[defer_cur_][1].as<long long>();
+  for (int v = 0; v < n_vals_; ++v) p.d_val[v] = defer_[defer_cur_][2 + v].as<long long>();
+  p.defer_cap = defer_cap_;
+
+  int grid = (int)std::min<long long>(tiles, (long long)num_sms_ * 8);
+  if (grid < 1) grid = 1;
+  if (profile_) AB_CUDA(cudaEventRecord(L.t0, stream_));
+  switch (n_vals_) {
+    case 0: ingest_kernel<0><<<grid, THREADS, 0, stream_>>>(p); break;
+    case 1: ingest_kernel<1><<<grid, THREADS, 0, stream_>>>(p); break;
+    case 2: ingest_kernel<2><<<grid, THREADS, 0, stream_>>>(p); break;
+    case 3: ingest_kernel<3><<<grid, THREADS, 0, stream_>>>(p); break;
+    default: ingest_kernel<4><<<grid, THREADS, 0, stream_>>>(p); break;
+  }
+  AB_CUDA(cudaGetLastError());
+  if (profile_) AB_CUDA(cudaEventRecord(L.t1, stream_));
+  ++st_.kernel_launches;
+  ++st_.ingest_launches;
+  AB_CUDA(cudaMemcpyAsync(L.h_counters, counters_.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream_));
+  AB_CUDA(cudaMemcpyAsync(L.h_touched, touched_.p, ring_ * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream_));
+  AB_CUDA(cudaEventRecord(L.done, stream_));
+  if (chunk >= 0) AB_CUDA(cudaEventRecord(chunk_free_[chunk], stream_));
+  L.rows = rows;
+  L.in_flight = true;
+  L.chunk = chunk;
+  in_flight_.push_back(li);
+}
+
+void WindowAggOp::launch_pending() {
+  if (segs_.empty()) return;
+  std::vector<Segment> segs;
+  segs.swap(segs_);
+  pending_rows_ = 0;
+  int chunk = pending_uses_chunk_ ? cur_chunk_ : -1;
+  pending_uses_chunk_ = false;
+  launch_segments(segs, chunk);
+}
+
+void WindowAggOp::touch(int64_t bin) {
+  if (sliding_) sliding_planner_->touch(bin);
+  else tumbling_->touch(bin);
+}
+
+// Waits for one launch and folds its bookkeeping into the host state machine.
+void WindowAggOp::absorb(int li) {
+  LaunchRec& L = launches_[li];
+  AB_REQUIRE(L.in_flight, ARROYO_B200_RUNTIME, "absorb of an idle launch");
+  AB_CUDA(cudaEventSynchronize(L.done));
+  L.in_flight = false;
+  AB_REQUIRE(!in_flight_.empty() && in_flight_.front() == li, ARROYO_B200_RUNTIME, "launch order violated");
+  in_flight_.pop_front();
+  if (profile_) {
+    float ms = 0;
+    AB_CUDA(cudaEventElapsedTime(&ms, L.t0, L.t1));
+    st_.ingest_ms += ms;
+    st_.ingest_rows_timed += L.rows;
+  }
+  const Counters& c = *L.h_counters;
+  last_counters_ = c;
+  have_counters_ = true;
+  n_keys_host_ = (uint32_t)std::min<uint64_t>(c.n_keys, id_cap_);
+  if (c.max_bin != LLONG_MIN) max_bin_seen_ = std::max<int64_t>(max_bin_seen_, c.max_bin);
+  for (uint32_t s = 0; s < ring_; ++s) {
+    if (L.h_touched[s]) {
+      AB_REQUIRE(h_pane_bins_[s] != FREE_BIN, ARROYO_B200_RUNTIME, "touched a free ring slot");
+      touch(h_pane_bins_[s]);
+    }
+  }
+  if (c.lost) throw Error(ARROYO_B200_RUNTIME, "deferred-row buffer overflowed; rows were lost");
+  lookahead();
+}
+
+// Keep panes resident a little ahead of the newest bin seen so in-order streams never defer.
+void WindowAggOp::lookahead() {
+  if (max_bin_seen_ == LLONG_MIN) return;
+  for (int k = 0; k <= 2; ++k) {
+    int64_t b = max_bin_seen_ + (int64_t)k * slide_;
+    if (b >= late_bin_ && !panes_.count(b)) {
+      // only if the slot is free: never grow the ring speculatively
+      uint32_t slot = (uint32_t)((uint64_t)b / (uint64_t)slide_) & (ring_ - 1);
+      if (h_pane_bins_[slot] == FREE_BIN) ensure_pane(b);
+    }
+  }
+}
+
+void WindowAggOp::sync_all() {
+  while (!in_flight_.empty()) absorb(in_flight_.front());
+  drain_deferred();
+}
+
+// Slow path: rows the kernel could not place (pane not resident, dictionary full).  Grows what is
+// missing and re-ingests them; loops until nothing is deferred.
+void WindowAggOp::drain_deferred() {
+  struct Guard {
+    bool& f;
+    explicit Guard(bool& x) : f(x) { f = true; }
+    ~Guard() { f = false; }
+  } guard(draining_);
+  for (int iter = 0; iter < 64; ++iter) {
+    if (!have_counters_ || last_counters_.deferred == 0) return;
+    AB_REQUIRE(in_flight_.empty(), ARROYO_B200_RUNTIME, "drain with launches in flight");
+    const uint64_t n = last_counters_.deferred;
+    AB_REQUIRE(n <= defer_cap_, ARROYO_B200_RUNTIME, "deferred overflow");
+    st_.rows_deferred += n;
+    // which panes do the deferred rows need?
+    std::vector<long long> ts(n);
+    AB_CUDA(cudaMemcpyAsync(ts.data(), defer_[defer_cur_][1].p, n * 8, cudaMemcpyDeviceToHost, stream_));
+    AB_CUDA(cudaStreamSynchronize(stream_));
+    std::set<int64_t> bins;
+    for (uint64_t i = 0; i < n; ++i) {
+      int64_t b = (int64_t)((uint64_t)ts[i] / (uint64_t)slide_ * (uint64_t)slide_);
+      if (b >= late_bin_) bins.insert(b);
+    }
+    for (int64_t b : bins) ensure_pane(b);
+    // dictionary pressure: grow when half full (keeps probes short) or when ids ran out
+    while (keyed_ && (uint64_t)last_counters_.n_keys + n / 2 >= id_cap_ / 2 + id_cap_ / 4) {
+      n_keys_host_ = (uint32_t)std::min<uint64_t>(last_counters_.n_keys, id_cap_);
+      grow_ids();
+      last_counters_.n_keys = n_keys_host_;
+    }
+    // re-ingest from the filled set while new deferrals go to the other set
+    const int full = defer_cur_;
+    defer_cur_ ^= 1;
+    unsigned long long zero = 0;
+    AB_CUDA(cudaMemcpyAsync((char*)counters_.p + offsetof(Counters, deferred), &zero, sizeof zero,
+                            cudaMemcpyHostToDevice, stream_));
+    Segment s{};
+    s.key = defer_[full][0].as<long long>();
+    s.ts = defer_[full][1].as<long long>();
+    for (int v = 0; v < n_vals_; ++v) s.val[v] = defer_[full][2 + v].as<long long>();
+    s.n = (long long)n;
+    // deferred rows were already counted (late rows among them are counted when re-ingested)
+    launch_segments({s}, -1);
+    while (!in_flight_.empty()) absorb(in_flight_.front());
+  }
+  throw Error(ARROYO_B200_RUNTIME, "deferred rows did not converge");
+}
+
+void WindowAggOp::flush() {
+  set_device();
+  launch_pending();
+  sync_all();
+  poll_releases(true);
+}
+
+WindowAggOp::OutSet* WindowAggOp::out_set(size_t i, uint64_t cap) {
+  while (out_sets_.size() <= i) out_sets_.emplace_back(new OutSet());
+  OutSet* os = out_sets_[i].get();
+  if (os->cap < cap) {
+    uint64_t c = std::max<uint64_t>(cap, 1024);
+    os->key.alloc(c * 8);
+    os->wstart.alloc(c * 8);
+    os->wend.alloc(c * 8);
+    os->ts.alloc(c * 8);
+    for (int g = 0; g < n_aggs_; ++g) os->agg[g].alloc(c * 8);
+    os->cap = c;
+    for (int a = 0; a < MAX_ACC; ++a) os->state[a].release();
+  }
+  return os;
+}
+
+// Runs the merge/emit kernel; returns the number of output rows (synchronises on the count).
+int64_t WindowAggOp::run_emit(const std::vector<const unsigned long long*>& blocks, int n_add, bool use_running,
+                              bool partial, int64_t wstart, int64_t wend, int64_t ts, OutSet* os) {
+  AB_REQUIRE(blocks.size() <= (size_t)MAX_MERGE, ARROYO_B200_RUNTIME, "too many panes in one window");
+  const uint32_t n_ids = n_keys_host_;
+  if (!blocks.empty())
+    AB_CUDA(cudaMemcpyAsync(d_emit_panes_.p, blocks.data(), blocks.size() * sizeof(void*), cudaMemcpyHostToDevice, stream_));
+  AB_CUDA(cudaMemsetAsync(d_out_count_.p, 0, sizeof(unsigned int), stream_));
+  EmitParams p{};
+  p.panes = d_emit_panes_.as<const unsigned long long*>();
+  p.n_panes = (int)blocks.size();
+  p.n_acc = n_acc_;
+  p.id_cap = id_cap_;
+  p.n_ids = n_ids;
+  p.keyed = keyed_ ? 1 : 0;
+  for (int a = 0; a < n_acc_; ++a) p.acc_kind[a] = acc_kind_[a];
+  p.n_aggs = n_aggs_;
+  for (int g = 0; g < n_aggs_; ++g) {
+    p.agg_kind[g] = agg_kind_[g];
+    p.agg_acc[g] = agg_acc_[g];
+    p.out_agg[g] = os->agg[g].as<unsigned long long>();
+  }
+  p.id_keys = id_keys_.as<long long>();
+  p.out_key = os->key.as<long long>();
+  const bool proj = cfg.final_projection != 0 && !partial;
+  p.out_wstart = proj ? os->wstart.as<long long>() : nullptr;
+  p.out_wend = proj ? os->wend.as<long long>() : nullptr;
+  p.out_ts = os->ts.as<long long>();
+  p.wstart = wstart;
+  p.wend = wend;
+  p.ts = ts;
+  p.out_count = d_out_count_.as<unsigned int>();
+  p.running = use_running ? running_ : nullptr;
+  p.n_add = n_add;
+  p.partial = partial ? 1 : 0;
+  if (partial) {
+    for (int a = 0; a < n_acc_; ++a) {
+      if (!os->state[a].p) os->state[a].alloc(os->cap * 8);
+      p.out_state[a] = os->state[a].as<unsigned long long>();
+    }
+  }
+  const uint32_t n_iter = (n_ids + EMIT_THREADS - 1) / EMIT_THREADS;
+  int grid = (int)std::min<uint32_t>(std::max<uint32_t>(n_iter, 1u), (uint32_t)num_sms_ * 8);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (profile_) {
+    AB_CUDA(cudaEventCreate(&e0));
+    AB_CUDA(cudaEventCreate(&e1));
+    AB_CUDA(cudaEventRecord(e0, stream_));
+  }
+  emit_kernel<<<grid, EMIT_THREADS, 0, stream_>>>(p);
+  AB_CUDA(cudaGetLastError());
+  if (profile_) {
+    AB_CUDA(cudaEventRecord(e1, stream_));
+    emit_events_.emplace_back(e0, e1);
+    st_.emit_rows_timed += n_ids;
+  }
+  ++st_.kernel_launches;
+  ++st_.emit_launches;
+  AB_CUDA(cudaMemcpyAsync(h_out_count_.p, d_out_count_.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream_));
+  AB_CUDA(cudaStreamSynchronize(stream_));
+  return (int64_t)*h_out_count_.as<unsigned int>();
+}
+
+static void* d2h_column(const void* dev, int64_t n, cudaStream_t s, uint64_t* bytes) {
+  void* h = PinnedPool::get().alloc((size_t)std::max<int64_t>(n, 1) * 8);
+  if (n > 0) AB_CUDA(cudaMemcpyAsync(h, dev, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+  *bytes += (uint64_t)n * 8;
+  return h;
+}
+
+// Output batch in the operator's out_schema order: aggregate output columns [key?, aggs...] with the
+// window struct inserted at window_index, then _timestamp (planner extension/aggregate.rs:306-389).
+void WindowAggOp::export_window(OutSet* os, int64_t n, BatchesPriv* out_host) {
+  std::vector<OutColumn> cols;
+  if (keyed_) {
+    OutColumn k;
+    k.name = "key";
+    k.format = key_format_;
+    k.data = d2h_column(os->key.p, n, stream_, &st_.d2h_bytes);
+    cols.push_back(k);
+  }
+  for (int g = 0; g < n_aggs_; ++g) {
+    OutColumn a;
+    a.name = "agg" + std::to_string(g);
+    a.format = agg_format_[g];
+    a.data = d2h_column(os->agg[g].p, n, stream_, &st_.d2h_bytes);
+    cols.push_back(a);
+  }
+  if (cfg.final_projection) {
+    OutColumn w;
+    w.name = "window";
+    w.format = "+s";
+    OutColumn ws, we;
+    ws.name = "start";
+    ws.format = "tsn:";
+    ws.data = d2h_column(os->wstart.p, n, stream_, &st_.d2h_bytes);
+    we.name = "end";
+    we.format = "tsn:";
+    we.data = d2h_column(os->wend.p, n, stream_, &st_.d2h_bytes);
+    w.children = {ws, we};
+    int wi = std::min<int>(std::max<int>(cfg.window_index, 0), (int)cols.size());
+    cols.insert(cols.begin() + wi, w);
+  }
+  OutColumn t;
+  t.name = "_timestamp";
+  t.format = "tsn:";
+  t.data = d2h_column(os->ts.p, n, stream_, &st_.d2h_bytes);
+  cols.push_back(t);
+  AB_CUDA(cudaStreamSynchronize(stream_));
+  out_host->arrays.emplace_back();
+  out_host->schemas.emplace_back();
+  export_batch(cols, n, &out_host->arrays.back(), &out_host->schemas.back());
+}
+
+// Partial-state batch in `partial_schema`: [key?, state cols..., _timestamp = pane start]
+// (arroyo-planner/src/builder.rs:163-192).  COUNT -> count; SUM -> sum; AVG -> (count u64, sum f64).
+void WindowAggOp::export_partial(OutSet* os, int64_t n, BatchesPriv* out) {
+  std::vector<OutColumn> cols;
+  if (keyed_) {
+    OutColumn k;
+    k.name = "key";
+    k.format = key_format_;
+    k.data = d2h_column(os->key.p, n, stream_, &st_.d2h_bytes);
+    cols.push_back(k);
+  }
+  for (int g = 0; g < n_aggs_; ++g) {
+    auto add = [&](const char* nm, const char* fmt, const void* dev) {
+      OutColumn c;
+      c.name = std::string("agg") + std::to_string(g) + nm;
+      c.format = fmt;
+      c.data = d2h_column(dev, n, stream_, &st_.d2h_bytes);
+      cols.push_back(c);
+    };
+    switch (agg_kind_[g]) {
+      case ARROYO_B200_AGG_COUNT_STAR: add("[count]", "l", os->state[0].p); break;
+      case ARROYO_B200_AGG_SUM_I64: add("[sum]", "l", os->state[agg_acc_[g]].p); break;
+      case ARROYO_B200_AGG_AVG_I64:
+        add("[count]", "L", os->state[0].p);
+        add("[sum]", "g", os->state[agg_acc_[g]].p);
+        break;
+      case ARROYO_B200_AGG_MIN_I64: add("[min]", agg_format_[g].c_str(), os->state[agg_acc_[g]].p); break;
+      case ARROYO_B200_AGG_MAX_I64: add("[max]", agg_format_[g].c_str(), os->state[agg_acc_[g]].p); break;
+    }
+  }
+  OutColumn t;
+  t.name = "_timestamp";
+  t.format = "tsn:";
+  t.data = d2h_column(os->ts.p, n, stream_, &st_.d2h_bytes);
+  cols.push_back(t);
+  AB_CUDA(cudaStreamSynchronize(stream_));
+  out->arrays.emplace_back();
+  out->schemas.emplace_back();
+  export_batch(cols, n, &out->arrays.back(), &out->schemas.back());
+}
+
+void WindowAggOp::emit_window(int64_t a, int64_t b, size_t out_index, BatchesPriv* out_host,
+                              std::vector<ArroyoB200DeviceBatch>* out_dev) {
+  // panes of the window = window store (tier) restricted to [a, b)   (sliding :161-168)
+  std::vector<int64_t> members;
+  for (auto it = panes_.lower_bound(a); it != panes_.end() && it->first < b; ++it)
+    if (it->second.in_tier) members.push_back(it->first);
+  std::vector<const unsigned long long*> blocks;
+  int n_add = 0;
+  bool use_running = false;
+  if (running_mode_) {
+    if (!running_) {
+      running_ = acquire_block();
+      // W starts from all-zero (identity of the invertible accumulators)
+    }
+    std::set<int64_t> target(members.begin(), members.end());
+    std::vector<const unsigned long long*> add, sub;
+    for (int64_t m : target)
+      if (!in_running_.count(m)) {
+        const Pane& p = panes_.at(m);
+        add.push_back(p.dev);
+        if (p.frozen) add.push_back(p.frozen);
+      }
+    for (int64_t m : in_running_)
+      if (!target.count(m)) {
+        auto zi = zombies_.find(m);
+        const Pane& p = zi != zombies_.end() ? zi->second : panes_.at(m);
+        sub.push_back(p.dev);
+        if (p.frozen) sub.push_back(p.frozen);
+      }
+    blocks = add;
+    n_add = (int)add.size();
+    blocks.insert(blocks.end(), sub.begin(), sub.end());
+    in_running_ = target;
+    use_running = true;
+    if (target.empty()) {
+      // nothing in the window: W is all zero by construction; nothing to emit
+      if (blocks.empty()) return;
+    }
+  } else {
+    for (int64_t m : members) {
+      const Pane& p = panes_.at(m);
+      blocks.push_back(p.dev);
+      if (p.frozen) blocks.push_back(p.frozen);
+    }
+    if (blocks.empty()) return;  // aggregate over an empty input has no groups
+  }
+  OutSet* os = out_set(out_dev ? out_index : 0, std::max<uint64_t>(n_keys_host_, 1));
+  const int64_t ts = cfg.final_projection ? b - 1 : a;
+  int64_t n = run_emit(blocks, n_add, use_running, false, a, b, ts, os);
+  // blocks of panes that had already left the store have now been subtracted from W
+  for (auto& z : zombies_) {
+    release_block(z.second.dev);
+    release_block(z.second.frozen);
+  }
+  zombies_.clear();
+  if (n == 0) return;
+  st_.rows_out += (uint64_t)n;
+  ++st_.windows_out;
+  if (out_host) {
+    export_window(os, n, out_host);
+  } else {
+    ArroyoB200DeviceBatch d{};
+    d.n_rows = n;
+    int c = 0;
+    std::vector<uint64_t> cols;
+    if (keyed_) cols.push_back((uint64_t)os->key.p);
+    for (int g = 0; g < n_aggs_; ++g) cols.push_back((uint64_t)os->agg[g].p);
+    if (cfg.final_projection) {
+      int wi = std::min<int>(std::max<int>(cfg.window_index, 0), (int)cols.size());
+      cols.insert(cols.begin() + wi, (uint64_t)os->wend.p);
+      cols.insert(cols.begin() + wi, (uint64_t)os->wstart.p);
+    }
+    cols.push_back((uint64_t)os->ts.p);
+    for (uint64_t v : cols) d.cols[c++] = v;
+    d.n_cols = c;
+    out_dev->push_back(d);
+  }
+}
+
+void WindowAggOp::handle_watermark(int64_t wm, BatchesPriv* out_host, std::vector<ArroyoB200DeviceBatch>* out_dev) {
+  set_device();
+  launch_pending();
+  sync_all();
+  poll_releases(false);
+  std::vector<PlanStep> steps;
+  if (sliding_) sliding_planner_->watermark(wm, steps);
+  else tumbling_->watermark(wm, steps);
+  size_t out_index = 0;
+  for (const PlanStep& s : steps) {
+    switch (s.kind) {
+      case PlanStep::JOIN: {
+        auto it = panes_.find(s.a);
+        AB_REQUIRE(it != panes_.end(), ARROYO_B200_RUNTIME, "closing a pane that is not resident");
+        it->second.in_tier = true;
+        break;
+      }
+      case PlanStep::EMIT: {
+        if (!sliding_) {
+          // tumbling: the popped bin is the whole window (tumbling :340-385)
+          auto it = panes_.find(s.c);
+          AB_REQUIRE(it != panes_.end(), ARROYO_B200_RUNTIME, "emitting a pane that is not resident");
+          it->second.in_tier = true;
+          emit_window(s.a, s.b, out_index++, out_host, out_dev);
+          drop_pane(s.c);
+        } else {
+          emit_window(s.a, s.b, out_index++, out_host, out_dev);
+        }
+        break;
+      }
+      case PlanStep::LEAVE: {
+        if (running_mode_ && in_running_.count(s.a)) {
+          // W still contains this pane: keep its blocks until the next emit subtracts them in the
+          // same pass that adds the entering pane (one kernel per slide)
+          auto it = panes_.find(s.a);
+          Pane z = it->second;
+          it->second.dev = nullptr;
+          it->second.frozen = nullptr;
+          z.slot = -1;
+          zombies_[s.a] = z;
+        }
+        drop_pane(s.a);
+        break;
+      }
+      default:
+        break;
+    }
+  }
+  // bins below bin(watermark) are late from now on (tumbling :282-291, sliding :631-633)
+  int64_t new_late = bin_start(wm, slide_);
+  if (new_late > late_bin_) late_bin_ = new_late;
+  // panes that were made resident ahead of time but can no longer receive rows
+  std::vector<int64_t> dead;
+  const auto& execs = sliding_ ? sliding_planner_->execs() : tumbling_->execs();
+  for (auto& kv : panes_)
+    if (kv.first < late_bin_ && !kv.second.in_tier && !execs.count(kv.first)) dead.push_back(kv.first);
+  for (int64_t b : dead) drop_pane(b);
+  // make the pane at the watermark resident so the next rows do not defer
+  if (wm != INT64_MAX && max_bin_seen_ != LLONG_MIN) {
+    if (!panes_.count(late_bin_)) {
+      uint32_t slot = (uint32_t)((uint64_t)late_bin_ / (uint64_t)slide_) & (ring_ - 1);
+      if (h_pane_bins_[slot] == FREE_BIN && late_bin_ <= max_bin_seen_ + 2 * slide_) ensure_pane(late_bin_);
+    }
+  }
+  if (profile_) {
+    for (auto& e : emit_events_) {
+      float ms = 0;
+      AB_CUDA(cudaEventElapsedTime(&ms, e.first, e.second));
+      st_.emit_ms += ms;
+      cudaEventDestroy(e.first);
+      cudaEventDestroy(e.second);
+    }
+    emit_events_.clear();
+  }
+}
+
+void WindowAggOp::handle_checkpoint(int64_t wm, BatchesPriv* out) {
+  set_device();
+  launch_pending();
+  sync_all();
+  std::vector<PlanStep> steps;
+  if (sliding_) sliding_planner_->checkpoint(wm != INT64_MIN, wm, steps);
+  else tumbling_->checkpoint(steps);
+  for (const PlanStep& s : steps) {
+    if (s.kind != PlanStep::CHECKPOINT_PANE) continue;
+    auto it = panes_.find(s.a);
+    AB_REQUIRE(it != panes_.end(), ARROYO_B200_RUNTIME, "checkpointing a pane that is not resident");
+    Pane& p = it->second;
+    OutSet* os = out_set(0, std::max<uint64_t>(n_keys_host_, 1));
+    // the rows received since the last drain = the active block (the reference drains the running
+    // Partial exec and writes its output, sliding :705-733)
+    int64_t n = run_emit({p.dev}, 1, false, true, 0, 0, s.a, os);
+    if (n > 0) export_partial(os, n, out);
+    // fold into the frozen block so the next checkpoint writes only new rows
+    if (!p.frozen) p.frozen = acquire_block();
+    FoldParams fp{};
+    fp.active = p.dev;
+    fp.frozen = p.frozen;
+    fp.id_cap = id_cap_;
+    fp.n_ids = n_keys_host_;
+    fp.n_acc = n_acc_;
+    for (int a = 0; a < n_acc_; ++a) fp.acc_kind[a] = acc_kind_[a];
+    int grid = (int)std::min<uint32_t>((n_keys_host_ + 255) / 256, (uint32_t)num_sms_ * 8);
+    fold_kernel<<<std::max(grid, 1), 256, 0, stream_>>>(fp);
+    AB_CUDA(cudaGetLastError());
+    ++st_.kernel_launches;
+  }
+  AB_CUDA(cudaStreamSynchronize(stream_));
+}
+
+// Restore (tumbling :228-248, sliding :556-595): partial batches go back into pane blocks.
+void WindowAggOp::on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, int64_t watermark, int64_t table_min) {
+  set_device();
+  const bool has_wm = watermark != INT64_MIN;
+  if (has_wm) late_bin_ = std::max<int64_t>(late_bin_, bin_start(watermark, slide_));
+  if (sliding_) sliding_planner_->restore_begin(has_wm, watermark);
+  // expected partial layout
+  int n_state_cols = 0;
+  for (int g = 0; g < n_aggs_; ++g) n_state_cols += agg_kind_[g] == ARROYO_B200_AGG_AVG_I64 ? 2 : 1;
+  const int expect_cols = (keyed_ ? 1 : 0) + n_state_cols + 1;
+  std::vector<DevBuf> keep;
+  for (int64_t bi = 0; bi < n; ++bi) {
+    int64_t rows = 0;
+    std::vector<InColumn> cols = import_batch(&state[bi], &schemas[bi], &rows);
+    AB_REQUIRE((int)cols.size() == expect_cols, ARROYO_B200_INVALID_ARGUMENT,
+               "state batch does not match the partial schema");
+    if (rows == 0) continue;
+    if (keyed_) key_format_ = cols[0].format;
+    const int64_t ts = (int64_t)cols.back().data[0];
+    const int64_t bin = bin_start(ts, slide_);
+    ensure_pane(bin);
+    Pane& p = panes_.at(bin);
+    if (!p.frozen) p.frozen = acquire_block();
+    bool to_tier = false;
+    if (sliding_) to_tier = sliding_planner_->restore_pane(ts);
+    else tumbling_->restore(bin);
+    if (to_tier) p.in_tier = true;
+    // upload columns
+    PartialParams pp{};
+    pp.n = rows;
+    pp.keyed = keyed_ ? 1 : 0;
+    pp.n_acc = n_acc_;
+    for (int a = 0; a < n_acc_; ++a) pp.acc_kind[a] = acc_kind_[a];
+    auto up = [&](const uint64_t* h) -> const unsigned long long* {
+      keep.emplace_back((size_t)rows * 8);
+      AB_CUDA(cudaMemcpyAsync(keep.back().p, h, (size_t)rows * 8, cudaMemcpyHostToDevice, stream_));
+      return keep.back().as<unsigned long long>();
+    };
+    int ci = 0;
+    if (keyed_) pp.key = (const long long*)up(cols[ci++].data);
+    for (int a = 0; a < MAX_ACC; ++a) pp.state[a] = nullptr;
+    for (int g = 0; g < n_aggs_; ++g) {
+      switch (agg_kind_[g]) {
+        case ARROYO_B200_AGG_COUNT_STAR: {
+          const unsigned long long* c = up(cols[ci++].data);
+          if (!pp.state[0]) pp.state[0] = c;
+          break;
+        }
+        case ARROYO_B200_AGG_AVG_I64: {
+          const unsigned long long* c = up(cols[ci++].data);
+          if (!pp.state[0]) pp.state[0] = c;
+          pp.state[agg_acc_[g]] = up(cols[ci++].data);
+          break;
+        }
+        default:
+          pp.state[agg_acc_[g]] = up(cols[ci++].data);
+          break;
+      }
+    }
+    AB_REQUIRE(pp.state[0] != nullptr, ARROYO_B200_UNSUPPORTED,
+               "restore needs a COUNT(*) or AVG state column to recover per-key row counts");
+    while (keyed_ && (uint64_t)n_keys_host_ + (uint64_t)rows >= id_cap_ / 2) {
+      AB_CUDA(cudaStreamSynchronize(stream_));
+      grow_ids();
+    }
+    pp.dict.slots = slots_.as<Slot>();
+    pp.dict.id_keys = id_keys_.as<long long>();
+    pp.dict.n_keys = (unsigned int*)((char*)counters_.p + offsetof(Counters, n_keys));
+    pp.dict.mask = keyed_ ? (uint32_t)(dict_cap_ - 1) : 0;
+    pp.dict.id_cap = (uint32_t)id_cap_;
+    pp.pane = panes_.at(bin).frozen;
+    pp.id_cap = id_cap_;
+    pp.counters = counters_.as<Counters>();
+    int grid = (int)std::min<int64_t>((rows + 255) / 256, (int64_t)num_sms_ * 8);
+    ingest_partial_kernel<<<std::max(grid, 1), 256, 0, stream_>>>(pp);
+    AB_CUDA(cudaGetLastError());
+    ++st_.kernel_launches;
+    Counters c{};
+    AB_CUDA(cudaMemcpyAsync(&c, counters_.p, sizeof c, cudaMemcpyDeviceToHost, stream_));
+    AB_CUDA(cudaStreamSynchronize(stream_));
+    AB_REQUIRE(c.lost == 0, ARROYO_B200_RUNTIME, "dictionary overflow during restore");
+    n_keys_host_ = (uint32_t)std::min<uint64_t>(c.n_keys, id_cap_);
+    last_counters_ = c;
+    max_bin_seen_ = std::max<int64_t>(max_bin_seen_, bin);
+    if (state[bi].release) state[bi].release(&state[bi]);
+  }
+  if (sliding_) sliding_planner_->restore_end(table_min != INT64_MIN, table_min);
+  AB_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void WindowAggOp::stats(ArroyoB200Stats* out) {
+  st_.n_keys = keyed_ ? (n_keys_host_ > 0 ? n_keys_host_ - 1 : 0) : 0;
+  st_.rows_late = last_counters_.late_rows;
+  *out = st_;
+}
+
+}  // namespace
+
+OpBase* make_window_agg_op(const ArroyoB200OpConfig& cfg) { return new WindowAggOp(cfg); }
+
+}  // namespace ab

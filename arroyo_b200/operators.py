@@ -1,0 +1,256 @@
+"""Host-side mirror of the reference's window operators over the C ABI.
+
+Class and method names follow arroyo-worker/src/arrow/{tumbling,sliding}_aggregating_window.rs and
+the ArrowOperator trait (arroyo-operator/src/operator.rs:1143-1257): name(), tables(), on_start(ctx),
+process_batch(batch, ctx, collector), handle_watermark(watermark, ctx, collector),
+handle_checkpoint(barrier, ctx, collector), on_close(final_message, ctx, collector).
+Batches are pyarrow RecordBatches crossing the boundary through the Arrow C Data Interface."""
+import ctypes as C
+from typing import List, Optional
+
+import pyarrow as pa
+
+from . import ffi
+from .context import Collector, OperatorContext, clamp_watermark
+
+TIMESTAMP = "_timestamp"
+_AGG_KINDS = {"count": ffi.AGG_COUNT_STAR, "sum": ffi.AGG_SUM_I64, "avg": ffi.AGG_AVG_I64,
+              "min": ffi.AGG_MIN_I64, "max": ffi.AGG_MAX_I64}
+
+
+def _check(lib, handle, status):
+    if status == ffi.OK:
+        return
+    msg = lib.arroyo_b200_op_last_error(handle)
+    msg = msg.decode() if msg else ""
+    if status == ffi.UNSUPPORTED:
+        raise ffi.UnsupportedPlan(status, msg)
+    raise ffi.ArroyoB200Error(status, msg)
+
+
+def export_batch(batch: pa.RecordBatch):
+    arr, sch = ffi.ArrowArray(), ffi.ArrowSchema()
+    batch._export_to_c(C.addressof(arr), C.addressof(sch))
+    return arr, sch
+
+
+def import_batches(lib, out: ffi.Batches) -> List[pa.RecordBatch]:
+    res = []
+    try:
+        for i in range(out.n_batches):
+            res.append(pa.RecordBatch._import_from_c(C.addressof(out.arrays[i]), C.addressof(out.schemas[i])))
+    finally:
+        lib.arroyo_b200_release_batches(C.byref(out))
+    return res
+
+
+class _NativeOperator:
+    """Owns one ArroyoB200Op handle."""
+
+    kind = 0
+
+    def __init__(self, device: int = 0, stream: int = 0, flags: int = 0, expected_keys: int = 0,
+                 task_index: int = 0, parallelism: int = 1):
+        self._lib = ffi.load()
+        self._h = C.c_void_p()
+        self._device = device
+        self._stream = stream
+        self._flags = flags
+        self._expected_keys = expected_keys
+        self._task_index = task_index
+        self._parallelism = parallelism
+
+    def _create(self, cfg: ffi.OpConfig):
+        cfg.device = self._device
+        cfg.stream = self._stream
+        cfg.flags = self._flags
+        cfg.expected_keys = self._expected_keys
+        cfg.task_index = self._task_index
+        cfg.parallelism = self._parallelism
+        err = C.create_string_buffer(1024)
+        st = self._lib.arroyo_b200_op_create(C.byref(cfg), C.byref(self._h), err, 1024)
+        if st != ffi.OK:
+            msg = err.value.decode()
+            if st == ffi.UNSUPPORTED:
+                raise ffi.UnsupportedPlan(st, msg)
+            raise ffi.ArroyoB200Error(st, msg)
+
+    @property
+    def created(self) -> bool:
+        return bool(self._h)
+
+    def close(self):
+        if self._h:
+            self._lib.arroyo_b200_op_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def flush(self):
+        _check(self._lib, self._h, self._lib.arroyo_b200_op_flush(self._h))
+
+    def stats(self) -> dict:
+        s = ffi.Stats()
+        _check(self._lib, self._h, self._lib.arroyo_b200_op_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+
+class _WindowAggregate(_NativeOperator):
+    def __init__(self, config, input_schema: Optional[pa.Schema] = None, **kw):
+        super().__init__(**kw)
+        self.config = config
+        self._names: Optional[List[str]] = None
+        if input_schema is not None:
+            self._build(input_schema.names)
+
+    # -- construction (OperatorConstructor::with_config) -------------------------------------
+    def _build(self, names: List[str]):
+        c = self.config
+        cfg = ffi.OpConfig()
+        cfg.kind = self.kind
+        cfg.width_ns = int(c.width)
+        cfg.slide_ns = int(getattr(c, "slide", 0) or 0)
+        cfg.n_cols = len(names)
+        cfg.timestamp_col = names.index(TIMESTAMP)
+        if len(c.key_names) > 1:
+            raise ffi.UnsupportedPlan(ffi.UNSUPPORTED, "more than one group-by key column")
+        cfg.n_key_cols = len(c.key_names)
+        cfg.key_col = names.index(c.key_names[0]) if c.key_names else 0
+        if len(c.aggs) > ffi.MAX_AGGS:
+            raise ffi.UnsupportedPlan(ffi.UNSUPPORTED, "too many aggregates")
+        cfg.n_aggs = len(c.aggs)
+        for i, a in enumerate(c.aggs):
+            if a.kind not in _AGG_KINDS:
+                raise ffi.UnsupportedPlan(ffi.UNSUPPORTED, f"aggregate {a.kind}")
+            cfg.aggs[i].kind = _AGG_KINDS[a.kind]
+            cfg.aggs[i].input_col = names.index(a.col) if a.col is not None else 0
+        cfg.final_projection = 1 if c.final_projection else 0
+        cfg.window_index = int(c.window_index)
+        self._create(cfg)
+        self._names = list(names)
+
+    def output_names(self) -> List[str]:
+        c = self.config
+        names = list(c.key_names) + [a.name for a in c.aggs]
+        if c.final_projection:
+            names.insert(min(max(c.window_index, 0), len(names)), "window")
+        return names + [TIMESTAMP]
+
+    def partial_names(self) -> List[str]:
+        c = self.config
+        names = list(c.key_names)
+        for a in c.aggs:
+            if a.kind == "avg":
+                names += [f"{a.name}[count]", f"{a.name}[sum]"]
+            else:
+                names.append(f"{a.name}[{a.kind}]")
+        return names + [TIMESTAMP]
+
+    # -- ArrowOperator ---------------------------------------------------------------------
+    def tables(self):
+        # table "t": partial aggregates, retention = width (tumbling :469-482, sliding :739-752)
+        return {"t": int(self.config.width)}
+
+    def on_start(self, ctx: OperatorContext):
+        wm = ctx.last_present_watermark()
+        table = ctx.table("t", int(self.config.width))
+        batches = [b for _, b in table.all_batches_for_watermark(wm)]
+        if not batches and not self.created:
+            return
+        if not self.created:
+            raise ffi.ArroyoB200Error(ffi.INVALID_ARGUMENT, "restore needs input_schema at construction")
+        n = len(batches)
+        arrs = (ffi.ArrowArray * max(n, 1))()
+        schs = (ffi.ArrowSchema * max(n, 1))()
+        for i, b in enumerate(batches):
+            b._export_to_c(C.addressof(arrs[i]), C.addressof(schs[i]))
+        mt = table.get_min_time()
+        st = self._lib.arroyo_b200_op_on_start(
+            self._h, arrs, schs, n, ffi.INT64_MIN if wm is None else clamp_watermark(wm),
+            ffi.INT64_MIN if mt is None else mt)
+        _check(self._lib, self._h, st)
+
+    def process_batch(self, batch: pa.RecordBatch, ctx: OperatorContext, collector: Collector):
+        if not self.created:
+            self._build(batch.schema.names)
+        arr, sch = export_batch(batch)
+        st = self._lib.arroyo_b200_op_process_batch(self._h, 0, 1, C.byref(arr), C.byref(sch))
+        if st != ffi.OK:
+            # on error the caller keeps ownership of the exported structs
+            for s in (arr, sch):
+                if s.release:
+                    C.CFUNCTYPE(None, C.c_void_p)(s.release)(C.addressof(s))
+        _check(self._lib, self._h, st)
+        # the schema struct stays ours
+        if sch.release:
+            C.CFUNCTYPE(None, C.c_void_p)(sch.release)(C.addressof(sch))
+
+    def process_device_batch(self, cols: List[int], n_rows: int):
+        """`cols` = device pointers (ints), one per input column."""
+        arr = (C.c_uint64 * len(cols))(*cols)
+        st = self._lib.arroyo_b200_op_process_device_batch(self._h, 0, 1, arr, len(cols), n_rows)
+        _check(self._lib, self._h, st)
+
+    def process_device_batches(self, cols_flat, n_rows, n_cols: int):
+        """A run of device batches in one FFI call; `cols_flat`/`n_rows` are prebuilt ctypes arrays
+        ((c_uint64 * (n_batches * n_cols)), (c_int64 * n_batches))."""
+        st = self._lib.arroyo_b200_op_process_device_batches(self._h, 0, 1, cols_flat, n_cols, n_rows, len(n_rows))
+        _check(self._lib, self._h, st)
+
+    def handle_watermark(self, watermark, ctx: OperatorContext, collector: Collector):
+        wm = ctx.last_present_watermark()
+        if wm is None or not self.created:
+            return None if self.kind == ffi.SLIDING_AGGREGATE and wm is None else watermark
+        out = ffi.Batches()
+        st = self._lib.arroyo_b200_op_handle_watermark(self._h, clamp_watermark(wm), C.byref(out))
+        _check(self._lib, self._h, st)
+        names = self.output_names()
+        for b in import_batches(self._lib, out):
+            collector.collect(pa.RecordBatch.from_arrays(b.columns, names=names))
+        return watermark
+
+    def handle_watermark_device(self, wm: int, max_out: int = 64):
+        """Emission left on the device: list of (n_rows, [device pointers])."""
+        out = (ffi.DeviceBatch * max_out)()
+        n = C.c_int64(0)
+        st = self._lib.arroyo_b200_op_handle_watermark_device(self._h, clamp_watermark(wm), out, max_out, C.byref(n))
+        _check(self._lib, self._h, st)
+        return [(out[i].n_rows, [out[i].cols[c] for c in range(out[i].n_cols)]) for i in range(n.value)]
+
+    def handle_checkpoint(self, barrier, ctx: OperatorContext, collector: Collector):
+        if not self.created:
+            return
+        w = ctx.watermark()
+        wm = ffi.INT64_MIN if (w is None or w == "idle") else clamp_watermark(w)
+        out = ffi.Batches()
+        st = self._lib.arroyo_b200_op_handle_checkpoint(self._h, wm, C.byref(out))
+        _check(self._lib, self._h, st)
+        table = ctx.table("t", int(self.config.width))
+        names = self.partial_names()
+        for b in import_batches(self._lib, out):
+            b = pa.RecordBatch.from_arrays(b.columns, names=names)
+            table.insert(int(b.column(len(names) - 1)[0].value), b)
+
+    def on_close(self, final_message, ctx: OperatorContext, collector: Collector):
+        if self.created:
+            self.flush()
+
+
+class TumblingAggregatingWindowFunc(_WindowAggregate):
+    """arroyo-worker/src/arrow/tumbling_aggregating_window.rs"""
+    kind = ffi.TUMBLING_AGGREGATE
+
+    def name(self):
+        return "tumbling_window"
+
+
+class SlidingAggregatingWindowFunc(_WindowAggregate):
+    """arroyo-worker/src/arrow/sliding_aggregating_window.rs"""
+    kind = ffi.SLIDING_AGGREGATE
+
+    def name(self):
+        return "sliding_window"

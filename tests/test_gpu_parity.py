@@ -1,0 +1,293 @@
+"""GPU parity: the CUDA operators (through the C ABI) against the oracle on seeded synthetic inputs.
+Bit-exact for keys, counts, window bounds, i64 SUM/MIN/MAX; 1e-6 relative for f64 AVG (north star)."""
+import numpy as np
+import pytest
+
+from oracle import arroyo_oracle as O
+from tests.golden_cases import multiset
+
+pytestmark = pytest.mark.gpu
+
+S = 1_000_000_000
+T0 = 1_700_000_000 * S
+
+
+@pytest.fixture(scope="module")
+def G():
+    from tests import gpu_ops as g
+    return g
+
+
+def gen_stream(rng, n_rows, n_keys, rate_per_s, disorder=50, key_dist="uniform", batch=4096, vmax=10**8):
+    """Nexmark-bid shaped rows: event time advances by 1/rate, permuted inside groups of `disorder`
+    events (nexmark/operator.rs:515-521); keys uniform or 75 % on a hot id."""
+    idx = np.arange(n_rows, dtype=np.int64)
+    if disorder > 1:
+        g = (idx // disorder) * disorder
+        perm = np.concatenate([rng.permutation(min(disorder, n_rows - s)) + s for s in range(0, n_rows, disorder)])
+        idx = perm
+        del g
+    ts = T0 + (idx * (S // rate_per_s)).astype(np.int64)
+    if key_dist == "uniform":
+        keys = rng.integers(0, n_keys, n_rows, dtype=np.int64) * 7919 - 13
+    else:
+        hot = rng.random(n_rows) < 0.75
+        keys = np.where(hot, 42, rng.integers(0, n_keys, n_rows, dtype=np.int64))
+    vals = rng.integers(-vmax, vmax, n_rows, dtype=np.int64)
+    cols = {"key": keys, "value": vals, O.TIMESTAMP: ts}
+    return O.source_batches(cols, batch)
+
+
+def run_both(G, make_oracle, make_gpu, batches, delay_ns=S):
+    want = O.run_single_input(make_oracle(), batches, delay_ns).batches
+    gop = make_gpu()
+    got = G.run_single_input(gop, batches, delay_ns).batches
+    return want, got, gop
+
+
+def rows_of(batches, float_cols=()):
+    rows = []
+    for b in batches:
+        for r in b.rows():
+            rows.append(r)
+    return rows
+
+
+def assert_same(want, got, float_cols=()):
+    """Exact multiset equality on the non-float columns; floats compared at 1e-6 relative after
+    aligning rows by the exact columns."""
+    def split(rows):
+        ex, fl = [], []
+        for r in rows:
+            ex.append(tuple(sorted((k, v) for k, v in r.items() if k not in float_cols)))
+            fl.append(tuple(r[c] for c in float_cols))
+        return ex, fl
+    we, wf = split(rows_of(want))
+    ge, gf = split(rows_of(got))
+    assert len(we) == len(ge)
+    wo = sorted(range(len(we)), key=lambda i: we[i])
+    go = sorted(range(len(ge)), key=lambda i: ge[i])
+    assert [we[i] for i in wo] == [ge[i] for i in go]
+    if float_cols:
+        a = np.array([wf[i] for i in wo], dtype=np.float64)
+        b = np.array([gf[i] for i in go], dtype=np.float64)
+        np.testing.assert_allclose(b, a, rtol=1e-6, atol=0)
+    # windows are emitted in ascending order
+    starts = [int(b["window_start"][0]) for b in got if "window_start" in b.cols]
+    assert starts == sorted(starts)
+
+
+SUM_AVG = [O.Agg("sum", "value", "sum"), O.Agg("avg", "value", "avg"), O.Agg("count", None, "count")]
+
+
+def test_tumbling_count_10k_keys(G):
+    """BASELINE config 2 shape: tumbling 1 s COUNT(*) GROUP BY key, 10 K keys."""
+    rng = np.random.default_rng(42)
+    batches = gen_stream(rng, 200_000, 10_000, rate_per_s=40_000)
+    cfg = O.WindowAggConfig(width=S, key_names=["key"], aggs=[O.Agg("count", None, "count")], window_index=1)
+    want, got, _ = run_both(G, lambda: O.TumblingAggregatingWindowFunc(cfg),
+                            lambda: G.TumblingAggregatingWindowFunc(cfg), batches)
+    assert len(want) >= 4
+    assert_same(want, got)
+
+
+@pytest.mark.parametrize("flags_name", ["running", "remerge"])
+@pytest.mark.parametrize("dist", ["uniform", "hot"])
+def test_sliding_sum_avg(G, flags_name, dist):
+    """BASELINE config 3 shape (reduced): hop(1 s, 10 s) SUM/AVG GROUP BY key."""
+    from arroyo_b200 import ffi
+    rng = np.random.default_rng(7)
+    batches = gen_stream(rng, 300_000, 5_000, rate_per_s=20_000, key_dist=dist)
+    cfg = O.WindowAggConfig(width=10 * S, slide=S, key_names=["key"], aggs=SUM_AVG, window_index=1)
+    flags = ffi.FLAG_REMERGE_ONLY if flags_name == "remerge" else 0
+    want, got, gop = run_both(G, lambda: O.SlidingAggregatingWindowFunc(cfg),
+                              lambda: G.SlidingAggregatingWindowFunc(cfg, flags=flags), batches)
+    assert len(want) >= 20
+    assert_same(want, got, float_cols=("avg",))
+    st = gop.stats()
+    assert st["rows_in"] == 300_000 and st["kernel_launches"] > 0
+
+
+def test_sliding_min_max_unkeyed_and_keyed(G):
+    rng = np.random.default_rng(11)
+    batches = gen_stream(rng, 50_000, 300, rate_per_s=5_000, batch=1000)
+    aggs = [O.Agg("min", "value", "mn"), O.Agg("max", "value", "mx"), O.Agg("count", None, "n")]
+    for keys in ([], ["key"]):
+        cfg = O.WindowAggConfig(width=6 * S, slide=2 * S, key_names=keys, aggs=aggs, window_index=len(keys))
+        want, got, _ = run_both(G, lambda: O.SlidingAggregatingWindowFunc(cfg),
+                                lambda: G.SlidingAggregatingWindowFunc(cfg), batches)
+        assert_same(want, got)
+
+
+def test_late_rows_are_dropped_like_the_reference(G):
+    """Heavy disorder with a tight watermark: whole late bins are dropped (tumbling :282-291)."""
+    rng = np.random.default_rng(5)
+    batches = gen_stream(rng, 120_000, 1_000, rate_per_s=10_000, disorder=30_000, batch=2048)
+    cfg = O.WindowAggConfig(width=S, key_names=["key"], aggs=SUM_AVG, window_index=1)
+    want, got, gop = run_both(G, lambda: O.TumblingAggregatingWindowFunc(cfg),
+                              lambda: G.TumblingAggregatingWindowFunc(cfg), batches, delay_ns=0)
+    assert_same(want, got, float_cols=("avg",))
+    assert gop.stats()["rows_late"] > 0
+
+
+def test_edge_cases_empty_ragged_offsets_sentinel_wraparound(G):
+    """Empty batches, 1-row batches, odd sizes (vector tail path), sliced batches (non-zero Arrow
+    offset), the key equal to the dictionary's empty sentinel, i64 SUM wrap-around."""
+    import pyarrow as pa
+    rng = np.random.default_rng(1)
+    I64MIN, I64MAX = -(1 << 63), (1 << 63) - 1
+    n = 10_007
+    keys = rng.integers(0, 50, n, dtype=np.int64)
+    keys[::97] = I64MIN
+    keys[5::89] = I64MAX
+    vals = rng.integers(-10, 10, n, dtype=np.int64)
+    vals[:40] = I64MAX  # forces wrapping sums
+    ts = T0 + np.sort(rng.integers(0, 5 * S, n)).astype(np.int64)
+    cols = {"key": keys, "value": vals, O.TIMESTAMP: ts}
+    sizes = [0, 1, 1, 2, 3, 1023, 1024, 1025, 0, 4097, 1, 2048]
+    batches, s = [], 0
+    for z in sizes:
+        batches.append(O.Batch({k: v[s:s + z] for k, v in cols.items()}))
+        s += z
+    batches.append(O.Batch({k: v[s:] for k, v in cols.items()}))
+    batches = [b for b in batches]
+    cfg = O.WindowAggConfig(width=S, key_names=["key"], aggs=[O.Agg("sum", "value", "sum"), O.Agg("count", None, "n")],
+                            window_index=0)
+    # oracle: empty batches are legal no-ops
+    oop = O.TumblingAggregatingWindowFunc(cfg)
+    want = O.run_single_input(oop, [b for b in batches if b.num_rows], S).batches
+    gop = G.TumblingAggregatingWindowFunc(cfg)
+    # feed the GPU operator sliced views of one big batch: every slice has a non-zero offset
+    big = G.to_arrow(O.Batch(cols))
+    ctx, out = O.OperatorContext(1), O.Collector()
+    gen = O.WatermarkGenerator(S)
+    s = 0
+    from tests.gpu_ops import _CollectAdapter
+    for b in batches:
+        z = b.num_rows
+        gop.op.process_batch(big.slice(s, z), ctx, _CollectAdapter(out))
+        s += z
+        if z:
+            wm = gen.process_batch(b[O.TIMESTAMP])
+            if wm is not None:
+                ctx.watermarks.set(0, wm)
+                gop.handle_watermark(wm, ctx, out)
+    ctx.watermarks.set(0, O.FINAL_WATERMARK)
+    gop.handle_watermark(O.FINAL_WATERMARK, ctx, out)
+    assert_same(want, out.batches)
+    assert any((b["key"] == I64MIN).any() for b in out.batches)
+
+
+def test_dictionary_growth_and_far_future_rows(G):
+    """expected_keys far too small (forces id-space growth + rehash) and rows far ahead of the pane ring
+    (forces the deferred path and ring growth)."""
+    rng = np.random.default_rng(9)
+    batches = gen_stream(rng, 150_000, 60_000, rate_per_s=50_000, batch=8192)
+    # one straggler batch 500 panes in the future, delivered early
+    fut = O.Batch({"key": np.arange(100, dtype=np.int64), "value": np.ones(100, dtype=np.int64),
+                   O.TIMESTAMP: np.full(100, T0 + 500 * S, dtype=np.int64)})
+    batches.insert(3, fut)
+    cfg = O.WindowAggConfig(width=4 * S, slide=S, key_names=["key"], aggs=SUM_AVG, window_index=1)
+    want, got, gop = run_both(G, lambda: O.SlidingAggregatingWindowFunc(cfg),
+                              lambda: G.SlidingAggregatingWindowFunc(cfg, expected_keys=256), batches)
+    assert_same(want, got, float_cols=("avg",))
+    st = gop.stats()
+    assert st["rows_deferred"] > 0 and st["n_keys"] >= 50_000
+
+
+def test_unsupported_inputs_fail_loudly(G):
+    import pyarrow as pa
+    from arroyo_b200 import ffi, operators as native
+    import arroyo_b200 as ab
+    cfg = ab.WindowAggConfig(width=S, key_names=["key"], aggs=[ab.Agg("sum", "value", "sum")])
+    op = native.TumblingAggregatingWindowFunc(cfg)
+    ts = pa.array(np.array([T0, T0 + 1], dtype=np.int64)).cast(pa.timestamp("ns"))
+    ctx, col = ab.OperatorContext(1), ab.Collector()
+    with pytest.raises(ffi.UnsupportedPlan):  # NULL value
+        op.process_batch(pa.RecordBatch.from_arrays([pa.array([1, 2]), pa.array([1, None], type=pa.int64()), ts],
+                                                    names=["key", "value", "_timestamp"]), ctx, col)
+    with pytest.raises(ffi.UnsupportedPlan):  # string key
+        op.process_batch(pa.RecordBatch.from_arrays([pa.array(["a", "b"]), pa.array([1, 2]), ts],
+                                                    names=["key", "value", "_timestamp"]), ctx, col)
+    with pytest.raises(ffi.UnsupportedPlan):  # instant window
+        native.TumblingAggregatingWindowFunc(ab.WindowAggConfig(width=0, aggs=[ab.Agg("count", None, "n")]),
+                                             input_schema=pa.schema([("_timestamp", pa.timestamp("ns"))]))
+
+
+def test_checkpoint_restore_round_trip(G):
+    """handle_checkpoint -> partial-state batches (partial_schema) -> on_start of a fresh operator
+    continues to the same final output as an uninterrupted oracle run (sliding :693-737, :556-595)."""
+    import arroyo_b200 as ab
+    from arroyo_b200 import operators as native
+    from tests.gpu_ops import from_arrow, to_arrow
+    rng = np.random.default_rng(21)
+    batches = gen_stream(rng, 80_000, 2_000, rate_per_s=10_000, batch=4000)
+    cfg = O.WindowAggConfig(width=4 * S, slide=S, key_names=["key"], aggs=SUM_AVG, window_index=1)
+    want = O.run_single_input(O.SlidingAggregatingWindowFunc(cfg), batches, S).batches
+
+    schema = to_arrow(batches[0]).schema
+    ctx = ab.OperatorContext(1)
+    out = ab.Collector()
+    gen = ab.WatermarkGenerator(S)
+    op = native.SlidingAggregatingWindowFunc(cfg, input_schema=schema)
+    half = len(batches) // 2
+    for i, b in enumerate(batches):
+        if i == half:
+            # checkpoint twice (the second must only carry rows since the first), then restart
+            op.handle_checkpoint(None, ctx, out)
+            op.process_batch(to_arrow(b), ctx, out)
+            op.handle_checkpoint(None, ctx, out)
+            op.close()
+            op = native.SlidingAggregatingWindowFunc(cfg, input_schema=schema)
+            op.on_start(ctx)
+        else:
+            op.process_batch(to_arrow(b), ctx, out)
+        wm = gen.on_batch(int(b[O.TIMESTAMP].min()), int(b[O.TIMESTAMP].max()))
+        if wm is not None:
+            ctx.watermarks.set(0, wm)
+            op.handle_watermark(wm, ctx, out)
+    ctx.watermarks.set(0, ab.FINAL_WATERMARK)
+    op.handle_watermark(ab.FINAL_WATERMARK, ctx, out)
+    got = [from_arrow(b) for b in out.batches]
+    assert_same(want, got, float_cols=("avg",))
+
+
+def test_device_resident_batches_and_device_output(G):
+    """process_device_batch / handle_watermark_device (the chaining + benchmark path) give the same
+    windows as the host path."""
+    import torch
+    import arroyo_b200 as ab
+    from arroyo_b200 import operators as native
+    rng = np.random.default_rng(3)
+    batches = gen_stream(rng, 100_000, 3_000, rate_per_s=10_000, batch=65_536)
+    cfg = O.WindowAggConfig(width=3 * S, slide=S, key_names=["key"], aggs=SUM_AVG, window_index=1)
+    want = O.run_single_input(O.SlidingAggregatingWindowFunc(cfg), batches, S).batches
+    import pyarrow as pa
+    schema = pa.schema([("key", pa.int64()), ("value", pa.int64()), ("_timestamp", pa.timestamp("ns"))])
+    op = native.SlidingAggregatingWindowFunc(cfg, input_schema=schema)
+    gen = ab.WatermarkGenerator(S)
+    keep = []
+    got = []
+
+    class _Ptr:
+        def __init__(self, ptr, n, typestr):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+    def collect(wins):
+        names = ["key", "window_start", "window_end", "sum", "avg", "count", O.TIMESTAMP]
+        for n, cols in wins:
+            host = {}
+            for name, ptr in zip(names, cols):
+                t = torch.as_tensor(_Ptr(ptr, n, "<f8" if name == "avg" else "<i8"), device="cuda")
+                host[name] = t.cpu().numpy().copy()
+            got.append(O.Batch(host))
+
+    for b in batches:
+        dev = [torch.from_numpy(np.ascontiguousarray(b[c])).cuda() for c in ("key", "value", O.TIMESTAMP)]
+        keep.append(dev)
+        op.process_device_batch([t.data_ptr() for t in dev], b.num_rows)
+        wm = gen.on_batch(int(b[O.TIMESTAMP].min()), int(b[O.TIMESTAMP].max()))
+        if wm is not None:
+            collect(op.handle_watermark_device(wm))
+    collect(op.handle_watermark_device(ab.FINAL_WATERMARK))
+    assert_same(want, got, float_cols=("avg",))
