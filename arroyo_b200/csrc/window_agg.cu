@@ -905,9 +905,9 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
   AB_CUDA(cudaMemcpyAsync(counters_.p, &init, sizeof init, cudaMemcpyHostToDevice, stream_));
   last_counters_ = init;
 
+  // dense id space: the expected key count + 12.5 % head-room (grown by doubling when it runs out)
   uint64_t want = c.expected_keys ? c.expected_keys : (1ull << 16);
-  uint64_t cap = 1024;
-  while (cap < 2 * want + 2) cap <<= 1;
+  uint64_t cap = ((want + want / 8 + 2 + 1023) / 1024) * 1024;
   if (!keyed_) cap = 1024;
   alloc_dictionary(cap);
 
@@ -966,13 +966,20 @@ WindowAggOp::~WindowAggOp() {
   if (own_stream_ && stream_) cudaStreamDestroy(stream_);
 }
 
+// slot count: power of two >= 1.75 x ids (load factor <= 0.57; 0.5 at the expected key count)
+static uint64_t slots_for(uint64_t ids) {
+  uint64_t c = 1024;
+  while (c * 4 < ids * 7) c <<= 1;
+  return c;
+}
+
 void WindowAggOp::alloc_dictionary(uint64_t id_cap) {
   id_cap_ = id_cap;
   id_keys_.alloc(id_cap_ * sizeof(long long));
   long long k0 = EMPTY_KEY;
   AB_CUDA(cudaMemcpyAsync(id_keys_.p, &k0, sizeof k0, cudaMemcpyHostToDevice, stream_));
   if (keyed_) {
-    dict_cap_ = id_cap_ * 2;
+    dict_cap_ = slots_for(id_cap_);
     AB_REQUIRE(dict_cap_ <= (1ull << 31), ARROYO_B200_RUNTIME, "key dictionary too large");
     slots_.alloc(dict_cap_ * sizeof(Slot));
     dict_init_kernel<<<num_sms_ * 4, 256, 0, stream_>>>(slots_.as<Slot>(), dict_cap_);
@@ -1049,7 +1056,7 @@ void WindowAggOp::grow_ids() {
   id_keys_ = std::move(new_keys);
   ring_dirty_ = true;
   if (keyed_) {
-    dict_cap_ = new_cap * 2;
+    dict_cap_ = slots_for(new_cap);
     AB_REQUIRE(dict_cap_ <= (1ull << 31), ARROYO_B200_RUNTIME, "key dictionary too large");
     slots_.alloc(dict_cap_ * sizeof(Slot));
     dict_init_kernel<<<num_sms_ * 4, 256, 0, stream_>>>(slots_.as<Slot>(), dict_cap_);

@@ -1,0 +1,476 @@
+#!/usr/bin/env python
+"""bench.py -- rows/sec of the sliding-window SUM/AVG hot path (BASELINE.json config 3) on N B200s.
+
+Workload (`config.workload`): hop(1 s slide, 10 s width) SUM(value), AVG(value), COUNT(*) GROUP BY key,
+1 048 576 distinct i64 keys (uniform), Arrow-shaped batches of 65 536 rows [key i64, value i64,
+_timestamp ts-ns], 16 Mi rows per 1-s pane (256 batches), Nexmark bounded disorder (groups of 50),
+watermark = batch-min timestamp - 1 s at most once per second of event time.
+
+A *step* = one pane: 256 batches through process_batch + the watermark that closes one pane and emits
+one 10-s window (<= 1 Mi rows x 6 columns).
+
+  value     device-resident: inputs already in HBM, windows left in HBM (process_device_batches /
+            handle_watermark_device of the C ABI); timed with CUDA events on the operator's stream
+  e2e       the same through the reference-facing call with HOST buffers: pinned Arrow batches in via
+            arroyo_b200_op_process_batch, emitted windows out as host Arrow batches
+  roofline  ingest kernel: 24 algorithmic bytes per input row / its CUDA-event time, against the
+            measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline / --impl reference
+            the C restatement of the reference's algorithm (oracle/window_oracle.c, "port": the Rust
+            reference cannot be built here) on all host cores, key-partitioned like the reference
+
+Multi-GPU (N > 1): one process per GPU; every rank ingests its own shard of the stream (seed 42 + rank),
+hash-partitions it on the device, exchanges the partitions with an NCCL all-to-all and aggregates the
+keys it owns (weak scaling: per-GPU input fixed).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S = 1_000_000_000
+T0 = 1_700_000_000 * S
+BATCH_ROWS = 65_536
+WIDTH, SLIDE, WM_DELAY = 10 * S, 1 * S, 1 * S
+KEY_MULT = 0x9E3779B97F4A7C15  # odd => bijection on u64: keys are scattered over the i64 range
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=12)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--keys", type=int, default=1 << 20)
+    ap.add_argument("--rows-per-pane", type=int, default=1 << 24)
+    ap.add_argument("--dist", default="uniform", choices=["uniform", "hot"])
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--remerge", action="store_true", help="re-merge all panes per slide (reference algorithm)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic Nexmark-bid-shaped input (generated on the device; seed 42 + rank)
+# ------------------------------------------------------------------------------------------------
+def make_generator(torch, device, rows_per_pane, n_keys, dist, seed):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    i = torch.arange(rows_per_pane, device=device, dtype=torch.int64)
+    # event i of a pane happens at i * (1 s / rows_per_pane); events are permuted inside groups of 50
+    # (nexmark/operator.rs:515-521 out_of_order_group_size)
+    grp = (i // 50).to(torch.float64) + torch.rand(rows_per_pane, device=device, generator=g, dtype=torch.float64) * 0.999
+    order = torch.argsort(grp)
+    offs = (order * S) // rows_per_pane
+    del grp, order, i
+
+    def pane(p):
+        ts = offs + (T0 + p * SLIDE)
+        if dist == "uniform":
+            kid = torch.randint(0, n_keys, (rows_per_pane,), device=device, generator=g, dtype=torch.int64)
+        else:  # 75 % of the rows on the current hot id (nexmark hot_bidders_ratio), the rest uniform
+            kid = torch.randint(0, n_keys, (rows_per_pane,), device=device, generator=g, dtype=torch.int64)
+            hot = torch.rand(rows_per_pane, device=device, generator=g) < 0.75
+            kid = torch.where(hot, torch.full_like(kid, (p // 4) % n_keys), kid)
+        key = kid * torch.tensor(KEY_MULT - (1 << 64), dtype=torch.int64, device=device)  # wrapping multiply
+        # price = floor(10^U(0,6) * 100)  (nexmark/operator.rs:643-645)
+        u = torch.rand(rows_per_pane, device=device, generator=g, dtype=torch.float64) * 6.0
+        val = torch.floor(torch.pow(10.0, u) * 100.0).to(torch.int64)
+        return key, val, ts
+
+    return pane
+
+
+def watermark_schedule(ts_min_max):
+    """Simulates the WatermarkGenerator over the per-batch (min, max) timestamps: returns, per batch,
+    the watermark it broadcasts after the batch (or None)."""
+    from arroyo_b200 import WatermarkGenerator
+    gen = WatermarkGenerator(WM_DELAY)
+    return [gen.on_batch(mn, mx) for mn, mx in ts_min_max]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def ncu_traffic():
+    """dram bytes per ingest launch from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "ingest_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+def window_config():
+    import arroyo_b200 as ab
+    return ab.WindowAggConfig(width=WIDTH, slide=SLIDE, key_names=["key"],
+                              aggs=[ab.Agg("sum", "value", "sum"), ab.Agg("avg", "value", "avg"),
+                                    ab.Agg("count", None, "count")], window_index=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the C restatement on the host cores
+# ------------------------------------------------------------------------------------------------
+def host_panes(torch, gen_pane, n):
+    out = []
+    for p in range(n):
+        k, v, t = gen_pane(p)
+        out.append((k.cpu().numpy(), v.cpu().numpy(), t.cpu().numpy()))
+    return out
+
+
+def run_cpu(torch, args, device, budget_s, warm_panes, timed_panes):
+    """Times the oracle port on all host cores over `timed_panes` panes after `warm_panes` warm-up panes.
+    If a full pane is too slow for the budget the timed panes carry fewer rows (bounded sample)."""
+    from oracle import c_oracle
+    threads = c_oracle.load().oracle_max_threads()
+    threads = max(1, min(threads, 1024))
+    rows = args.rows_per_pane
+    gen_pane = make_generator(torch, device, rows, args.keys, args.dist, 42)
+    r = c_oracle.Runner(threads, WIDTH, SLIDE, WM_DELAY, BATCH_ROWS)
+    k, v, t = [x.cpu().numpy() for x in gen_pane(0)]
+    dt0 = r.feed(k, v, t)
+    # bounded sample: shrink the per-pane row count so the rest of the run fits the budget
+    est = dt0 * 2.5  # later panes also pay a 10-pane merge per slide
+    total = warm_panes + timed_panes - 1
+    frac = 1.0
+    if est * total > budget_s:
+        frac = max(budget_s / (est * total), 1.0 / 64)
+    n_rows = max(BATCH_ROWS, int(rows * frac) // BATCH_ROWS * BATCH_ROWS)
+    step_s = []
+    for p in range(1, warm_panes + timed_panes):
+        k, v, t = gen_pane(p)
+        if n_rows < rows:
+            # every BATCH_ROWS-row batch keeps its shape; whole batches are dropped uniformly over the pane
+            nb = rows // BATCH_ROWS
+            keep = torch.linspace(0, nb - 1, n_rows // BATCH_ROWS, device=device).round().to(torch.int64)
+            idx = (keep[:, None] * BATCH_ROWS + torch.arange(BATCH_ROWS, device=device)[None, :]).reshape(-1)
+            k, v, t = k[idx], v[idx], t[idx]
+        dt = r.feed(k.cpu().numpy(), v.cpu().numpy(), t.cpu().numpy())
+        if p >= warm_panes:
+            step_s.append(dt)
+    res = r.result()
+    r.close()
+    secs = sum(step_s)
+    return {"rows_per_s": n_rows * len(step_s) / secs, "threads": threads, "rows_per_step": n_rows,
+            "steps": len(step_s), "ms_per_step": 1e3 * secs / len(step_s), "rows_out": int(res.rows_out),
+            "sample": (f"{len(step_s)} panes x {n_rows} rows ({n_rows // BATCH_ROWS} batches of {BATCH_ROWS}) after "
+                       f"{warm_panes} warm-up panes, {args.keys} keys, hop(1s,10s); "
+                       f"{threads} key-partitioned single-threaded subtasks")}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def build_batch_lists(torch, panes, rows_per_pane):
+    """Per pane: prebuilt ctypes arrays of (key, value, ts) device pointers per 65 536-row batch, plus the
+    watermark each batch triggers."""
+    nb = rows_per_pane // BATCH_ROWS
+    plans = []
+    mins, maxs = [], []
+    for (k, v, t) in panes:
+        tb = t.view(nb, BATCH_ROWS)
+        mins.append(tb.amin(dim=1))
+        maxs.append(tb.amax(dim=1))
+    mins = torch.stack(mins).cpu().numpy().reshape(-1).tolist()
+    maxs = torch.stack(maxs).cpu().numpy().reshape(-1).tolist()
+    wms = watermark_schedule(list(zip(mins, maxs)))
+    for pi, (k, v, t) in enumerate(panes):
+        segs = []  # (cols ctypes array, rows ctypes array, watermark after the run or None)
+        start = 0
+        for b in range(nb):
+            wm = wms[pi * nb + b]
+            if wm is not None or b == nb - 1:
+                n = b - start + 1
+                cols = (C.c_uint64 * (3 * n))()
+                rows = (C.c_int64 * n)()
+                for j in range(n):
+                    off = (start + j) * BATCH_ROWS * 8
+                    cols[3 * j + 0] = k.data_ptr() + off
+                    cols[3 * j + 1] = v.data_ptr() + off
+                    cols[3 * j + 2] = t.data_ptr() + off
+                    rows[j] = BATCH_ROWS
+                segs.append((cols, rows, wm))
+                start = b + 1
+        plans.append(segs)
+    return plans
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import arroyo_b200 as ab
+    from arroyo_b200 import ffi, operators as native
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if ffi.load().arroyo_b200_device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: arroyo_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        from arroyo_b200 import multi_gpu
+        return multi_gpu.bench(args, torch, dist, rank, world, local)
+
+    W, K = max(args.warmup, 3), args.steps
+    rows = args.rows_per_pane
+    assert rows % BATCH_ROWS == 0
+    gen_pane = make_generator(torch, device, rows, args.keys, args.dist, 42 + rank)
+    panes = [gen_pane(p) for p in range(W + K)]
+    plans = build_batch_lists(torch, panes, rows)
+    torch.cuda.synchronize()
+
+    import pyarrow as pa
+    schema = pa.schema([("key", pa.int64()), ("value", pa.int64()), ("_timestamp", pa.timestamp("ns"))])
+    flags = ffi.FLAG_PROFILE | (ffi.FLAG_REMERGE_ONLY if args.remerge else 0)
+    stream = torch.cuda.current_stream().cuda_stream
+    op = native.SlidingAggregatingWindowFunc(window_config(), input_schema=schema, device=local, stream=stream,
+                                             flags=flags, expected_keys=args.keys)
+    rows_out = 0
+
+    def step(p):
+        nonlocal rows_out
+        for cols, nrows, wm in plans[p]:
+            op.process_device_batches(cols, nrows, 3)
+            if wm is not None:
+                for n, _ in op.handle_watermark_device(wm):
+                    rows_out += n
+
+    for p in range(W):
+        step(p)
+    op.flush()
+    torch.cuda.synchronize()
+    st0 = op.stats()
+    rows_out = 0
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for p in range(W, W + K):
+        step(p)
+    op.flush()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    st1 = op.stats()
+    op.close()
+    del panes, plans
+    torch.cuda.empty_cache()
+
+    value = K * rows / (ms * 1e-3)
+    peak, peak_kind = measured_peak()
+    d = {k: st1[k] - st0[k] for k in st1}
+    ingest_gbs = 24.0 * d["ingest_rows_timed"] / (d["ingest_ms"] * 1e-3) / 1e9 if d["ingest_ms"] else None
+    emit_share = d["emit_ms"] / ms if ms else None
+    step_bytes = 24.0 * rows + 72.0 * args.keys + 48.0 * (rows_out / max(K, 1))
+    traffic = ncu_traffic()
+    roof = {"bound": "hbm", "kernel": "ingest_kernel<1>", "achieved": round(ingest_gbs, 1) if ingest_gbs else None,
+            "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+            "frac": round(ingest_gbs / peak, 4) if ingest_gbs else None,
+            "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+            "algorithmic_bytes_per_launch": 24.0 * d["ingest_rows_timed"] / max(d["ingest_launches"], 1),
+            "ingest_ms_per_step": d["ingest_ms"] / K, "emit_ms_per_step": d["emit_ms"] / K,
+            "ingest_share_of_step": round(d["ingest_ms"] / ms, 3), "emit_share_of_step": round(emit_share, 3),
+            "pipeline_frac": round(step_bytes * K / (ms * 1e-3) / 1e9 / peak, 4)}
+
+    out = {"metric": "rows/sec sliding-window SUM (1M keys)", "value": value, "unit": "rows/s", "n_gpus": 1,
+           "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+           "config": {"workload": "BASELINE configs[2]: hop(1s slide,10s width) SUM/AVG/COUNT GROUP BY key, "
+                                  f"{args.keys} i64 keys ({args.dist}), {rows} rows/pane in {rows // BATCH_ROWS} "
+                                  f"batches of {BATCH_ROWS}, 1 step = 1 pane + 1 emitted window",
+                      "keys": args.keys, "rows_per_step": rows, "batch_rows": BATCH_ROWS, "width_s": 10, "slide_s": 1,
+                      "emission": "remerge" if args.remerge else "running add/evict",
+                      "l2": "inputs larger than L2 (402 MB per step, never re-read)", "parallelism": "1 gpu"},
+           "rows_out_per_step": rows_out / max(K, 1), "gpu_launches": int(d["kernel_launches"]),
+           "roofline": roof, "clocks": clocks}
+
+    # ---- e2e: host Arrow batches in, host Arrow batches out, through the reference-facing call ----
+    if not args.skip_e2e:
+        out["e2e"] = run_e2e(args, torch, device, local, gen_pane)
+    if not args.skip_cpu:
+        cpu = run_cpu(torch, args, device, budget_s=25.0, warm_panes=11, timed_panes=3)
+        out["cpu_baseline"] = {"value": cpu["rows_per_s"], "unit": "rows/s", "cores": cpu["threads"], "kind": "port",
+                               "sample": cpu["sample"]}
+    print(json.dumps(out), flush=True)
+
+
+def run_e2e(args, torch, device, local, gen_pane):
+    import pyarrow as pa
+
+    import arroyo_b200 as ab
+    from arroyo_b200 import ffi, operators as native
+    K = args.e2e_steps or min(args.steps, 10)
+    W = 11
+    rows = args.rows_per_pane
+    nb = rows // BATCH_ROWS
+    # pinned host panes holding the same synthetic stream
+    host = []
+    for p in range(W + K):
+        cols = []
+        for x in gen_pane(p):
+            h = torch.empty(rows, dtype=torch.int64, pin_memory=True)
+            h.copy_(x)
+            cols.append(h)
+        host.append(cols)
+    torch.cuda.synchronize()
+    ts_type = pa.timestamp("ns")
+
+    def arrow_batch(cols, b):
+        arrs = []
+        for ci, h in enumerate(cols):
+            a = h.numpy()[b * BATCH_ROWS:(b + 1) * BATCH_ROWS]
+            buf = pa.py_buffer(a)  # zero copy: the Arrow buffer *is* the pinned memory
+            arrs.append(pa.Array.from_buffers(ts_type if ci == 2 else pa.int64(), BATCH_ROWS, [None, buf]))
+        return pa.RecordBatch.from_arrays(arrs, names=["key", "value", "_timestamp"])
+
+    batches = [[arrow_batch(cols, b) for b in range(nb)] for cols in host]
+    mm = []
+    for cols in host:
+        t = cols[2].view(nb, BATCH_ROWS)
+        mm += list(zip(t.amin(dim=1).tolist(), t.amax(dim=1).tolist()))
+    wms = watermark_schedule(mm)
+    op = native.SlidingAggregatingWindowFunc(window_config(), device=local, expected_keys=args.keys,
+                                             flags=ffi.FLAG_REMERGE_ONLY if args.remerge else 0)
+    ctx = ab.OperatorContext(1)
+    col = ab.Collector()
+    d2h = 0
+
+    def step(p):
+        nonlocal d2h
+        for b in range(nb):
+            op.process_batch(batches[p][b], ctx, col)
+            wm = wms[p * nb + b]
+            if wm is not None:
+                ctx.watermarks.set(0, wm)
+                op.handle_watermark(wm, ctx, col)
+                for rb in col.batches:
+                    d2h += rb.num_rows * 48
+                col.batches.clear()
+
+    for p in range(W):
+        step(p)
+    op.flush()
+    torch.cuda.synchronize()
+    d2h = 0
+    t0 = time.perf_counter()
+    for p in range(W, W + K):
+        step(p)
+    op.flush()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    op.close()
+    return {"value": K * rows / dt, "unit": "rows/s", "h2d_bytes_per_step": rows * 24,
+            "d2h_bytes_per_step": d2h // max(K, 1), "steps": K, "ms_per_step": 1e3 * dt / K,
+            "path": "pinned host Arrow batches -> arroyo_b200_op_process_batch -> host Arrow windows"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The Rust
+    reference cannot be built in this image (no rustc/cargo, DataFusion/arrow-rs not vendored), so this is
+    the C port of its algorithm (oracle/window_oracle.c), pinned by the reference's golden vectors."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if torch.cuda.is_available() else torch.device("cpu")
+    W, K = max(args.warmup, 3), args.steps
+    cpu = run_cpu(torch, args, device, budget_s=150.0, warm_panes=W, timed_panes=K)
+    line = {"impl": "reference", "metric": "rows/sec sliding-window SUM (1M keys)", "value": cpu["rows_per_s"],
+            "unit": "rows/s", "n_gpus": args.gpus, "steps": cpu["steps"], "warmup": W,
+            "ms_per_step": cpu["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2]: hop(1s slide,10s width) SUM/AVG/COUNT GROUP BY key, "
+                                   f"{args.keys} i64 keys ({args.dist}); bounded sample per step: "
+                                   f"{cpu['rows_per_step']} rows", "keys": args.keys,
+                       "rows_per_step": cpu["rows_per_step"], "batch_rows": BATCH_ROWS},
+            "cpu_baseline": {"value": cpu["rows_per_s"], "unit": "rows/s", "cores": cpu["threads"], "kind": "port",
+                             "sample": cpu["sample"]},
+            "e2e": {"value": cpu["rows_per_s"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
