@@ -61,9 +61,9 @@ struct Counters {
   unsigned long long late_rows;
   unsigned long long deferred;
   unsigned long long lost;
-  unsigned long long ontime_rows;
-  long long max_bin;
-  long long min_bin;
+  unsigned long long reserved0;
+  long long max_ts;
+  long long reserved1;
   unsigned int n_keys;
   unsigned int pad;
 };
@@ -103,7 +103,7 @@ struct IngestParams {
   int acc_kind[MAX_ACC];
   int acc_val[MAX_ACC];
   Counters* counters;
-  unsigned int* touched;
+  unsigned long long* slot_rows;  // on-time rows per ring slot, added by this launch
   long long* d_key;
   long long* d_ts;
   long long* d_val[MAX_VALS];
@@ -211,11 +211,27 @@ __global__ void pane_init_kernel(const __grid_constant__ InitParams p) {
   }
 }
 
+__device__ __forceinline__ const long long* ldg_ptr(const long long* const* pp) {
+  return reinterpret_cast<const long long*>(__ldg(reinterpret_cast<const unsigned long long*>(pp)));
+}
+
 // -------------------------------------------------------------------------------------------
 // ingest: window-assign + keyed partial aggregate
 // -------------------------------------------------------------------------------------------
-__device__ __forceinline__ const long long* ldg_ptr(const long long* const* pp) {
-  return reinterpret_cast<const long long*>(__ldg(reinterpret_cast<const unsigned long long*>(pp)));
+// RED (fire-and-forget reduction, no return trip).  The pane pointers come out of memory, so the
+// compiler only knows them as generic addresses and would emit the slower generic ATOM: state the
+// address space explicitly.
+__device__ __forceinline__ void red_add_u64(unsigned long long* a, unsigned long long v) {
+  asm volatile("red.global.add.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(a)), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_f64(unsigned long long* a, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(a)), "d"(v) : "memory");
+}
+__device__ __forceinline__ void red_min_s64(unsigned long long* a, long long v) {
+  asm volatile("red.global.min.s64 [%0], %1;" ::"l"(__cvta_generic_to_global(a)), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_max_s64(unsigned long long* a, long long v) {
+  asm volatile("red.global.max.s64 [%0], %1;" ::"l"(__cvta_generic_to_global(a)), "l"(v) : "memory");
 }
 
 template <int NV>
@@ -226,7 +242,7 @@ struct Row {
 };
 
 template <int NV>
-__device__ __forceinline__ void defer_row(const IngestParams& p, const Row<NV>& r) {
+__device__ __noinline__ void defer_row(const IngestParams& p, const Row<NV>& r) {
   unsigned long long idx = atomicAdd(&p.counters->deferred, 1ull);
   if (idx < p.defer_cap) {
     p.d_key[idx] = r.key;
@@ -238,38 +254,57 @@ __device__ __forceinline__ void defer_row(const IngestParams& p, const Row<NV>& 
   }
 }
 
-template <int NV>
-__device__ __forceinline__ void process_row(const IngestParams& p, const Row<NV>& r, unsigned char* s_touched,
-                                            unsigned long long& late, unsigned long long& ontime, long long& maxb,
-                                            long long& minb) {
-  // K1: bin = ts - ts % slide (tumbling_aggregating_window.rs:65-73)
-  uint64_t q = p.slide_div.div((uint64_t)r.ts);
-  long long bin = (long long)(q * (uint64_t)p.slide);
-  // K7: late bins are dropped (tumbling :282-291, sliding :631-633)
-  if (bin < p.late_bin) {
-    ++late;
-    return;
-  }
-  maxb = max(maxb, bin);
-  minb = min(minb, bin);
-  uint32_t slot = (uint32_t)q & p.ring_mask;
-  if (__ldg(p.pane_bins + slot) != bin) {
-    defer_row<NV>(p, r);
-    return;
-  }
-  uint32_t id = 0;
-  if (p.keyed) {
-    id = dict_lookup_insert(p.dict, r.key);
-    if (id >= ID_OVERFLOW) {
-      defer_row<NV>(p, r);
-      return;
+// Probes after a first-slot miss (collision chain, or a key seen for the first time).
+__device__ __noinline__ uint32_t dict_slow_path(const DictView& d, long long key, uint32_t pos) {
+#pragma unroll 1
+  for (int probe = 0; probe < MAX_PROBE; ++probe) {
+    Slot* sp = d.slots + pos;
+    ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(sp));
+    long long k = (long long)raw.x;
+    uint32_t id = (uint32_t)raw.y;
+    if (k == key) {
+      if (id == ID_UNSET) id = wait_id(sp);
+      return id;
     }
+    if (k == EMPTY_KEY) {
+      unsigned long long old =
+          atomicCAS(reinterpret_cast<unsigned long long*>(&sp->key), (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+      if (old == (unsigned long long)EMPTY_KEY) {
+        uint32_t nid = atomicAdd(d.n_keys, 1u);
+        if (nid >= d.id_cap) {
+          nid = ID_OVERFLOW;
+        } else {
+          d.id_keys[nid] = key;
+        }
+        __threadfence();
+        atomicExch(&sp->id, nid);
+        return nid;
+      }
+      if ((long long)old == key) return wait_id(sp);
+    }
+    pos = (pos + 1) & d.mask;
   }
-  ++ontime;
-  s_touched[slot] = 1;
-  unsigned long long* pane = reinterpret_cast<unsigned long long*>(__ldg(reinterpret_cast<const unsigned long long*>(p.pane_ptrs + slot)));
-  // K3: partial aggregate.  Results are unused => the compiler emits RED (no return trip).
-  atomicAdd(pane + id, 1ull);
+  return ID_OVERFLOW;
+}
+
+// Per-thread view of the pane ring: the slot of the previous row lives in registers, so the common
+// case (a warp's rows all in one pane) touches neither the ring tables nor any shared counter.
+struct PaneCache {
+  uint32_t slot = 0xFFFFFFFFu;
+  uint32_t cnt = 0;  // on-time rows this thread aggregated into `slot`
+  long long bin = FREE_BIN;
+  unsigned long long* ptr = nullptr;
+};
+
+struct Tally {
+  uint32_t late = 0;
+  long long max_ts = LLONG_MIN;  // newest on-time event time seen (host derives the newest bin)
+};
+
+// The RED updates of one row into pane block `pane` (K3: partial aggregate).
+template <int NV>
+__device__ __forceinline__ void accumulate(const IngestParams& p, const Row<NV>& r, unsigned long long* pane, uint32_t id) {
+  red_add_u64(pane + id, 1ull);
 #pragma unroll
   for (int a = 1; a < MAX_ACC; ++a) {
     if (a < p.n_acc) {
@@ -279,35 +314,70 @@ __device__ __forceinline__ void process_row(const IngestParams& p, const Row<NV>
       for (int x = 0; x < NV; ++x)
         if (p.acc_val[a] == x) v = r.val[x];
       switch (p.acc_kind[a]) {
-        case ACC_SUM_I64:
-          atomicAdd(dst, (unsigned long long)v);
-          break;
-        case ACC_SUM_F64:
-          atomicAdd(reinterpret_cast<double*>(dst), (double)v);
-          break;
-        case ACC_MIN_I64:
-          atomicMin(reinterpret_cast<long long*>(dst), v);
-          break;
-        case ACC_MAX_I64:
-          atomicMax(reinterpret_cast<long long*>(dst), v);
-          break;
-        default:
-          break;
+        case ACC_SUM_I64: red_add_u64(dst, (unsigned long long)v); break;
+        case ACC_SUM_F64: red_add_f64(dst, (double)v); break;
+        case ACC_MIN_I64: red_min_s64(dst, v); break;
+        case ACC_MAX_I64: red_max_s64(dst, v); break;
+        default: break;
       }
     }
   }
 }
 
-template <int NV>
-__global__ void __launch_bounds__(THREADS) ingest_kernel(const __grid_constant__ IngestParams p) {
-  __shared__ unsigned char s_touched[MAX_RING];
-  __shared__ unsigned long long s_red[4][THREADS / 32];
-  const int tid = threadIdx.x;
-  for (int i = tid; i < MAX_RING; i += THREADS) s_touched[i] = 0;
-  __syncthreads();
+// id of the row's key given the first probe (already loaded), or ID_OVERFLOW
+__device__ __forceinline__ uint32_t resolve_id(const IngestParams& p, long long key, const ulonglong2& raw, uint32_t pos) {
+  if ((long long)raw.x == key && (uint32_t)raw.y < ID_OVERFLOW) return (uint32_t)raw.y;
+  if (key == EMPTY_KEY) return 0;  // id 0 is reserved for the one key that equals the empty sentinel
+  return dict_slow_path(p.dict, key, pos);
+}
 
-  unsigned long long late = 0, ontime = 0;
-  long long maxb = LLONG_MIN, minb = LLONG_MAX;
+// Row whose pane is not the thread's cached one (pane boundary inside a warp, tail tiles, tiny
+// batches): look the ring up directly and count the row with its own atomic.
+template <int NV>
+__device__ __noinline__ void slow_row(const IngestParams& p, const Row<NV>& r, uint64_t q, long long bin, bool probed,
+                                      ulonglong2 raw, uint32_t pos) {
+  const uint32_t slot = (uint32_t)q & p.ring_mask;
+  if (__ldg(p.pane_bins + slot) != bin) {
+    defer_row<NV>(p, r);
+    return;
+  }
+  uint32_t id = probed ? resolve_id(p, r.key, raw, pos) : 0u;
+  if (id >= ID_OVERFLOW) {
+    defer_row<NV>(p, r);
+    return;
+  }
+  unsigned long long* pane =
+      reinterpret_cast<unsigned long long*>(__ldg(reinterpret_cast<const unsigned long long*>(p.pane_ptrs + slot)));
+  atomicAdd(p.slot_rows + slot, 1ull);
+  accumulate<NV>(p, r, pane, id);
+}
+
+// Warp-combined publication of the per-thread on-time row counts (all 32 lanes must call).
+__device__ __forceinline__ void flush_counts(const IngestParams& p, PaneCache& pc, int lane) {
+  const unsigned int peers = __match_any_sync(0xffffffffu, pc.slot);
+  const unsigned int total = __reduce_add_sync(peers, pc.cnt);
+  if (total && (__ffs(peers) - 1) == lane) atomicAdd(p.slot_rows + pc.slot, (unsigned long long)total);
+  pc.cnt = 0;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(THREADS, 5) ingest_kernel(const __grid_constant__ IngestParams p) {
+  __shared__ unsigned long long s_late;
+  __shared__ long long s_max_ts;
+  __shared__ unsigned int s_done;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  if (tid == 0) {
+    s_late = 0;
+    s_max_ts = LLONG_MIN;
+    s_done = 0;
+  }
+  __syncthreads();  // the only block barrier: all warps arrive together at kernel start
+
+  PaneCache pc;
+  Tally tl;
+  const FastDivU64 sd = p.slide_div;
+  const bool keyed = p.keyed != 0;
 
   for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     int lo = 0, hi = p.n_segs - 1;
@@ -321,78 +391,131 @@ __global__ void __launch_bounds__(THREADS) ingest_kernel(const __grid_constant__
     const int cnt = nrem < TILE ? (int)nrem : TILE;
     const long long* kcol = ldg_ptr(&sg->key);
     const long long* tcol = ldg_ptr(&sg->ts);
-    const long long* vcol[NV > 0 ? NV : 1];
-#pragma unroll
-    for (int v = 0; v < NV; ++v) vcol[v] = ldg_ptr(&sg->val[v]);
 
     if (cnt == TILE && __ldg(&sg->vec_ok)) {
-      // 128-bit streaming loads: a warp instruction covers 512 contiguous bytes per column
-      Row<NV> rows[PAIRS * 2];
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < PAIRS; ++j) {
+        // 128-bit streaming loads: a warp instruction covers 512 contiguous bytes per column
         const long long r0 = base + 2ll * (j * THREADS + tid);
-        longlong2 t2 = __ldcs(reinterpret_cast<const longlong2*>(tcol + r0));
-        rows[2 * j].ts = t2.x;
-        rows[2 * j + 1].ts = t2.y;
-        if (p.keyed) {
-          longlong2 k2 = __ldcs(reinterpret_cast<const longlong2*>(kcol + r0));
-          rows[2 * j].key = k2.x;
-          rows[2 * j + 1].key = k2.y;
-        } else {
-          rows[2 * j].key = 0;
-          rows[2 * j + 1].key = 0;
+        Row<NV> ra, rb;
+        const longlong2 t2 = __ldcs(reinterpret_cast<const longlong2*>(tcol + r0));
+        ra.ts = t2.x;
+        rb.ts = t2.y;
+        ra.key = 0;
+        rb.key = 0;
+        ulonglong2 pa = {0, 0}, pb = {0, 0};
+        uint32_t posa = 0, posb = 0;
+        if (keyed) {
+          const longlong2 k2 = __ldcs(reinterpret_cast<const longlong2*>(kcol + r0));
+          ra.key = k2.x;
+          rb.key = k2.y;
+          // both dictionary probes are in flight before either is consumed
+          posa = (uint32_t)mix64((uint64_t)ra.key) & p.dict.mask;
+          posb = (uint32_t)mix64((uint64_t)rb.key) & p.dict.mask;
+          pa = __ldcg(reinterpret_cast<const ulonglong2*>(p.dict.slots + posa));
+          pb = __ldcg(reinterpret_cast<const ulonglong2*>(p.dict.slots + posb));
         }
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
-          longlong2 v2 = __ldcs(reinterpret_cast<const longlong2*>(vcol[v] + r0));
-          rows[2 * j].val[v] = v2.x;
-          rows[2 * j + 1].val[v] = v2.y;
+          const longlong2 v2 = __ldcs(reinterpret_cast<const longlong2*>(ldg_ptr(&sg->val[v]) + r0));
+          ra.val[v] = v2.x;
+          rb.val[v] = v2.y;
+        }
+        // K1: bin = ts - ts % slide (tumbling_aggregating_window.rs:65-73)
+        const uint64_t qa = sd.div((uint64_t)ra.ts), qb = sd.div((uint64_t)rb.ts);
+        const long long bina = (long long)(qa * (uint64_t)p.slide), binb = (long long)(qb * (uint64_t)p.slide);
+        // K7: late bins are dropped (tumbling :282-291, sliding :631-633)
+        const bool livea = bina >= p.late_bin, liveb = binb >= p.late_bin;
+        tl.late += (livea ? 0u : 1u) + (liveb ? 0u : 1u);
+        if (livea) tl.max_ts = max(tl.max_ts, ra.ts);
+        if (liveb) tl.max_ts = max(tl.max_ts, rb.ts);
+        // refresh the cached pane when this thread's first live row moved to another pane; the vote
+        // keeps the warp-combined count flush convergent
+        const uint32_t want = (uint32_t)(livea ? qa : qb) & p.ring_mask;
+        if (__any_sync(0xffffffffu, (livea || liveb) && want != pc.slot)) {
+          flush_counts(p, pc, lane);
+          if (livea || liveb) {
+            pc.slot = want;
+            pc.bin = __ldg(p.pane_bins + want);
+            pc.ptr = reinterpret_cast<unsigned long long*>(
+                __ldg(reinterpret_cast<const unsigned long long*>(p.pane_ptrs + want)));
+          }
+        }
+        if (livea) {
+          if (bina == pc.bin) {
+            const uint32_t id = keyed ? resolve_id(p, ra.key, pa, posa) : 0u;
+            if (id < ID_OVERFLOW) {
+              ++pc.cnt;
+              accumulate<NV>(p, ra, pc.ptr, id);
+            } else {
+              defer_row<NV>(p, ra);
+            }
+          } else {
+            slow_row<NV>(p, ra, qa, bina, keyed, pa, posa);
+          }
+        }
+        if (liveb) {
+          if (binb == pc.bin) {
+            const uint32_t id = keyed ? resolve_id(p, rb.key, pb, posb) : 0u;
+            if (id < ID_OVERFLOW) {
+              ++pc.cnt;
+              accumulate<NV>(p, rb, pc.ptr, id);
+            } else {
+              defer_row<NV>(p, rb);
+            }
+          } else {
+            slow_row<NV>(p, rb, qb, binb, keyed, pb, posb);
+          }
         }
       }
-#pragma unroll
-      for (int j = 0; j < PAIRS * 2; ++j) process_row<NV>(p, rows[j], s_touched, late, ontime, maxb, minb);
     } else {
+      // tail tile / unaligned segment / tiny batch: scalar loads, uncached ring lookups
       for (int i = tid; i < cnt; i += THREADS) {
         Row<NV> r;
         r.ts = __ldcs(tcol + base + i);
-        r.key = p.keyed ? __ldcs(kcol + base + i) : 0;
+        r.key = keyed ? __ldcs(kcol + base + i) : 0;
 #pragma unroll
-        for (int v = 0; v < NV; ++v) r.val[v] = __ldcs(vcol[v] + base + i);
-        process_row<NV>(p, r, s_touched, late, ontime, maxb, minb);
+        for (int v = 0; v < NV; ++v) r.val[v] = __ldcs(ldg_ptr(&sg->val[v]) + base + i);
+        ulonglong2 raw = {0, 0};
+        uint32_t pos = 0;
+        if (keyed) {
+          pos = (uint32_t)mix64((uint64_t)r.key) & p.dict.mask;
+          raw = __ldcg(reinterpret_cast<const ulonglong2*>(p.dict.slots + pos));
+        }
+        const uint64_t q = sd.div((uint64_t)r.ts);
+        const long long bin = (long long)(q * (uint64_t)p.slide);
+        if (bin < p.late_bin) {
+          ++tl.late;
+          continue;
+        }
+        tl.max_ts = max(tl.max_ts, r.ts);
+        slow_row<NV>(p, r, q, bin, keyed, raw, pos);
       }
     }
   }
 
-  // block-level reductions of the bookkeeping counters: a handful of atomics per CTA
+  // per-pane on-time row counts: one atomic per (warp, pane) after a warp-level combine
+  __syncwarp();
+  flush_counts(p, pc, lane);
+  // bookkeeping counters: warp reduce -> shared -> the last warp of the block publishes
+  unsigned long long late = tl.late;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     late += __shfl_xor_sync(0xffffffffu, late, o);
-    ontime += __shfl_xor_sync(0xffffffffu, ontime, o);
-    maxb = max(maxb, __shfl_xor_sync(0xffffffffu, maxb, o));
-    minb = min(minb, __shfl_xor_sync(0xffffffffu, minb, o));
+    tl.max_ts = max(tl.max_ts, __shfl_xor_sync(0xffffffffu, tl.max_ts, o));
   }
-  const int w = tid >> 5;
-  if ((tid & 31) == 0) {
-    s_red[0][w] = late;
-    s_red[1][w] = ontime;
-    s_red[2][w] = (unsigned long long)maxb;
-    s_red[3][w] = (unsigned long long)minb;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    for (int i = 1; i < THREADS / 32; ++i) {
-      late += s_red[0][i];
-      ontime += s_red[1][i];
-      maxb = max(maxb, (long long)s_red[2][i]);
-      minb = min(minb, (long long)s_red[3][i]);
+  if (lane == 0) {
+    if (late) atomicAdd(&s_late, late);
+    if (tl.max_ts != LLONG_MIN) atomicMax(&s_max_ts, tl.max_ts);
+    __threadfence_block();
+    if (atomicAdd(&s_done, 1u) == THREADS / 32 - 1) {
+      __threadfence_block();
+      const unsigned long long bl = *(volatile unsigned long long*)&s_late;
+      const long long mx = *(volatile long long*)&s_max_ts;
+      if (bl) atomicAdd(&p.counters->late_rows, bl);
+      if (mx != LLONG_MIN) atomicMax(&p.counters->max_ts, mx);
     }
-    if (late) atomicAdd(&p.counters->late_rows, late);
-    if (ontime) atomicAdd(&p.counters->ontime_rows, ontime);
-    if (maxb != LLONG_MIN) atomicMax(&p.counters->max_bin, maxb);
-    if (minb != LLONG_MAX) atomicMin(&p.counters->min_bin, minb);
   }
-  for (int i = tid; i <= (int)p.ring_mask; i += THREADS)
-    if (s_touched[i]) p.touched[i] = 1u;
 }
 
 // Restore: merge a partial-state batch (AggregateExec(Partial) output written at a checkpoint,
@@ -658,13 +781,14 @@ struct Pane {
   unsigned long long* frozen = nullptr;  // state already written to a checkpoint / restored
   int slot = -1;
   bool in_tier = false;
+  uint64_t rows = 0;  // on-time rows aggregated into this pane
 };
 
 struct LaunchRec {
   cudaEvent_t done = nullptr;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   Counters* h_counters = nullptr;  // pinned
-  unsigned int* h_touched = nullptr;  // pinned [MAX_RING]
+  unsigned long long* h_slot_rows = nullptr;  // pinned [MAX_RING]
   uint64_t rows = 0;
   bool in_flight = false;
   int chunk = -1;  // staging chunk read by this launch (-1: none)
@@ -717,7 +841,7 @@ class WindowAggOp final : public OpBase {
   // dictionary
   uint64_t id_cap_ = 0;
   uint64_t dict_cap_ = 0;
-  DevBuf slots_, id_keys_, counters_, touched_;
+  DevBuf slots_, id_keys_, counters_, slot_rows_;
   uint32_t n_keys_host_ = 1;
 
   // ring
@@ -755,7 +879,7 @@ class WindowAggOp final : public OpBase {
   PinnedBuf h_segs_[NLAUNCH];
   DevBuf d_segs_[NLAUNCH];
   LaunchRec launches_[NLAUNCH];
-  PinnedBuf h_counters_[NLAUNCH], h_touched_[NLAUNCH];
+  PinnedBuf h_counters_[NLAUNCH], h_slot_rows_[NLAUNCH];
   int next_launch_ = 0;
   std::deque<int> in_flight_;
   std::deque<PendingRelease> releases_;
@@ -897,10 +1021,9 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
   else tumbling_.reset(new TumblingPlanner(width_));
 
   counters_.alloc(sizeof(Counters));
-  touched_.alloc(MAX_RING * sizeof(unsigned int));
+  slot_rows_.alloc(MAX_RING * sizeof(unsigned long long));
   Counters init{};
-  init.max_bin = LLONG_MIN;
-  init.min_bin = LLONG_MAX;
+  init.max_ts = LLONG_MIN;
   init.n_keys = 1;
   AB_CUDA(cudaMemcpyAsync(counters_.p, &init, sizeof init, cudaMemcpyHostToDevice, stream_));
   last_counters_ = init;
@@ -929,9 +1052,9 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
     h_segs_[i].alloc(MAX_SEGS * sizeof(Segment));
     d_segs_[i].alloc(MAX_SEGS * sizeof(Segment));
     h_counters_[i].alloc(sizeof(Counters));
-    h_touched_[i].alloc(MAX_RING * sizeof(unsigned int));
+    h_slot_rows_[i].alloc(MAX_RING * sizeof(unsigned long long));
     launches_[i].h_counters = h_counters_[i].as<Counters>();
-    launches_[i].h_touched = h_touched_[i].as<unsigned int>();
+    launches_[i].h_slot_rows = h_slot_rows_[i].as<unsigned long long>();
     AB_CUDA(cudaEventCreateWithFlags(&launches_[i].done, cudaEventDisableTiming));
     if (profile_) {
       AB_CUDA(cudaEventCreate(&launches_[i].t0));
@@ -1286,7 +1409,7 @@ void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk
   }
   AB_CUDA(cudaMemcpyAsync(d_segs_[li].p, hs, segs_in.size() * sizeof(Segment), cudaMemcpyHostToDevice, stream_));
   upload_ring();
-  AB_CUDA(cudaMemsetAsync(touched_.p, 0, ring_ * sizeof(unsigned int), stream_));
+  AB_CUDA(cudaMemsetAsync(slot_rows_.p, 0, ring_ * sizeof(unsigned long long), stream_));
   if (!defer_[defer_cur_][0].p) {
     for (int c = 0; c < 2 + n_vals_; ++c) defer_[defer_cur_][c].alloc(defer_cap_ * 8);
   }
@@ -1314,7 +1437,7 @@ void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk
     p.acc_val[a] = acc_val_[a];
   }
   p.counters = counters_.as<Counters>();
-  p.touched = touched_.as<unsigned int>();
+  p.slot_rows = slot_rows_.as<unsigned long long>();
   p.d_key = defer_[defer_cur_][0].as<long long>();
   p.d_ts = defer_[defer_cur_][1].as<long long>();
   for (int v = 0; v < n_vals_; ++v) p.d_val[v] = defer_[defer_cur_][2 + v].as<long long>();
@@ -1335,7 +1458,7 @@ void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk
   ++st_.kernel_launches;
   ++st_.ingest_launches;
   AB_CUDA(cudaMemcpyAsync(L.h_counters, counters_.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream_));
-  AB_CUDA(cudaMemcpyAsync(L.h_touched, touched_.p, ring_ * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream_));
+  AB_CUDA(cudaMemcpyAsync(L.h_slot_rows, slot_rows_.p, ring_ * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
   AB_CUDA(cudaEventRecord(L.done, stream_));
   if (chunk >= 0) AB_CUDA(cudaEventRecord(chunk_free_[chunk], stream_));
   L.rows = rows;
@@ -1377,10 +1500,11 @@ void WindowAggOp::absorb(int li) {
   last_counters_ = c;
   have_counters_ = true;
   n_keys_host_ = (uint32_t)std::min<uint64_t>(c.n_keys, id_cap_);
-  if (c.max_bin != LLONG_MIN) max_bin_seen_ = std::max<int64_t>(max_bin_seen_, c.max_bin);
+  if (c.max_ts != LLONG_MIN) max_bin_seen_ = std::max<int64_t>(max_bin_seen_, bin_start(c.max_ts, slide_));
   for (uint32_t s = 0; s < ring_; ++s) {
-    if (L.h_touched[s]) {
+    if (L.h_slot_rows[s]) {
       AB_REQUIRE(h_pane_bins_[s] != FREE_BIN, ARROYO_B200_RUNTIME, "touched a free ring slot");
+      panes_.at(h_pane_bins_[s]).rows += L.h_slot_rows[s];
       touch(h_pane_bins_[s]);
     }
   }

@@ -190,10 +190,12 @@ def test_dictionary_growth_and_far_future_rows(G):
     (forces the deferred path and ring growth)."""
     rng = np.random.default_rng(9)
     batches = gen_stream(rng, 150_000, 60_000, rate_per_s=50_000, batch=8192)
-    # one straggler batch 500 panes in the future, delivered early
-    fut = O.Batch({"key": np.arange(100, dtype=np.int64), "value": np.ones(100, dtype=np.int64),
-                   O.TIMESTAMP: np.full(100, T0 + 500 * S, dtype=np.int64)})
-    batches.insert(3, fut)
+    # 100 rows 500 panes in the future, delivered early inside an ordinary batch (so the batch's min
+    # timestamp, hence the watermark, stays current)
+    b3 = batches[3]
+    batches[3] = O.Batch({"key": np.concatenate([b3["key"], np.arange(100, dtype=np.int64)]),
+                          "value": np.concatenate([b3["value"], np.ones(100, dtype=np.int64)]),
+                          O.TIMESTAMP: np.concatenate([b3[O.TIMESTAMP], np.full(100, T0 + 500 * S, dtype=np.int64)])})
     cfg = O.WindowAggConfig(width=4 * S, slide=S, key_names=["key"], aggs=SUM_AVG, window_index=1)
     want, got, gop = run_both(G, lambda: O.SlidingAggregatingWindowFunc(cfg),
                               lambda: G.SlidingAggregatingWindowFunc(cfg, expected_keys=256), batches)
