@@ -39,6 +39,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     ]
     if verbose:
         flags += ["-Xptxas", "-v"]
+    if os.environ.get("AB_INGEST_MIN_BLOCKS"):  # tuning knob for experiments
+        flags += ["-DAB_INGEST_MIN_BLOCKS=" + os.environ["AB_INGEST_MIN_BLOCKS"]]
     build_dir = os.path.join(HERE, "build")
     os.makedirs(build_dir, exist_ok=True)
     procs = []

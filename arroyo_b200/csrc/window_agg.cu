@@ -62,7 +62,7 @@ struct Counters {
   unsigned long long deferred;
   unsigned long long lost;
   unsigned long long reserved0;
-  long long max_ts;
+  unsigned long long max_q;  // newest on-time pane number (ts / slide) seen
   long long reserved1;
   unsigned int n_keys;
   unsigned int pad;
@@ -82,9 +82,16 @@ struct DictView {
   Slot* slots;
   long long* id_keys;
   unsigned int* n_keys;
-  uint32_t mask;
+  uint32_t cap;  // number of slots (any value: placement is multiply-shift, not a mask)
   uint32_t id_cap;
 };
+
+__host__ __device__ __forceinline__ uint32_t dict_home(uint64_t key, uint32_t cap) {
+  return (uint32_t)(((mix64(key) >> 32) * (uint64_t)cap) >> 32);
+}
+__host__ __device__ __forceinline__ uint32_t dict_next(uint32_t pos, uint32_t cap) {
+  return pos + 1 == cap ? 0u : pos + 1;
+}
 
 struct IngestParams {
   const Segment* segs;
@@ -95,6 +102,7 @@ struct IngestParams {
   FastDivU64 slide_div;
   long long slide;
   long long late_bin;
+  unsigned long long late_q;  // late_bin / slide (0 when there is no watermark yet)
   uint32_t ring_mask;
   int n_acc;
   const long long* pane_bins;
@@ -122,42 +130,6 @@ __device__ __forceinline__ uint32_t wait_id(const Slot* s) {
   return id;
 }
 
-// Returns the dense id of `key`, inserting it if absent; ID_OVERFLOW if no id / slot is available.
-__device__ __forceinline__ uint32_t dict_lookup_insert(const DictView& d, long long key) {
-  if (key == EMPTY_KEY) return 0;  // id 0 is reserved for the one key that equals the sentinel
-  uint32_t pos = (uint32_t)mix64((uint64_t)key) & d.mask;
-#pragma unroll 1
-  for (int probe = 0; probe < MAX_PROBE; ++probe) {
-    Slot* sp = d.slots + pos;
-    ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(sp));
-    long long k = (long long)raw.x;
-    uint32_t id = (uint32_t)raw.y;
-    if (k == key) {
-      if (id == ID_UNSET) id = wait_id(sp);
-      return id;
-    }
-    if (k == EMPTY_KEY) {
-      unsigned long long old =
-          atomicCAS(reinterpret_cast<unsigned long long*>(&sp->key), (unsigned long long)EMPTY_KEY, (unsigned long long)key);
-      if (old == (unsigned long long)EMPTY_KEY) {
-        uint32_t nid = atomicAdd(d.n_keys, 1u);
-        if (nid >= d.id_cap) {
-          nid = ID_OVERFLOW;
-        } else {
-          d.id_keys[nid] = key;
-        }
-        __threadfence();
-        atomicExch(&sp->id, nid);
-        return nid;
-      }
-      if ((long long)old == key) return wait_id(sp);
-      // another key claimed the slot: keep probing
-    }
-    pos = (pos + 1) & d.mask;
-  }
-  return ID_OVERFLOW;
-}
-
 __global__ void dict_init_kernel(Slot* slots, uint64_t n) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -169,12 +141,12 @@ __global__ void dict_init_kernel(Slot* slots, uint64_t n) {
 }
 
 // re-insert ids [1, n) after the slot array was replaced
-__global__ void dict_rebuild_kernel(Slot* slots, uint32_t mask, const long long* id_keys, uint32_t n) {
+__global__ void dict_rebuild_kernel(Slot* slots, uint32_t cap, const long long* id_keys, uint32_t n) {
   uint32_t id = blockIdx.x * blockDim.x + threadIdx.x + 1;
   uint32_t stride = gridDim.x * blockDim.x;
   for (; id < n; id += stride) {
     long long key = id_keys[id];
-    uint32_t pos = (uint32_t)mix64((uint64_t)key) & mask;
+    uint32_t pos = dict_home((uint64_t)key, cap);
     while (true) {
       unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&slots[pos].key),
                                          (unsigned long long)EMPTY_KEY, (unsigned long long)key);
@@ -182,7 +154,7 @@ __global__ void dict_rebuild_kernel(Slot* slots, uint32_t mask, const long long*
         slots[pos].id = id;
         break;
       }
-      pos = (pos + 1) & mask;
+      pos = dict_next(pos, cap);
     }
   }
 }
@@ -234,28 +206,38 @@ __device__ __forceinline__ void red_max_s64(unsigned long long* a, long long v) 
   asm volatile("red.global.max.s64 [%0], %1;" ::"l"(__cvta_generic_to_global(a)), "l"(v) : "memory");
 }
 
-template <int NV>
-struct Row {
-  long long key;
-  long long ts;
-  long long val[NV > 0 ? NV : 1];
+// Rows travel through the kernel as scalars (key, ts, up to MAX_VALS values): nothing in the hot loop
+// is addressable, so nothing is forced into local memory.
+struct Vals {
+  long long v0, v1, v2, v3;
 };
-
 template <int NV>
-__device__ __noinline__ void defer_row(const IngestParams& p, const Row<NV>& r) {
+__device__ __forceinline__ Vals pack_vals(const long long (&v)[NV > 0 ? NV : 1]) {
+  Vals o{0, 0, 0, 0};
+  if (NV > 0) o.v0 = v[0];
+  if (NV > 1) o.v1 = v[NV > 1 ? 1 : 0];
+  if (NV > 2) o.v2 = v[NV > 2 ? 2 : 0];
+  if (NV > 3) o.v3 = v[NV > 3 ? 3 : 0];
+  return o;
+}
+
+__device__ __noinline__ void defer_row(const IngestParams& p, long long key, long long ts, long long v0, long long v1,
+                                       long long v2, long long v3) {
   unsigned long long idx = atomicAdd(&p.counters->deferred, 1ull);
   if (idx < p.defer_cap) {
-    p.d_key[idx] = r.key;
-    p.d_ts[idx] = r.ts;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) p.d_val[v][idx] = r.val[v];
+    p.d_key[idx] = key;
+    p.d_ts[idx] = ts;
+    if (p.d_val[0]) p.d_val[0][idx] = v0;
+    if (p.d_val[1]) p.d_val[1][idx] = v1;
+    if (p.d_val[2]) p.d_val[2][idx] = v2;
+    if (p.d_val[3]) p.d_val[3][idx] = v3;
   } else {
     atomicAdd(&p.counters->lost, 1ull);
   }
 }
 
-// Probes after a first-slot miss (collision chain, or a key seen for the first time).
-__device__ __noinline__ uint32_t dict_slow_path(const DictView& d, long long key, uint32_t pos) {
+// First sighting of a key: claim the empty slot found at `pos` (or keep walking if somebody else took it).
+__device__ __noinline__ uint32_t dict_insert(const DictView& d, long long key, uint32_t pos) {
 #pragma unroll 1
   for (int probe = 0; probe < MAX_PROBE; ++probe) {
     Slot* sp = d.slots + pos;
@@ -282,100 +264,143 @@ __device__ __noinline__ uint32_t dict_slow_path(const DictView& d, long long key
       }
       if ((long long)old == key) return wait_id(sp);
     }
-    pos = (pos + 1) & d.mask;
+    pos = dict_next(pos, d.cap);
   }
   return ID_OVERFLOW;
 }
 
-// Per-thread view of the pane ring: the slot of the previous row lives in registers, so the common
-// case (a warp's rows all in one pane) touches neither the ring tables nor any shared counter.
-struct PaneCache {
-  uint32_t slot = 0xFFFFFFFFu;
-  uint32_t cnt = 0;  // on-time rows this thread aggregated into `slot`
-  long long bin = FREE_BIN;
-  unsigned long long* ptr = nullptr;
-};
+// Dense id of `key` given its home slot contents `raw` (already loaded).  Existing keys resolve with
+// read-only probes inline; the insert path is out of line.
+__device__ __forceinline__ uint32_t resolve_id(const DictView& d, long long key, unsigned long long k0, uint32_t id0) {
+  if ((long long)k0 == key && id0 < ID_OVERFLOW) return id0;
+  if (key == EMPTY_KEY) return 0;  // id 0 is reserved for the one key that equals the empty sentinel
+  uint32_t pos = dict_home((uint64_t)key, d.cap);
+  if ((long long)k0 == EMPTY_KEY || (long long)k0 == key) return dict_insert(d, key, pos);
+#pragma unroll 1
+  for (int probe = 1; probe < MAX_PROBE; ++probe) {
+    pos = dict_next(pos, d.cap);
+    const ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(d.slots + pos));
+    if ((long long)raw.x == key && (uint32_t)raw.y < ID_OVERFLOW) return (uint32_t)raw.y;
+    if ((long long)raw.x == EMPTY_KEY || (long long)raw.x == key) return dict_insert(d, key, pos);
+  }
+  return ID_OVERFLOW;
+}
 
-struct Tally {
-  uint32_t late = 0;
-  long long max_ts = LLONG_MIN;  // newest on-time event time seen (host derives the newest bin)
-};
+// Accumulator signature: the kinds of accumulators 1..3 packed 3 bits each (0 = none); GENERIC_SIG =
+// read kinds / value slots from the params at run time.  The common signatures are compiled as
+// straight-line code.
+constexpr int GENERIC_SIG = -1;
+constexpr int sig_of(int k1, int k2 = 0, int k3 = 0) { return k1 | (k2 << 3) | (k3 << 6); }
 
-// The RED updates of one row into pane block `pane` (K3: partial aggregate).
-template <int NV>
-__device__ __forceinline__ void accumulate(const IngestParams& p, const Row<NV>& r, unsigned long long* pane, uint32_t id) {
-  red_add_u64(pane + id, 1ull);
-#pragma unroll
-  for (int a = 1; a < MAX_ACC; ++a) {
-    if (a < p.n_acc) {
-      unsigned long long* dst = pane + (unsigned long long)a * p.id_cap + id;
-      long long v = 0;
-#pragma unroll
-      for (int x = 0; x < NV; ++x)
-        if (p.acc_val[a] == x) v = r.val[x];
-      switch (p.acc_kind[a]) {
-        case ACC_SUM_I64: red_add_u64(dst, (unsigned long long)v); break;
-        case ACC_SUM_F64: red_add_f64(dst, (double)v); break;
-        case ACC_MIN_I64: red_min_s64(dst, v); break;
-        case ACC_MAX_I64: red_max_s64(dst, v); break;
-        default: break;
-      }
-    }
+__device__ __forceinline__ void red_kind(int kind, unsigned long long* dst, long long v) {
+  switch (kind) {
+    case ACC_SUM_I64: red_add_u64(dst, (unsigned long long)v); break;
+    case ACC_SUM_F64: red_add_f64(dst, (double)v); break;
+    case ACC_MIN_I64: red_min_s64(dst, v); break;
+    case ACC_MAX_I64: red_max_s64(dst, v); break;
+    default: break;
   }
 }
 
-// id of the row's key given the first probe (already loaded), or ID_OVERFLOW
-__device__ __forceinline__ uint32_t resolve_id(const IngestParams& p, long long key, const ulonglong2& raw, uint32_t pos) {
-  if ((long long)raw.x == key && (uint32_t)raw.y < ID_OVERFLOW) return (uint32_t)raw.y;
-  if (key == EMPTY_KEY) return 0;  // id 0 is reserved for the one key that equals the empty sentinel
-  return dict_slow_path(p.dict, key, pos);
+// The RED updates of one row into pane block `pane` (K3: partial aggregate).
+template <int NV, int SIG>
+__device__ __forceinline__ void accumulate(const IngestParams& p, const Vals& v, unsigned long long* pane, uint32_t id) {
+  red_add_u64(pane + id, 1ull);
+  if (SIG == GENERIC_SIG) {
+#pragma unroll
+    for (int a = 1; a < MAX_ACC; ++a) {
+      if (a < p.n_acc) {
+        const int x = p.acc_val[a];
+        const long long val = x == 0 ? v.v0 : x == 1 ? v.v1 : x == 2 ? v.v2 : v.v3;
+        red_kind(p.acc_kind[a], pane + (unsigned long long)a * p.id_cap + id, val);
+      }
+    }
+  } else {
+    // at most one value column: every accumulator reads v0
+    constexpr int k1 = SIG & 7, k2 = (SIG >> 3) & 7, k3 = (SIG >> 6) & 7;
+    if (k1) red_kind(k1, pane + p.id_cap + id, v.v0);
+    if (k2) red_kind(k2, pane + 2 * p.id_cap + id, v.v0);
+    if (k3) red_kind(k3, pane + 3 * p.id_cap + id, v.v0);
+  }
 }
 
 // Row whose pane is not the thread's cached one (pane boundary inside a warp, tail tiles, tiny
-// batches): look the ring up directly and count the row with its own atomic.
-template <int NV>
-__device__ __noinline__ void slow_row(const IngestParams& p, const Row<NV>& r, uint64_t q, long long bin, bool probed,
-                                      ulonglong2 raw, uint32_t pos) {
+// batches, non-resident pane): look the ring up directly and count the row with its own atomic.
+template <int NV, int SIG>
+__device__ __noinline__ void slow_row(const IngestParams& p, long long key, long long ts, uint64_t q, long long v0,
+                                      long long v1, long long v2, long long v3) {
   const uint32_t slot = (uint32_t)q & p.ring_mask;
-  if (__ldg(p.pane_bins + slot) != bin) {
-    defer_row<NV>(p, r);
-    return;
+  uint32_t id = 0;
+  bool ok = __ldg(p.pane_bins + slot) == (long long)(q * (uint64_t)p.slide);
+  if (ok && p.keyed) {
+    const uint32_t pos = dict_home((uint64_t)key, p.dict.cap);
+    const ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(p.dict.slots + pos));
+    id = resolve_id(p.dict, key, raw.x, (uint32_t)raw.y);
+    ok = id < ID_OVERFLOW;
   }
-  uint32_t id = probed ? resolve_id(p, r.key, raw, pos) : 0u;
-  if (id >= ID_OVERFLOW) {
-    defer_row<NV>(p, r);
+  if (!ok) {
+    defer_row(p, key, ts, v0, v1, v2, v3);
     return;
   }
   unsigned long long* pane =
       reinterpret_cast<unsigned long long*>(__ldg(reinterpret_cast<const unsigned long long*>(p.pane_ptrs + slot)));
   atomicAdd(p.slot_rows + slot, 1ull);
-  accumulate<NV>(p, r, pane, id);
+  const Vals v{v0, v1, v2, v3};
+  accumulate<NV, SIG>(p, v, pane, id);
 }
+
+// Per-thread view of the pane ring: the pane (quotient ts / slide) of the previous row lives in
+// registers, so the common case -- a warp's rows all in one pane -- touches neither the ring tables nor
+// any shared counter.
+struct PaneCache {
+  uint64_t q = ~0ull;                  // cached pane number
+  unsigned long long* ptr = nullptr;   // its block, or nullptr when the pane is not resident
+  uint32_t cnt = 0;                    // on-time rows this thread aggregated into it
+};
 
 // Warp-combined publication of the per-thread on-time row counts (all 32 lanes must call).
 __device__ __forceinline__ void flush_counts(const IngestParams& p, PaneCache& pc, int lane) {
-  const unsigned int peers = __match_any_sync(0xffffffffu, pc.slot);
+  const unsigned int peers = __match_any_sync(0xffffffffu, pc.q);
   const unsigned int total = __reduce_add_sync(peers, pc.cnt);
-  if (total && (__ffs(peers) - 1) == lane) atomicAdd(p.slot_rows + pc.slot, (unsigned long long)total);
+  if (total && (__ffs(peers) - 1) == lane)
+    atomicAdd(p.slot_rows + ((uint32_t)pc.q & p.ring_mask), (unsigned long long)total);
   pc.cnt = 0;
 }
 
-template <int NV>
-__global__ void __launch_bounds__(THREADS, 5) ingest_kernel(const __grid_constant__ IngestParams p) {
-  __shared__ unsigned long long s_late;
-  __shared__ long long s_max_ts;
+// One on-time-or-late row on the hot path.
+template <int NV, int SIG>
+__device__ __forceinline__ void hot_row(const IngestParams& p, PaneCache& pc, uint64_t& maxq, bool keyed, long long key,
+                                        long long ts, uint64_t q, const Vals& v, unsigned long long k0, uint32_t id0) {
+  uint32_t id = ID_OVERFLOW;
+  if (q == pc.q && pc.ptr != nullptr) id = keyed ? resolve_id(p.dict, key, k0, id0) : 0u;
+  if (id < ID_OVERFLOW) {
+    ++pc.cnt;
+    accumulate<NV, SIG>(p, v, pc.ptr, id);
+  } else {
+    maxq = max(maxq, q);
+    slow_row<NV, SIG>(p, key, ts, q, v.v0, v.v1, v.v2, v.v3);
+  }
+}
+
+#ifndef AB_INGEST_MIN_BLOCKS
+#define AB_INGEST_MIN_BLOCKS 6
+#endif
+template <int NV, int SIG>
+__global__ void __launch_bounds__(THREADS, AB_INGEST_MIN_BLOCKS) ingest_kernel(const __grid_constant__ IngestParams p) {
+  __shared__ unsigned long long s_late, s_maxq;
   __shared__ unsigned int s_done;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   if (tid == 0) {
     s_late = 0;
-    s_max_ts = LLONG_MIN;
+    s_maxq = 0;
     s_done = 0;
   }
   __syncthreads();  // the only block barrier: all warps arrive together at kernel start
 
   PaneCache pc;
-  Tally tl;
+  uint32_t late = 0;
+  uint64_t maxq = 0;  // newest on-time pane seen (0 = none: pane 0 is 1970)
   const FastDivU64 sd = p.slide_div;
   const bool keyed = p.keyed != 0;
 
@@ -389,108 +414,46 @@ __global__ void __launch_bounds__(THREADS, 5) ingest_kernel(const __grid_constan
     const long long base = (tile - __ldg(&sg->tile_start)) * TILE;
     const long long nrem = __ldg(&sg->n) - base;
     const int cnt = nrem < TILE ? (int)nrem : TILE;
-    const long long* kcol = ldg_ptr(&sg->key);
-    const long long* tcol = ldg_ptr(&sg->ts);
 
-    if (cnt == TILE && __ldg(&sg->vec_ok)) {
+    // One row per lane per iteration: a warp instruction covers 256 contiguous bytes per column, and
+    // with eight resident blocks per SM there are 2048 independent probe chains in flight per SM
+    // (profiles/r01_probe2.txt: occupancy beats rows-per-thread for the scattered part).
+    // The trip count is uniform so that the warp votes below stay convergent in tail tiles.
 #pragma unroll 1
-      for (int j = 0; j < PAIRS; ++j) {
-        // 128-bit streaming loads: a warp instruction covers 512 contiguous bytes per column
-        const long long r0 = base + 2ll * (j * THREADS + tid);
-        Row<NV> ra, rb;
-        const longlong2 t2 = __ldcs(reinterpret_cast<const longlong2*>(tcol + r0));
-        ra.ts = t2.x;
-        rb.ts = t2.y;
-        ra.key = 0;
-        rb.key = 0;
-        ulonglong2 pa = {0, 0}, pb = {0, 0};
-        uint32_t posa = 0, posb = 0;
+    for (int i = tid; i < TILE; i += THREADS) {
+      const bool valid = i < cnt;
+      long long key = 0, ts = 0;
+      long long v[NV > 0 ? NV : 1] = {0};
+      ulonglong2 raw = {0, 0};
+      if (valid) {
         if (keyed) {
-          const longlong2 k2 = __ldcs(reinterpret_cast<const longlong2*>(kcol + r0));
-          ra.key = k2.x;
-          rb.key = k2.y;
-          // both dictionary probes are in flight before either is consumed
-          posa = (uint32_t)mix64((uint64_t)ra.key) & p.dict.mask;
-          posb = (uint32_t)mix64((uint64_t)rb.key) & p.dict.mask;
-          pa = __ldcg(reinterpret_cast<const ulonglong2*>(p.dict.slots + posa));
-          pb = __ldcg(reinterpret_cast<const ulonglong2*>(p.dict.slots + posb));
+          key = __ldcs(ldg_ptr(&sg->key) + base + i);
+          raw = __ldcg(reinterpret_cast<const ulonglong2*>(p.dict.slots + dict_home((uint64_t)key, p.dict.cap)));
         }
+        ts = __ldcs(ldg_ptr(&sg->ts) + base + i);
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const longlong2 v2 = __ldcs(reinterpret_cast<const longlong2*>(ldg_ptr(&sg->val[v]) + r0));
-          ra.val[v] = v2.x;
-          rb.val[v] = v2.y;
-        }
-        // K1: bin = ts - ts % slide (tumbling_aggregating_window.rs:65-73)
-        const uint64_t qa = sd.div((uint64_t)ra.ts), qb = sd.div((uint64_t)rb.ts);
-        const long long bina = (long long)(qa * (uint64_t)p.slide), binb = (long long)(qb * (uint64_t)p.slide);
-        // K7: late bins are dropped (tumbling :282-291, sliding :631-633)
-        const bool livea = bina >= p.late_bin, liveb = binb >= p.late_bin;
-        tl.late += (livea ? 0u : 1u) + (liveb ? 0u : 1u);
-        if (livea) tl.max_ts = max(tl.max_ts, ra.ts);
-        if (liveb) tl.max_ts = max(tl.max_ts, rb.ts);
-        // refresh the cached pane when this thread's first live row moved to another pane; the vote
-        // keeps the warp-combined count flush convergent
-        const uint32_t want = (uint32_t)(livea ? qa : qb) & p.ring_mask;
-        if (__any_sync(0xffffffffu, (livea || liveb) && want != pc.slot)) {
-          flush_counts(p, pc, lane);
-          if (livea || liveb) {
-            pc.slot = want;
-            pc.bin = __ldg(p.pane_bins + want);
-            pc.ptr = reinterpret_cast<unsigned long long*>(
-                __ldg(reinterpret_cast<const unsigned long long*>(p.pane_ptrs + want)));
-          }
-        }
-        if (livea) {
-          if (bina == pc.bin) {
-            const uint32_t id = keyed ? resolve_id(p, ra.key, pa, posa) : 0u;
-            if (id < ID_OVERFLOW) {
-              ++pc.cnt;
-              accumulate<NV>(p, ra, pc.ptr, id);
-            } else {
-              defer_row<NV>(p, ra);
-            }
-          } else {
-            slow_row<NV>(p, ra, qa, bina, keyed, pa, posa);
-          }
-        }
-        if (liveb) {
-          if (binb == pc.bin) {
-            const uint32_t id = keyed ? resolve_id(p, rb.key, pb, posb) : 0u;
-            if (id < ID_OVERFLOW) {
-              ++pc.cnt;
-              accumulate<NV>(p, rb, pc.ptr, id);
-            } else {
-              defer_row<NV>(p, rb);
-            }
-          } else {
-            slow_row<NV>(p, rb, qb, binb, keyed, pb, posb);
-          }
+        for (int x = 0; x < NV; ++x) v[x] = __ldcs(ldg_ptr(&sg->val[x]) + base + i);
+      }
+      // K1: pane = ts / slide, i.e. bin = ts - ts % slide (tumbling_aggregating_window.rs:65-73)
+      const uint64_t q = sd.div((uint64_t)ts);
+      // K7: late bins are dropped (tumbling :282-291, sliding :631-633)
+      const bool live = valid && q >= p.late_q;
+      late += (valid && !live) ? 1u : 0u;
+      // refresh the cached pane when this lane moved to another pane; the vote keeps the warp-combined
+      // count flush convergent
+      if (__any_sync(0xffffffffu, live && q != pc.q)) {
+        flush_counts(p, pc, lane);
+        if (live) {
+          const uint32_t slot = (uint32_t)q & p.ring_mask;
+          const bool resident = __ldg(p.pane_bins + slot) == (long long)(q * (uint64_t)p.slide);
+          pc.q = q;
+          pc.ptr = resident ? reinterpret_cast<unsigned long long*>(
+                                  __ldg(reinterpret_cast<const unsigned long long*>(p.pane_ptrs + slot)))
+                            : nullptr;
+          maxq = max(maxq, q);
         }
       }
-    } else {
-      // tail tile / unaligned segment / tiny batch: scalar loads, uncached ring lookups
-      for (int i = tid; i < cnt; i += THREADS) {
-        Row<NV> r;
-        r.ts = __ldcs(tcol + base + i);
-        r.key = keyed ? __ldcs(kcol + base + i) : 0;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) r.val[v] = __ldcs(ldg_ptr(&sg->val[v]) + base + i);
-        ulonglong2 raw = {0, 0};
-        uint32_t pos = 0;
-        if (keyed) {
-          pos = (uint32_t)mix64((uint64_t)r.key) & p.dict.mask;
-          raw = __ldcg(reinterpret_cast<const ulonglong2*>(p.dict.slots + pos));
-        }
-        const uint64_t q = sd.div((uint64_t)r.ts);
-        const long long bin = (long long)(q * (uint64_t)p.slide);
-        if (bin < p.late_bin) {
-          ++tl.late;
-          continue;
-        }
-        tl.max_ts = max(tl.max_ts, r.ts);
-        slow_row<NV>(p, r, q, bin, keyed, raw, pos);
-      }
+      if (live) hot_row<NV, SIG>(p, pc, maxq, keyed, key, ts, q, pack_vals<NV>(v), raw.x, (uint32_t)raw.y);
     }
   }
 
@@ -498,22 +461,22 @@ __global__ void __launch_bounds__(THREADS, 5) ingest_kernel(const __grid_constan
   __syncwarp();
   flush_counts(p, pc, lane);
   // bookkeeping counters: warp reduce -> shared -> the last warp of the block publishes
-  unsigned long long late = tl.late;
+  unsigned long long wl = late;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    late += __shfl_xor_sync(0xffffffffu, late, o);
-    tl.max_ts = max(tl.max_ts, __shfl_xor_sync(0xffffffffu, tl.max_ts, o));
+    wl += __shfl_xor_sync(0xffffffffu, wl, o);
+    maxq = max(maxq, __shfl_xor_sync(0xffffffffu, maxq, o));
   }
   if (lane == 0) {
-    if (late) atomicAdd(&s_late, late);
-    if (tl.max_ts != LLONG_MIN) atomicMax(&s_max_ts, tl.max_ts);
+    if (wl) atomicAdd(&s_late, wl);
+    if (maxq) atomicMax(&s_maxq, (unsigned long long)maxq);
     __threadfence_block();
     if (atomicAdd(&s_done, 1u) == THREADS / 32 - 1) {
       __threadfence_block();
       const unsigned long long bl = *(volatile unsigned long long*)&s_late;
-      const long long mx = *(volatile long long*)&s_max_ts;
+      const unsigned long long mq = *(volatile unsigned long long*)&s_maxq;
       if (bl) atomicAdd(&p.counters->late_rows, bl);
-      if (mx != LLONG_MIN) atomicMax(&p.counters->max_ts, mx);
+      if (mq) atomicMax(&p.counters->max_q, mq);
     }
   }
 }
@@ -539,7 +502,7 @@ __global__ void ingest_partial_kernel(const __grid_constant__ PartialParams p) {
   for (; i < p.n; i += stride) {
     uint32_t id = 0;
     if (p.keyed) {
-      id = dict_lookup_insert(p.dict, p.key[i]);
+      id = p.key[i] == EMPTY_KEY ? 0u : dict_insert(p.dict, p.key[i], dict_home((uint64_t)p.key[i], p.dict.cap));
       if (id >= ID_OVERFLOW) {
         atomicAdd(&p.counters->lost, 1ull);
         continue;
@@ -782,6 +745,8 @@ struct Pane {
   int slot = -1;
   bool in_tier = false;
   uint64_t rows = 0;  // on-time rows aggregated into this pane
+  bool exported = false;  // its state is already in the shim's state table (checkpointed / restored)
+  bool delta_exported = false;  // `frozen` is in the state table; only `dev` is new
 };
 
 struct LaunchRec {
@@ -1023,7 +988,7 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
   counters_.alloc(sizeof(Counters));
   slot_rows_.alloc(MAX_RING * sizeof(unsigned long long));
   Counters init{};
-  init.max_ts = LLONG_MIN;
+  init.max_q = 0;
   init.n_keys = 1;
   AB_CUDA(cudaMemcpyAsync(counters_.p, &init, sizeof init, cudaMemcpyHostToDevice, stream_));
   last_counters_ = init;
@@ -1089,12 +1054,10 @@ WindowAggOp::~WindowAggOp() {
   if (own_stream_ && stream_) cudaStreamDestroy(stream_);
 }
 
-// slot count: power of two >= 1.75 x ids (load factor <= 0.57; 0.5 at the expected key count)
-static uint64_t slots_for(uint64_t ids) {
-  uint64_t c = 1024;
-  while (c * 4 < ids * 7) c <<= 1;
-  return c;
-}
+// slot count: 3.5 x ids => load factor 0.25 at the expected key count (0.29 when every id is used).
+// Measured (profiles/r01_probe2.txt): the random 16-byte probe runs at 92 G/s at load 0.25 vs 72 G/s at
+// 0.5 -- shorter chains mean fewer divergent replays per warp.
+static uint64_t slots_for(uint64_t ids) { return std::max<uint64_t>(1024, ids * 7 / 2); }
 
 void WindowAggOp::alloc_dictionary(uint64_t id_cap) {
   id_cap_ = id_cap;
@@ -1186,7 +1149,7 @@ void WindowAggOp::grow_ids() {
     AB_CUDA(cudaGetLastError());
     if (n_valid > 1) {
       int blocks = (int)std::min<uint32_t>((n_valid + 255) / 256, (uint32_t)num_sms_ * 8);
-      dict_rebuild_kernel<<<blocks, 256, 0, stream_>>>(slots_.as<Slot>(), (uint32_t)(dict_cap_ - 1),
+      dict_rebuild_kernel<<<blocks, 256, 0, stream_>>>(slots_.as<Slot>(), (uint32_t)dict_cap_,
                                                        id_keys_.as<long long>(), n_valid);
       AB_CUDA(cudaGetLastError());
     }
@@ -1422,11 +1385,12 @@ void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk
   p.dict.slots = slots_.as<Slot>();
   p.dict.id_keys = id_keys_.as<long long>();
   p.dict.n_keys = (unsigned int*)((char*)counters_.p + offsetof(Counters, n_keys));
-  p.dict.mask = keyed_ ? (uint32_t)(dict_cap_ - 1) : 0;
+  p.dict.cap = keyed_ ? (uint32_t)dict_cap_ : 1;
   p.dict.id_cap = (uint32_t)std::min<uint64_t>(id_cap_, 0xFFFFFFF0ull);
   p.slide_div = FastDivU64::make((uint64_t)slide_);
   p.slide = slide_;
   p.late_bin = late_bin_;
+  p.late_q = late_bin_ == LLONG_MIN ? 0ull : (unsigned long long)late_bin_ / (unsigned long long)slide_;
   p.ring_mask = ring_ - 1;
   p.n_acc = n_acc_;
   p.pane_bins = d_pane_bins_.as<long long>();
@@ -1446,13 +1410,24 @@ void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk
   int grid = (int)std::min<long long>(tiles, (long long)num_sms_ * 8);
   if (grid < 1) grid = 1;
   if (profile_) AB_CUDA(cudaEventRecord(L.t0, stream_));
-  switch (n_vals_) {
-    case 0: ingest_kernel<0><<<grid, THREADS, 0, stream_>>>(p); break;
-    case 1: ingest_kernel<1><<<grid, THREADS, 0, stream_>>>(p); break;
-    case 2: ingest_kernel<2><<<grid, THREADS, 0, stream_>>>(p); break;
-    case 3: ingest_kernel<3><<<grid, THREADS, 0, stream_>>>(p); break;
-    default: ingest_kernel<4><<<grid, THREADS, 0, stream_>>>(p); break;
+  // straight-line specialisations for the common accumulator signatures, generic otherwise
+  int sig = GENERIC_SIG;
+  if (n_vals_ <= 1 && n_acc_ <= 4) {
+    int k[3] = {0, 0, 0};
+    for (int a = 1; a < n_acc_; ++a) k[a - 1] = acc_kind_[a];
+    sig = sig_of(k[0], k[1], k[2]);
   }
+#define AB_LAUNCH(NV, SIG) ingest_kernel<NV, SIG><<<grid, THREADS, 0, stream_>>>(p)
+  if (n_vals_ == 0) AB_LAUNCH(0, 0);
+  else if (n_vals_ == 1 && sig == sig_of(ACC_SUM_I64)) AB_LAUNCH(1, sig_of(ACC_SUM_I64));
+  else if (n_vals_ == 1 && sig == sig_of(ACC_SUM_F64)) AB_LAUNCH(1, sig_of(ACC_SUM_F64));
+  else if (n_vals_ == 1 && sig == sig_of(ACC_SUM_I64, ACC_SUM_F64)) AB_LAUNCH(1, sig_of(ACC_SUM_I64, ACC_SUM_F64));
+  else if (n_vals_ == 1 && sig == sig_of(ACC_MIN_I64, ACC_MAX_I64)) AB_LAUNCH(1, sig_of(ACC_MIN_I64, ACC_MAX_I64));
+  else if (n_vals_ == 1) AB_LAUNCH(1, GENERIC_SIG);
+  else if (n_vals_ == 2) AB_LAUNCH(2, GENERIC_SIG);
+  else if (n_vals_ == 3) AB_LAUNCH(3, GENERIC_SIG);
+  else AB_LAUNCH(4, GENERIC_SIG);
+#undef AB_LAUNCH
   AB_CUDA(cudaGetLastError());
   if (profile_) AB_CUDA(cudaEventRecord(L.t1, stream_));
   ++st_.kernel_launches;
@@ -1500,7 +1475,7 @@ void WindowAggOp::absorb(int li) {
   last_counters_ = c;
   have_counters_ = true;
   n_keys_host_ = (uint32_t)std::min<uint64_t>(c.n_keys, id_cap_);
-  if (c.max_ts != LLONG_MIN) max_bin_seen_ = std::max<int64_t>(max_bin_seen_, bin_start(c.max_ts, slide_));
+  if (c.max_q) max_bin_seen_ = std::max<int64_t>(max_bin_seen_, (int64_t)(c.max_q * (uint64_t)slide_));
   for (uint32_t s = 0; s < ring_; ++s) {
     if (L.h_slot_rows[s]) {
       AB_REQUIRE(h_pane_bins_[s] != FREE_BIN, ARROYO_B200_RUNTIME, "touched a free ring slot");
@@ -1929,6 +1904,7 @@ void WindowAggOp::handle_checkpoint(int64_t wm, BatchesPriv* out) {
     int64_t n = run_emit({p.dev}, 1, false, true, 0, 0, s.a, os);
     if (n > 0) export_partial(os, n, out);
     // fold into the frozen block so the next checkpoint writes only new rows
+    p.delta_exported = true;
     if (!p.frozen) p.frozen = acquire_block();
     FoldParams fp{};
     fp.active = p.dev;
@@ -1941,6 +1917,21 @@ void WindowAggOp::handle_checkpoint(int64_t wm, BatchesPriv* out) {
     fold_kernel<<<std::max(grid, 1), 256, 0, stream_>>>(fp);
     AB_CUDA(cudaGetLastError());
     ++st_.kernel_launches;
+  }
+  // Panes that closed since the last checkpoint: the reference inserts their partial batches into table
+  // "t" when it closes them (sliding :133-158); here they stay on the device and are handed to the shim
+  // at the checkpoint, which is when the table is persisted -- restore sees the same table contents.
+  for (auto& kv : panes_) {
+    Pane& p = kv.second;
+    if (!p.in_tier || p.exported) continue;
+    // what the table does not have yet: the active block, plus the frozen one unless an earlier
+    // checkpoint (or the restore) already wrote it
+    std::vector<const unsigned long long*> blocks{p.dev};
+    if (p.frozen && !p.delta_exported) blocks.push_back(p.frozen);
+    OutSet* os = out_set(0, std::max<uint64_t>(n_keys_host_, 1));
+    int64_t n = run_emit(blocks, (int)blocks.size(), false, true, 0, 0, kv.first, os);
+    if (n > 0) export_partial(os, n, out);
+    p.exported = true;
   }
   AB_CUDA(cudaStreamSynchronize(stream_));
 }
@@ -1972,6 +1963,8 @@ void WindowAggOp::on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, i
     if (sliding_) to_tier = sliding_planner_->restore_pane(ts);
     else tumbling_->restore(bin);
     if (to_tier) p.in_tier = true;
+    p.exported = to_tier;
+    p.delta_exported = true;
     // upload columns
     PartialParams pp{};
     pp.n = rows;
@@ -2013,7 +2006,7 @@ void WindowAggOp::on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, i
     pp.dict.slots = slots_.as<Slot>();
     pp.dict.id_keys = id_keys_.as<long long>();
     pp.dict.n_keys = (unsigned int*)((char*)counters_.p + offsetof(Counters, n_keys));
-    pp.dict.mask = keyed_ ? (uint32_t)(dict_cap_ - 1) : 0;
+    pp.dict.cap = keyed_ ? (uint32_t)dict_cap_ : 1;
     pp.dict.id_cap = (uint32_t)id_cap_;
     pp.pane = panes_.at(bin).frozen;
     pp.id_cap = id_cap_;
