@@ -1,7 +1,648 @@
-// Instant (windowed) join -- implemented in a later milestone of this round.
+// Instant (windowed) join on sm_100a.
+//
+// Replaces InstantJoin (arroyo-worker/src/arrow/instant_join.rs:109-172 process_side, :241-283
+// process_batch_index / handle_watermark) and the DataFusion HashJoinExec it runs once per window instant
+// (K10).  Both inputs carry window-stamped rows: every row of a window has the same `_timestamp`, and only
+// rows with equal `_timestamp` may join.  The reference keeps one join exec per distinct timestamp; here
+// rows of both sides are appended to device arenas and, at a watermark, every row with
+// `_timestamp < watermark` is joined in ONE build / probe pass on the composite key (_timestamp, key):
+// equal timestamps are part of the equality, so the result is the union of the per-instant joins.
+//
+//   build   : right rows -> open-addressing table of row indices (CAS claim, linear probing)
+//   count   : left rows walk their chain and count matches (outer joins: unmatched rows count 1)
+//   scan    : exclusive prefix sum of the counts = output offsets
+//   write   : left rows walk again and write (left idx, right idx) pairs; matched right rows are flagged
+//   append  : right / full joins: unmatched right rows appended with left idx = -1
+//   gather  : output columns materialised from the pairs (+ validity bytes for the missing side),
+//             `_timestamp = max(l._timestamp, r._timestamp)` (arroyo-planner/src/plan/join.rs:165-185)
+//   compact : rows with `_timestamp >= watermark` are kept for later watermarks
+//
+// Output = [left payload cols..., right payload cols..., _timestamp]; the leading `_key_*` routing copies
+// of each side are stripped like `unkeyed_batch` does (arroyo-rpc/src/df.rs:359-367).
+#include <algorithm>
+#include <climits>
+
 #include "op.h"
+
 namespace ab {
-OpBase* make_instant_join_op(const ArroyoB200OpConfig&) {
-  throw Error(ARROYO_B200_UNSUPPORTED, "InstantJoin is not built yet: use the stock operator");
+namespace {
+
+constexpr int JT = 256;
+
+__device__ __forceinline__ uint64_t pair_hash(long long key, long long ts) {
+  return mix64((uint64_t)key ^ mix64((uint64_t)ts));
 }
+
+// eligible[i] = ts[i] < wm; also min timestamp of all rows (panic check) and the eligible count
+__global__ void mark_kernel(const long long* __restrict__ ts, long long n, long long wm, unsigned char* __restrict__ elig,
+                            unsigned long long* __restrict__ n_elig, long long* __restrict__ min_ts) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  unsigned long long c = 0;
+  long long mn = LLONG_MAX;
+  for (; i < n; i += stride) {
+    long long t = ts[i];
+    bool e = t < wm;
+    elig[i] = e ? 1 : 0;
+    c += e ? 1 : 0;
+    mn = min(mn, t);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (c) atomicAdd(n_elig, c);
+    if (mn != LLONG_MAX) atomicMin(min_ts, mn);
+  }
+}
+
+__global__ void build_kernel(const long long* __restrict__ key, const long long* __restrict__ ts,
+                             const unsigned char* __restrict__ elig, long long n, unsigned int* __restrict__ tab,
+                             uint32_t mask) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    if (!elig[i]) continue;
+    uint32_t pos = (uint32_t)pair_hash(key[i], ts[i]) & mask;
+    while (atomicCAS(&tab[pos], 0u, (unsigned int)i + 1u) != 0u) pos = (pos + 1) & mask;
+  }
+}
+
+// pass 0: cnt[i] = number of output rows of left row i; pass 1: write the pairs at off[i]
+template <int PASS>
+__global__ void probe_kernel(const long long* __restrict__ lkey, const long long* __restrict__ lts,
+                             const unsigned char* __restrict__ lelig, long long n_left,
+                             const long long* __restrict__ rkey, const long long* __restrict__ rts,
+                             const unsigned int* __restrict__ tab, uint32_t mask, int keep_unmatched_left,
+                             unsigned int* __restrict__ cnt, const unsigned long long* __restrict__ off,
+                             int* __restrict__ out_l, int* __restrict__ out_r, unsigned char* __restrict__ r_matched) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n_left; i += stride) {
+    if (!lelig[i]) {
+      if (PASS == 0) cnt[i] = 0;
+      continue;
+    }
+    const long long k = lkey[i], t = lts[i];
+    uint32_t pos = (uint32_t)pair_hash(k, t) & mask;
+    unsigned int c = 0;
+    unsigned long long o = PASS == 1 ? off[i] : 0;
+    while (true) {
+      unsigned int e = tab[pos];
+      if (e == 0) break;
+      unsigned int j = e - 1;
+      if (rkey[j] == k && rts[j] == t) {
+        if (PASS == 1) {
+          out_l[o + c] = (int)i;
+          out_r[o + c] = (int)j;
+          r_matched[j] = 1;
+        }
+        ++c;
+      }
+      pos = (pos + 1) & mask;
+    }
+    if (c == 0 && keep_unmatched_left) {
+      if (PASS == 1) {
+        out_l[o] = (int)i;
+        out_r[o] = -1;
+      }
+      c = 1;
+    }
+    if (PASS == 0) cnt[i] = c;
+  }
+}
+
+// Exclusive scan of 32-bit counts into 64-bit offsets: block sums, serial scan of the (few) block sums,
+// then per-block scan.  n is at most a few hundred million: 1024-element blocks.
+constexpr int SCAN_BLOCK = 1024;
+__global__ void scan_block_sums(const unsigned int* __restrict__ in, long long n, unsigned long long* __restrict__ sums) {
+  __shared__ unsigned long long s[32];
+  long long i = (long long)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+  unsigned long long v = i < n ? in[i] : 0;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned long long t = s[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) sums[blockIdx.x] = t;
+  }
+}
+__global__ void scan_sums_serial(unsigned long long* sums, long long n_blocks, unsigned long long* total) {
+  unsigned long long acc = 0;
+  for (long long b = 0; b < n_blocks; ++b) {
+    unsigned long long v = sums[b];
+    sums[b] = acc;
+    acc += v;
+  }
+  *total = acc;
+}
+__global__ void scan_apply(const unsigned int* __restrict__ in, long long n, const unsigned long long* __restrict__ sums,
+                           unsigned long long* __restrict__ out) {
+  __shared__ unsigned long long s_warp[32];
+  long long i = (long long)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+  unsigned long long v = i < n ? in[i] : 0;
+  unsigned long long x = v;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) s_warp[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    unsigned long long t = s_warp[lane];
+    unsigned long long u = t;
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long y = __shfl_up_sync(0xffffffffu, u, o);
+      if (lane >= o) u += y;
+    }
+    s_warp[lane] = u - t;
+  }
+  __syncthreads();
+  if (i < n) out[i] = sums[blockIdx.x] + s_warp[w] + x - v;
+}
+
+// right / full joins: eligible right rows nobody matched, appended after the probe output
+__global__ void append_unmatched_kernel(const unsigned char* __restrict__ elig, const unsigned char* __restrict__ matched,
+                                        long long n, unsigned long long* __restrict__ cursor, int* __restrict__ out_l,
+                                        int* __restrict__ out_r) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    bool take = elig[i] && !matched[i];
+    unsigned int b = __ballot_sync(__activemask(), take);
+    if (!take) continue;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(b) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(b));
+    base = __shfl_sync(b, base, leader);
+    unsigned long long o = base + __popc(b & ((1u << lane) - 1u));
+    out_l[o] = -1;
+    out_r[o] = (int)i;
+  }
+}
+
+struct GatherParams {
+  const int* idx;          // pair side to read
+  const long long* src;    // source column
+  long long* dst;
+  unsigned char* valid;    // optional validity bytes
+  long long n;
+};
+__global__ void gather_kernel(const __grid_constant__ GatherParams p) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < p.n; i += stride) {
+    int j = p.idx[i];
+    p.dst[i] = j >= 0 ? p.src[j] : 0;
+    if (p.valid) p.valid[i] = j >= 0 ? 1 : 0;
+  }
+}
+__global__ void gather_ts_kernel(const int* __restrict__ il, const int* __restrict__ ir, const long long* __restrict__ lts,
+                                 const long long* __restrict__ rts, long long* __restrict__ dst, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    int a = il[i], b = ir[i];
+    long long ta = a >= 0 ? lts[a] : LLONG_MIN, tb = b >= 0 ? rts[b] : LLONG_MIN;
+    dst[i] = max(ta, tb);
+  }
+}
+// validity bytes -> Arrow validity bitmap (LSB first)
+__global__ void pack_bits_kernel(const unsigned char* __restrict__ bytes, long long n, unsigned int* __restrict__ words) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long n_pad = (n + 31) / 32 * 32;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n_pad; i += stride) {
+    bool v = i < n && bytes[i];
+    unsigned int b = __ballot_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) words[i >> 5] = b;
+  }
+}
+// keep[i] = !elig[i] as counts for the compaction scan
+__global__ void keep_counts_kernel(const unsigned char* __restrict__ elig, long long n, unsigned int* __restrict__ cnt) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) cnt[i] = elig[i] ? 0u : 1u;
+}
+__global__ void compact_kernel(const long long* __restrict__ src, const unsigned char* __restrict__ elig,
+                               const unsigned long long* __restrict__ off, long long n, long long* __restrict__ dst) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride)
+    if (!elig[i]) dst[off[i]] = src[i];
+}
+
+struct Side {
+  int n_cols = 0, ts_col = 0, key_col = 0, n_routing = 0;
+  std::vector<int> payload;             // input column indices that appear in the output
+  std::vector<std::string> formats;     // Arrow format per input column
+  std::vector<DevBuf> cols, cols_alt;   // arenas (and the compaction target)
+  int64_t n = 0, cap = 0;
+  DevBuf elig, cnt, off;
+  int64_t scratch_cap = 0;
+};
+
+class InstantJoinOp final : public OpBase {
+ public:
+  explicit InstantJoinOp(const ArroyoB200OpConfig& c);
+  ~InstantJoinOp() override;
+  void on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, int64_t, int64_t) override {
+    AB_REQUIRE(n == 0, ARROYO_B200_UNSUPPORTED, "InstantJoin restore: replay the 'left'/'right' tables through process_batch");
+    (void)state;
+    (void)schemas;
+  }
+  void process_batch(uint32_t index, uint32_t in_partitions, ArrowArray* batch, const ArrowSchema* schema) override;
+  void process_device_batch(uint32_t index, uint32_t in_partitions, const uint64_t* cols, int32_t n_cols,
+                            int64_t n_rows) override;
+  void handle_watermark(int64_t wm, BatchesPriv* out_host, std::vector<ArroyoB200DeviceBatch>* out_dev) override;
+  void handle_checkpoint(int64_t, BatchesPriv*) override { flush(); }  // tables left/right are written by the shim
+  void on_close(int, BatchesPriv*) override { flush(); }
+  void flush() override {
+    AB_CUDA(cudaSetDevice(device_));
+    AB_CUDA(cudaStreamSynchronize(stream_));
+    release_inputs();
+  }
+  void stats(ArroyoB200Stats* out) override { *out = st_; }
+
+ private:
+  int device_;
+  cudaStream_t stream_ = nullptr;
+  bool own_stream_ = false;
+  int num_sms_ = 148;
+  int join_type_;
+  Side side_[2];
+  int64_t last_wm_ = INT64_MIN;
+  DevBuf scalars_;  // [0] n_elig L, [1] n_elig R, [2] min_ts L, [3] min_ts R, [4] total, [5] cursor
+  PinnedBuf h_scalars_;
+  DevBuf tab_, sums_, pair_l_, pair_r_, r_matched_;
+  int64_t pair_cap_ = 0;
+  std::vector<DevBuf> out_cols_;
+  std::vector<DevBuf> out_valid_;
+  DevBuf out_ts_;
+  std::vector<std::pair<cudaEvent_t, ArrowArray>> pending_;
+  ArroyoB200Stats st_{};
+
+  void release_inputs();
+  void reserve(Side& s, int64_t extra);
+  void append(Side& s, const uint64_t* const* cols, int64_t n, bool host);
+  int grid_for(int64_t n) const { return (int)std::max<int64_t>(1, std::min<int64_t>((n + JT - 1) / JT, (int64_t)num_sms_ * 8)); }
+  void exclusive_scan(const unsigned int* cnt, int64_t n, unsigned long long* off, unsigned long long* total_dev);
+  void compact(Side& s);
+};
+
+InstantJoinOp::InstantJoinOp(const ArroyoB200OpConfig& c) {
+  cfg = c;
+  name = "InstantJoin";
+  join_type_ = c.join_type;
+  AB_REQUIRE(join_type_ >= 0 && join_type_ <= 3, ARROYO_B200_INVALID_ARGUMENT, "bad join type");
+  auto init_side = [&](Side& s, int n_cols, int ts_col, int key_col, int n_routing) {
+    AB_REQUIRE(n_cols >= 2 && n_cols <= ARROYO_B200_MAX_COLS, ARROYO_B200_INVALID_ARGUMENT, "bad join side n_cols");
+    AB_REQUIRE(ts_col >= 0 && ts_col < n_cols && key_col >= 0 && key_col < n_cols && n_routing >= 0 && n_routing < n_cols,
+               ARROYO_B200_INVALID_ARGUMENT, "bad join side columns");
+    s.n_cols = n_cols;
+    s.ts_col = ts_col;
+    s.key_col = key_col;
+    s.n_routing = n_routing;
+    for (int i = n_routing; i < n_cols; ++i)
+      if (i != ts_col) s.payload.push_back(i);
+    s.cols.resize(n_cols);
+    s.cols_alt.resize(n_cols);
+    s.formats.assign(n_cols, "l");
+    s.formats[ts_col] = "tsn:";
+  };
+  init_side(side_[0], c.n_cols, c.timestamp_col, c.left_key_col, c.left_n_routing);
+  init_side(side_[1], c.right_n_cols, c.right_timestamp_col, c.right_key_col, c.right_n_routing);
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0)
+    throw Error(ARROYO_B200_FATAL, "no CUDA device available: libarroyo_b200 has no CPU fallback");
+  device_ = c.device;
+  AB_REQUIRE(device_ >= 0 && device_ < count, ARROYO_B200_INVALID_ARGUMENT, "bad device ordinal");
+  AB_CUDA(cudaSetDevice(device_));
+  cudaDeviceProp prop{};
+  AB_CUDA(cudaGetDeviceProperties(&prop, device_));
+  num_sms_ = prop.multiProcessorCount;
+  if (c.stream) stream_ = (cudaStream_t)c.stream;
+  else {
+    AB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    own_stream_ = true;
+  }
+  scalars_.alloc(8 * sizeof(unsigned long long));
+  h_scalars_.alloc(8 * sizeof(unsigned long long));
+}
+
+InstantJoinOp::~InstantJoinOp() {
+  cudaSetDevice(device_);
+  cudaStreamSynchronize(stream_);
+  for (auto& p : pending_) {
+    if (p.second.release) p.second.release(&p.second);
+    cudaEventDestroy(p.first);
+  }
+  if (own_stream_ && stream_) cudaStreamDestroy(stream_);
+}
+
+void InstantJoinOp::release_inputs() {
+  for (auto& p : pending_) {
+    cudaEventSynchronize(p.first);
+    if (p.second.release) p.second.release(&p.second);
+    cudaEventDestroy(p.first);
+  }
+  pending_.clear();
+}
+
+void InstantJoinOp::reserve(Side& s, int64_t extra) {
+  if (s.n + extra <= s.cap) return;
+  int64_t nc = std::max<int64_t>(s.cap * 2, 1 << 16);
+  while (nc < s.n + extra) nc *= 2;
+  for (int c = 0; c < s.n_cols; ++c) {
+    if (c < s.n_routing) continue;
+    DevBuf nb((size_t)nc * 8);
+    if (s.n) AB_CUDA(cudaMemcpyAsync(nb.p, s.cols[c].p, (size_t)s.n * 8, cudaMemcpyDeviceToDevice, stream_));
+    AB_CUDA(cudaStreamSynchronize(stream_));
+    s.cols[c] = std::move(nb);
+    s.cols_alt[c].release();
+  }
+  s.cap = nc;
+}
+
+void InstantJoinOp::append(Side& s, const uint64_t* const* cols, int64_t n, bool host) {
+  reserve(s, n);
+  for (int c = s.n_routing; c < s.n_cols; ++c)
+    AB_CUDA(cudaMemcpyAsync(s.cols[c].as<long long>() + s.n, cols[c], (size_t)n * 8,
+                            host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream_));
+  if (host) st_.h2d_bytes += (uint64_t)n * 8 * (uint64_t)(s.n_cols - s.n_routing);
+  s.n += n;
+  st_.rows_in += (uint64_t)n;
+}
+
+void InstantJoinOp::process_batch(uint32_t index, uint32_t in_partitions, ArrowArray* batch, const ArrowSchema* schema) {
+  AB_CUDA(cudaSetDevice(device_));
+  AB_REQUIRE(in_partitions >= 2 && in_partitions % 2 == 0, ARROYO_B200_INVALID_ARGUMENT, "join needs an even number of inputs");
+  const int sd = (int)(index / (in_partitions / 2));  // instant_join.rs:249-253
+  AB_REQUIRE(sd == 0 || sd == 1, ARROYO_B200_INVALID_ARGUMENT, "bad input index");
+  Side& s = side_[sd];
+  int64_t n = 0;
+  std::vector<InColumn> cols = import_batch(batch, schema, &n);
+  AB_REQUIRE((int)cols.size() == s.n_cols, ARROYO_B200_INVALID_ARGUMENT, "join side has the wrong number of columns");
+  AB_REQUIRE(n > 0, ARROYO_B200_PANIC, "should have max timestamp (empty batch; instant_join.rs:123)");
+  for (int c = 0; c < s.n_cols; ++c) s.formats[c] = cols[c].format;
+  const uint64_t* ptrs[ARROYO_B200_MAX_COLS];
+  for (int c = 0; c < s.n_cols; ++c) ptrs[c] = cols[c].data;
+  append(s, ptrs, n, true);
+  cudaEvent_t ev;
+  AB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  AB_CUDA(cudaEventRecord(ev, stream_));
+  pending_.emplace_back(ev, *batch);
+  batch->release = nullptr;
+}
+
+void InstantJoinOp::process_device_batch(uint32_t index, uint32_t in_partitions, const uint64_t* cols, int32_t n_cols,
+                                         int64_t n_rows) {
+  AB_CUDA(cudaSetDevice(device_));
+  AB_REQUIRE(in_partitions >= 2 && in_partitions % 2 == 0, ARROYO_B200_INVALID_ARGUMENT, "join needs an even number of inputs");
+  const int sd = (int)(index / (in_partitions / 2));
+  Side& s = side_[sd];
+  AB_REQUIRE(n_cols == s.n_cols, ARROYO_B200_INVALID_ARGUMENT, "join side has the wrong number of columns");
+  if (n_rows <= 0) return;
+  const uint64_t* ptrs[ARROYO_B200_MAX_COLS];
+  for (int c = 0; c < s.n_cols; ++c) ptrs[c] = (const uint64_t*)cols[c];
+  append(s, ptrs, n_rows, false);
+}
+
+void InstantJoinOp::exclusive_scan(const unsigned int* cnt, int64_t n, unsigned long long* off, unsigned long long* total_dev) {
+  int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  if (sums_.bytes < (size_t)std::max<int64_t>(nb, 1) * 8) sums_.alloc((size_t)std::max<int64_t>(nb, 1) * 8 * 2);
+  if (nb > 0) {
+    scan_block_sums<<<(unsigned)nb, SCAN_BLOCK, 0, stream_>>>(cnt, n, sums_.as<unsigned long long>());
+    AB_CUDA(cudaGetLastError());
+  }
+  scan_sums_serial<<<1, 1, 0, stream_>>>(sums_.as<unsigned long long>(), nb, total_dev);
+  AB_CUDA(cudaGetLastError());
+  if (nb > 0) {
+    scan_apply<<<(unsigned)nb, SCAN_BLOCK, 0, stream_>>>(cnt, n, sums_.as<unsigned long long>(), off);
+    AB_CUDA(cudaGetLastError());
+  }
+  st_.kernel_launches += 3;
+}
+
+// keep rows that did not take part in this watermark's join
+void InstantJoinOp::compact(Side& s) {
+  if (s.n == 0) return;
+  keep_counts_kernel<<<grid_for(s.n), JT, 0, stream_>>>(s.elig.as<unsigned char>(), s.n, s.cnt.as<unsigned int>());
+  AB_CUDA(cudaGetLastError());
+  unsigned long long* total = scalars_.as<unsigned long long>() + 4;
+  exclusive_scan(s.cnt.as<unsigned int>(), s.n, s.off.as<unsigned long long>(), total);
+  for (int c = s.n_routing; c < s.n_cols; ++c) {
+    if (s.cols_alt[c].bytes < (size_t)s.cap * 8) s.cols_alt[c].alloc((size_t)s.cap * 8);
+    compact_kernel<<<grid_for(s.n), JT, 0, stream_>>>(s.cols[c].as<long long>(), s.elig.as<unsigned char>(),
+                                                     s.off.as<unsigned long long>(), s.n, s.cols_alt[c].as<long long>());
+    AB_CUDA(cudaGetLastError());
+    ++st_.kernel_launches;
+  }
+  AB_CUDA(cudaMemcpyAsync(h_scalars_.as<unsigned long long>() + 4, total, 8, cudaMemcpyDeviceToHost, stream_));
+  AB_CUDA(cudaStreamSynchronize(stream_));
+  for (int c = s.n_routing; c < s.n_cols; ++c) std::swap(s.cols[c], s.cols_alt[c]);
+  s.n = (int64_t)h_scalars_.as<unsigned long long>()[4];
+  ++st_.kernel_launches;
+}
+
+static void* d2h(const void* dev, size_t bytes, cudaStream_t s, uint64_t* acc) {
+  void* h = PinnedPool::get().alloc(std::max<size_t>(bytes, 8));
+  if (bytes) AB_CUDA(cudaMemcpyAsync(h, dev, bytes, cudaMemcpyDeviceToHost, s));
+  *acc += bytes;
+  return h;
+}
+
+void InstantJoinOp::handle_watermark(int64_t wm, BatchesPriv* out_host, std::vector<ArroyoB200DeviceBatch>* out_dev) {
+  AB_CUDA(cudaSetDevice(device_));
+  Side& L = side_[0];
+  Side& R = side_[1];
+  unsigned long long* sc = scalars_.as<unsigned long long>();
+  unsigned long long init[8] = {0, 0, (unsigned long long)LLONG_MAX, (unsigned long long)LLONG_MAX, 0, 0, 0, 0};
+  AB_CUDA(cudaMemcpyAsync(sc, init, sizeof init, cudaMemcpyHostToDevice, stream_));
+  for (int sd = 0; sd < 2; ++sd) {
+    Side& s = side_[sd];
+    if (s.scratch_cap < s.cap) {
+      s.elig.alloc((size_t)s.cap);
+      s.cnt.alloc((size_t)s.cap * 4);
+      s.off.alloc((size_t)s.cap * 8);
+      s.scratch_cap = s.cap;
+    }
+    if (s.n) {
+      mark_kernel<<<grid_for(s.n), JT, 0, stream_>>>(s.cols[s.ts_col].as<long long>(), s.n, wm, s.elig.as<unsigned char>(),
+                                                    sc + sd, (long long*)(sc + 2 + sd));
+      AB_CUDA(cudaGetLastError());
+      ++st_.kernel_launches;
+    }
+  }
+  AB_CUDA(cudaMemcpyAsync(h_scalars_.p, sc, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+  AB_CUDA(cudaStreamSynchronize(stream_));
+  release_inputs();
+  const unsigned long long* hs = h_scalars_.as<unsigned long long>();
+  const int64_t nl = (int64_t)hs[0], nr = (int64_t)hs[1];
+  const int64_t min_ts = std::min<int64_t>((int64_t)hs[2], (int64_t)hs[3]);
+  // rows older than the watermark that was in force when they arrived: the reference panics (:129-139)
+  if (last_wm_ != INT64_MIN && min_ts < last_wm_ && (L.n || R.n)) {
+    // only rows appended since the previous watermark can be that old: everything older was joined then
+    throw Error(ARROYO_B200_PANIC, "shouldn't have a batch with a timestamp before the watermark (instant_join.rs:129-139)");
+  }
+  last_wm_ = wm;
+  if (nl + nr == 0) return;
+
+  const bool keep_l = join_type_ == ARROYO_B200_JOIN_LEFT || join_type_ == ARROYO_B200_JOIN_FULL;
+  const bool keep_r = join_type_ == ARROYO_B200_JOIN_RIGHT || join_type_ == ARROYO_B200_JOIN_FULL;
+  // build on the right side
+  uint64_t cap = 1024;
+  while (cap < (uint64_t)nr * 2 + 2) cap <<= 1;
+  AB_REQUIRE(cap <= (1ull << 31), ARROYO_B200_RUNTIME, "join build side too large");
+  if (tab_.bytes < cap * 4) tab_.alloc(cap * 4);
+  AB_CUDA(cudaMemsetAsync(tab_.p, 0, cap * 4, stream_));
+  if (r_matched_.bytes < (size_t)std::max<int64_t>(R.n, 1)) r_matched_.alloc((size_t)std::max<int64_t>(R.cap, 1));
+  if (R.n) AB_CUDA(cudaMemsetAsync(r_matched_.p, 0, (size_t)R.n, stream_));
+  if (nr) {
+    build_kernel<<<grid_for(R.n), JT, 0, stream_>>>(R.cols[R.key_col].as<long long>(), R.cols[R.ts_col].as<long long>(),
+                                                   R.elig.as<unsigned char>(), R.n, tab_.as<unsigned int>(), (uint32_t)(cap - 1));
+    AB_CUDA(cudaGetLastError());
+    ++st_.kernel_launches;
+  }
+  int64_t n_probe_out = 0;
+  if (L.n) {
+    probe_kernel<0><<<grid_for(L.n), JT, 0, stream_>>>(
+        L.cols[L.key_col].as<long long>(), L.cols[L.ts_col].as<long long>(), L.elig.as<unsigned char>(), L.n,
+        R.cols[R.key_col].as<long long>(), R.cols[R.ts_col].as<long long>(), tab_.as<unsigned int>(), (uint32_t)(cap - 1),
+        keep_l ? 1 : 0, L.cnt.as<unsigned int>(), nullptr, nullptr, nullptr, nullptr);
+    AB_CUDA(cudaGetLastError());
+    exclusive_scan(L.cnt.as<unsigned int>(), L.n, L.off.as<unsigned long long>(), sc + 4);
+    AB_CUDA(cudaMemcpyAsync(h_scalars_.as<unsigned long long>() + 4, sc + 4, 8, cudaMemcpyDeviceToHost, stream_));
+    AB_CUDA(cudaStreamSynchronize(stream_));
+    n_probe_out = (int64_t)h_scalars_.as<unsigned long long>()[4];
+    ++st_.kernel_launches;
+  }
+  const int64_t max_out = n_probe_out + (keep_r ? nr : 0);
+  AB_REQUIRE(max_out < (int64_t)INT_MAX, ARROYO_B200_RUNTIME, "join output too large for one watermark");
+  int64_t n_out = n_probe_out;
+  if (max_out > 0) {
+    if (pair_cap_ < max_out) {
+      pair_l_.alloc((size_t)max_out * 4);
+      pair_r_.alloc((size_t)max_out * 4);
+      pair_cap_ = max_out;
+    }
+    if (n_probe_out) {
+      probe_kernel<1><<<grid_for(L.n), JT, 0, stream_>>>(
+          L.cols[L.key_col].as<long long>(), L.cols[L.ts_col].as<long long>(), L.elig.as<unsigned char>(), L.n,
+          R.cols[R.key_col].as<long long>(), R.cols[R.ts_col].as<long long>(), tab_.as<unsigned int>(), (uint32_t)(cap - 1),
+          keep_l ? 1 : 0, nullptr, L.off.as<unsigned long long>(), pair_l_.as<int>(), pair_r_.as<int>(),
+          r_matched_.as<unsigned char>());
+      AB_CUDA(cudaGetLastError());
+      ++st_.kernel_launches;
+    }
+    if (keep_r && nr) {
+      unsigned long long cur = (unsigned long long)n_probe_out;
+      AB_CUDA(cudaMemcpyAsync(sc + 5, &cur, 8, cudaMemcpyHostToDevice, stream_));
+      append_unmatched_kernel<<<grid_for(R.n), JT, 0, stream_>>>(R.elig.as<unsigned char>(), r_matched_.as<unsigned char>(),
+                                                                R.n, sc + 5, pair_l_.as<int>(), pair_r_.as<int>());
+      AB_CUDA(cudaGetLastError());
+      AB_CUDA(cudaMemcpyAsync(h_scalars_.as<unsigned long long>() + 5, sc + 5, 8, cudaMemcpyDeviceToHost, stream_));
+      AB_CUDA(cudaStreamSynchronize(stream_));
+      n_out = (int64_t)h_scalars_.as<unsigned long long>()[5];
+      ++st_.kernel_launches;
+    }
+  }
+
+  if (n_out > 0) {
+    // gather [left payload..., right payload..., _timestamp]
+    const size_t n_oc = L.payload.size() + R.payload.size();
+    out_cols_.resize(n_oc);
+    out_valid_.resize(n_oc);
+    const bool l_nullable = keep_r, r_nullable = keep_l;
+    size_t oc = 0;
+    for (int sd = 0; sd < 2; ++sd) {
+      Side& s = side_[sd];
+      const bool nullable = sd == 0 ? l_nullable : r_nullable;
+      for (int c : s.payload) {
+        if (out_cols_[oc].bytes < (size_t)n_out * 8) out_cols_[oc].alloc((size_t)n_out * 8);
+        if (nullable && out_valid_[oc].bytes < (size_t)n_out + 64) out_valid_[oc].alloc((size_t)n_out + 64);
+        GatherParams gp{sd == 0 ? pair_l_.as<int>() : pair_r_.as<int>(), s.cols[c].as<long long>(),
+                        out_cols_[oc].as<long long>(), nullable ? out_valid_[oc].as<unsigned char>() : nullptr, n_out};
+        gather_kernel<<<grid_for(n_out), JT, 0, stream_>>>(gp);
+        AB_CUDA(cudaGetLastError());
+        ++st_.kernel_launches;
+        ++oc;
+      }
+    }
+    if (out_ts_.bytes < (size_t)n_out * 8) out_ts_.alloc((size_t)n_out * 8);
+    gather_ts_kernel<<<grid_for(n_out), JT, 0, stream_>>>(pair_l_.as<int>(), pair_r_.as<int>(), L.cols[L.ts_col].as<long long>(),
+                                                         R.cols[R.ts_col].as<long long>(), out_ts_.as<long long>(), n_out);
+    AB_CUDA(cudaGetLastError());
+    ++st_.kernel_launches;
+    st_.rows_out += (uint64_t)n_out;
+    ++st_.windows_out;
+
+    if (out_host) {
+      std::vector<OutColumn> cols;
+      oc = 0;
+      DevBuf bits;
+      for (int sd = 0; sd < 2; ++sd) {
+        Side& s = side_[sd];
+        const bool nullable = sd == 0 ? l_nullable : r_nullable;
+        for (int c : s.payload) {
+          OutColumn o;
+          o.name = std::string(sd == 0 ? "l" : "r") + std::to_string(c);
+          o.format = s.formats[c];
+          o.data = d2h(out_cols_[oc].p, (size_t)n_out * 8, stream_, &st_.d2h_bytes);
+          if (nullable) {
+            const size_t words = (size_t)((n_out + 31) / 32);
+            if (bits.bytes < words * 4) bits.alloc(words * 4 + 64);
+            pack_bits_kernel<<<grid_for(n_out), JT, 0, stream_>>>(out_valid_[oc].as<unsigned char>(), n_out, bits.as<unsigned int>());
+            AB_CUDA(cudaGetLastError());
+            o.validity = d2h(bits.p, words * 4, stream_, &st_.d2h_bytes);
+            AB_CUDA(cudaStreamSynchronize(stream_));  // `bits` is reused by the next column
+            const unsigned int* w = (const unsigned int*)o.validity;
+            int64_t set = 0;
+            for (size_t i = 0; i < words; ++i) set += __builtin_popcount(w[i]);
+            o.null_count = n_out - set;
+            o.nullable = true;
+            if (o.null_count == 0) {
+              PinnedPool::get().free(o.validity);
+              o.validity = nullptr;
+            }
+          }
+          cols.push_back(o);
+          ++oc;
+        }
+      }
+      OutColumn t;
+      t.name = "_timestamp";
+      t.format = "tsn:";
+      t.data = d2h(out_ts_.p, (size_t)n_out * 8, stream_, &st_.d2h_bytes);
+      cols.push_back(t);
+      AB_CUDA(cudaStreamSynchronize(stream_));
+      out_host->arrays.emplace_back();
+      out_host->schemas.emplace_back();
+      export_batch(cols, n_out, &out_host->arrays.back(), &out_host->schemas.back());
+    } else {
+      AB_REQUIRE(join_type_ == ARROYO_B200_JOIN_INNER, ARROYO_B200_UNSUPPORTED,
+                 "device-resident join output is only available for inner joins (no validity bitmaps)");
+      ArroyoB200DeviceBatch d{};
+      d.n_rows = n_out;
+      int c = 0;
+      for (size_t i = 0; i < n_oc; ++i) d.cols[c++] = (uint64_t)out_cols_[i].p;
+      d.cols[c++] = (uint64_t)out_ts_.p;
+      d.n_cols = c;
+      out_dev->push_back(d);
+      AB_CUDA(cudaStreamSynchronize(stream_));
+    }
+  }
+  // rows at or after the watermark stay for later
+  compact(L);
+  compact(R);
+}
+
+}  // namespace
+
+OpBase* make_instant_join_op(const ArroyoB200OpConfig& cfg) { return new InstantJoinOp(cfg); }
+
 }  // namespace ab

@@ -63,7 +63,7 @@ struct Counters {
   unsigned long long lost;
   unsigned long long reserved0;
   unsigned long long max_q;  // newest on-time pane number (ts / slide) seen
-  long long reserved1;
+  unsigned long long big_vals;  // rows deferred because a value exceeded the exact-AVG guard
   unsigned int n_keys;
   unsigned int pad;
 };
@@ -103,6 +103,8 @@ struct IngestParams {
   long long slide;
   long long late_bin;
   unsigned long long late_q;  // late_bin / slide (0 when there is no watermark yet)
+  unsigned int guard_vals;    // bit x set: value slot x must satisfy |v| < 2^31 (exact-sum AVG, see avg_exact_)
+  int combine;                // warp-combine equal (pane, id) before the REDs
   uint32_t ring_mask;
   int n_acc;
   const long long* pane_bins;
@@ -324,6 +326,12 @@ __device__ __forceinline__ void accumulate(const IngestParams& p, const Vals& v,
   }
 }
 
+__device__ __forceinline__ bool big_one(long long v) { return (unsigned long long)(v + (1ll << 31)) >= (1ull << 32); }
+__device__ __forceinline__ bool big_value(unsigned int mask, const Vals& v) {
+  return ((mask & 1u) && big_one(v.v0)) || ((mask & 2u) && big_one(v.v1)) || ((mask & 4u) && big_one(v.v2)) ||
+         ((mask & 8u) && big_one(v.v3));
+}
+
 // Row whose pane is not the thread's cached one (pane boundary inside a warp, tail tiles, tiny
 // batches, non-resident pane): look the ring up directly and count the row with its own atomic.
 template <int NV, int SIG>
@@ -338,6 +346,11 @@ __device__ __noinline__ void slow_row(const IngestParams& p, long long key, long
     id = resolve_id(p.dict, key, raw.x, (uint32_t)raw.y);
     ok = id < ID_OVERFLOW;
   }
+  const Vals v{v0, v1, v2, v3};
+  if (ok && NV > 0 && p.guard_vals && big_value(p.guard_vals, v)) {
+    atomicAdd(&p.counters->big_vals, 1ull);
+    ok = false;
+  }
   if (!ok) {
     defer_row(p, key, ts, v0, v1, v2, v3);
     return;
@@ -345,7 +358,6 @@ __device__ __noinline__ void slow_row(const IngestParams& p, long long key, long
   unsigned long long* pane =
       reinterpret_cast<unsigned long long*>(__ldg(reinterpret_cast<const unsigned long long*>(p.pane_ptrs + slot)));
   atomicAdd(p.slot_rows + slot, 1ull);
-  const Vals v{v0, v1, v2, v3};
   accumulate<NV, SIG>(p, v, pane, id);
 }
 
@@ -367,23 +379,108 @@ __device__ __forceinline__ void flush_counts(const IngestParams& p, PaneCache& p
   pc.cnt = 0;
 }
 
-// One on-time-or-late row on the hot path.
+// Divergent half of a hot-path row: residency test, dictionary id, exact-AVG guard.  Returns the id to
+// accumulate into, or ID_OVERFLOW when the row was handled out of line (slow path / deferred).
 template <int NV, int SIG>
-__device__ __forceinline__ void hot_row(const IngestParams& p, PaneCache& pc, uint64_t& maxq, bool keyed, long long key,
-                                        long long ts, uint64_t q, const Vals& v, unsigned long long k0, uint32_t id0) {
+__device__ __forceinline__ uint32_t hot_resolve(const IngestParams& p, const PaneCache& pc, uint64_t& maxq, bool keyed,
+                                                long long key, long long ts, uint64_t q, const Vals& v,
+                                                unsigned long long k0, uint32_t id0) {
   uint32_t id = ID_OVERFLOW;
   if (q == pc.q && pc.ptr != nullptr) id = keyed ? resolve_id(p.dict, key, k0, id0) : 0u;
-  if (id < ID_OVERFLOW) {
-    ++pc.cnt;
-    accumulate<NV, SIG>(p, v, pc.ptr, id);
-  } else {
+  if (NV > 0 && p.guard_vals && big_value(p.guard_vals, v)) {
+    // AVG is being derived from the exact integer sum: a value this large could overflow it.  Park the
+    // row; the host promotes the operator to f64 AVG accumulators and re-ingests it.
+    atomicAdd(&p.counters->big_vals, 1ull);
+    defer_row(p, key, ts, v.v0, v.v1, v.v2, v.v3);
+    return ID_OVERFLOW;
+  }
+  if (id >= ID_OVERFLOW) {
     maxq = max(maxq, q);
     slow_row<NV, SIG>(p, key, ts, q, v.v0, v.v1, v.v2, v.v3);
+  }
+  return id;
+}
+
+__device__ __forceinline__ long long shfl_ll(unsigned mask, long long v, int src) {
+  return (long long)__shfl_sync(mask, (unsigned long long)v, src);
+}
+
+// Combines one accumulator across the lanes of `peers` (same pane, same id); valid in the leader.
+__device__ __forceinline__ long long group_reduce(int kind, unsigned peers, long long v) {
+  long long r = v;
+  bool first = true;
+  for (unsigned m = peers; m; m &= m - 1) {
+    const long long x = shfl_ll(peers, v, __ffs(m) - 1);
+    if (first) {
+      r = x;
+      first = false;
+      continue;
+    }
+    switch (kind) {
+      case ACC_SUM_I64: r = (long long)((unsigned long long)r + (unsigned long long)x); break;
+      case ACC_SUM_F64: r = __double_as_longlong(__longlong_as_double(r) + __longlong_as_double(x)); break;
+      case ACC_MIN_I64: r = min(r, x); break;
+      case ACC_MAX_I64: r = max(r, x); break;
+      default: break;
+    }
+  }
+  return r;
+}
+
+__device__ __forceinline__ void red_kind_combined(int kind, unsigned long long* dst, long long v) {
+  // v is already in the accumulator's domain (f64 bits for ACC_SUM_F64)
+  if (kind == ACC_SUM_F64) red_add_f64(dst, __longlong_as_double(v));
+  else red_kind(kind, dst, v);
+}
+
+// Convergent half: RED updates, after combining lanes of the warp that hit the same (pane, id).  Skewed
+// keys (Nexmark: 75 % of the bids on the hot bidder) would otherwise serialise tens of millions of REDs on
+// one L2 address; unkeyed aggregates hit a single address by construction.  The neighbour test keeps the
+// common case (all ids distinct) at two shuffles and a vote.
+template <int NV, int SIG>
+__device__ __forceinline__ void combine_accumulate(const IngestParams& p, const PaneCache& pc, bool fast, uint32_t id,
+                                                   const Vals& v, int lane) {
+  const unsigned long long gkey = fast ? ((unsigned long long)id | (pc.q << 32)) : (0xFFFFFFFF00000000ull | (unsigned)lane);
+  const unsigned long long nb = __shfl_xor_sync(0xffffffffu, gkey, 1);
+  if (!__any_sync(0xffffffffu, fast && nb == gkey)) {
+    if (fast) accumulate<NV, SIG>(p, v, pc.ptr, id);
+    return;
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, gkey);
+  const bool leader = (__ffs(peers) - 1) == lane;
+  unsigned long long* pane = pc.ptr;
+  if (fast && leader) red_add_u64(pane + id, (unsigned long long)__popc(peers));
+  if (SIG == GENERIC_SIG) {
+#pragma unroll
+    for (int a = 1; a < MAX_ACC; ++a) {
+      if (a < p.n_acc) {
+        const int x = p.acc_val[a];
+        long long val = x == 0 ? v.v0 : x == 1 ? v.v1 : x == 2 ? v.v2 : v.v3;
+        const int kind = p.acc_kind[a];
+        if (kind == ACC_SUM_F64) val = __double_as_longlong((double)val);
+        const long long r = group_reduce(kind, peers, val);
+        if (fast && leader) red_kind_combined(kind, pane + (unsigned long long)a * p.id_cap + id, r);
+      }
+    }
+  } else {
+    constexpr int k1 = SIG & 7, k2 = (SIG >> 3) & 7, k3 = (SIG >> 6) & 7;
+    if (k1) {
+      const long long r = group_reduce(k1, peers, k1 == ACC_SUM_F64 ? __double_as_longlong((double)v.v0) : v.v0);
+      if (fast && leader) red_kind_combined(k1, pane + p.id_cap + id, r);
+    }
+    if (k2) {
+      const long long r = group_reduce(k2, peers, k2 == ACC_SUM_F64 ? __double_as_longlong((double)v.v0) : v.v0);
+      if (fast && leader) red_kind_combined(k2, pane + 2 * p.id_cap + id, r);
+    }
+    if (k3) {
+      const long long r = group_reduce(k3, peers, k3 == ACC_SUM_F64 ? __double_as_longlong((double)v.v0) : v.v0);
+      if (fast && leader) red_kind_combined(k3, pane + 3 * p.id_cap + id, r);
+    }
   }
 }
 
 #ifndef AB_INGEST_MIN_BLOCKS
-#define AB_INGEST_MIN_BLOCKS 6
+#define AB_INGEST_MIN_BLOCKS 5
 #endif
 template <int NV, int SIG>
 __global__ void __launch_bounds__(THREADS, AB_INGEST_MIN_BLOCKS) ingest_kernel(const __grid_constant__ IngestParams p) {
@@ -453,7 +550,13 @@ __global__ void __launch_bounds__(THREADS, AB_INGEST_MIN_BLOCKS) ingest_kernel(c
           maxq = max(maxq, q);
         }
       }
-      if (live) hot_row<NV, SIG>(p, pc, maxq, keyed, key, ts, q, pack_vals<NV>(v), raw.x, (uint32_t)raw.y);
+      const Vals pv = pack_vals<NV>(v);
+      uint32_t id = ID_OVERFLOW;
+      if (live) id = hot_resolve<NV, SIG>(p, pc, maxq, keyed, key, ts, q, pv, raw.x, (uint32_t)raw.y);
+      const bool fast = id < ID_OVERFLOW;
+      if (fast) ++pc.cnt;
+      if (p.combine) combine_accumulate<NV, SIG>(p, pc, fast, id, pv, lane);
+      else if (fast) accumulate<NV, SIG>(p, pv, pc.ptr, id);
     }
   }
 
@@ -672,10 +775,15 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(const __grid_constan
               case ARROYO_B200_AGG_COUNT_STAR:
                 v = rows;
                 break;
-              case ARROYO_B200_AGG_AVG_I64:
-                v = (unsigned long long)__double_as_longlong(
-                    __longlong_as_double((long long)acc[p.agg_acc[g]]) / (double)rows);
+              case ARROYO_B200_AGG_AVG_I64: {
+                // f64 accumulator: sum of inputs cast to f64 (DataFusion's AVG state); integer
+                // accumulator: the exact sum, converted once (guarded against overflow on ingest)
+                const unsigned long long s = acc[p.agg_acc[g]];
+                const double num = p.acc_kind[p.agg_acc[g]] == ACC_SUM_F64 ? __longlong_as_double((long long)s)
+                                                                           : (double)(long long)s;
+                v = (unsigned long long)__double_as_longlong(num / (double)rows);
                 break;
+              }
               default:
                 v = acc[p.agg_acc[g]];
                 break;
@@ -793,6 +901,13 @@ class WindowAggOp final : public OpBase {
   int agg_kind_[ARROYO_B200_MAX_AGGS];
   int agg_acc_[ARROYO_B200_MAX_AGGS];
   bool invertible_ = true;
+  // AVG(Int64) from the exact integer sum instead of a separate f64 RED per row (one scattered access
+  // less per row).  Valid while no per-key sum can overflow i64: every guarded value is < 2^31 in
+  // magnitude (checked per row on the device) and no window holds 2^32 rows (checked on the host);
+  // otherwise the operator promotes itself to f64 accumulators (promote_avg).  The result differs from
+  // DataFusion's running f64 sum by at most n * 2^-53 relative (north-star tolerance: 1e-6).
+  bool avg_exact_ = true;
+  unsigned int guard_vals_ = 0;
   bool running_mode_ = false;
   bool profile_;
   std::string key_format_ = "l";
@@ -856,6 +971,7 @@ class WindowAggOp final : public OpBase {
   Counters last_counters_{};
   bool have_counters_ = false;
   bool draining_ = false;
+  bool need_promote_ = false;
 
   // emission output
   struct OutSet {
@@ -875,6 +991,8 @@ class WindowAggOp final : public OpBase {
   void set_device() { AB_CUDA(cudaSetDevice(device_)); }
   void alloc_dictionary(uint64_t id_cap);
   void grow_ids();
+  void promote_avg();
+  void relayout_blocks(int old_n_acc, const std::vector<std::pair<int, int>>& f64_from);
   unsigned long long* acquire_block();
   void release_block(unsigned long long* blk);
   void init_block(unsigned long long* blk, uint64_t n_ids);
@@ -921,6 +1039,7 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
   AB_REQUIRE(!keyed_ || (key_col_ >= 0 && key_col_ < c.n_cols), ARROYO_B200_INVALID_ARGUMENT, "bad key_col");
   AB_REQUIRE(c.n_aggs >= 1 && c.n_aggs <= ARROYO_B200_MAX_AGGS, ARROYO_B200_INVALID_ARGUMENT, "bad n_aggs");
   n_aggs_ = c.n_aggs;
+  avg_exact_ = !(c.flags & ARROYO_B200_FLAG_AVG_F64);
   acc_kind_[0] = ACC_ROWS;
   acc_val_[0] = 0;
   for (int g = 0; g < n_aggs_; ++g) {
@@ -944,7 +1063,12 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
     int ak;
     switch (kind) {
       case ARROYO_B200_AGG_SUM_I64: ak = ACC_SUM_I64; agg_format_.push_back("l"); break;
-      case ARROYO_B200_AGG_AVG_I64: ak = ACC_SUM_F64; agg_format_.push_back("g"); break;
+      case ARROYO_B200_AGG_AVG_I64:
+        // exact mode: AVG shares the wrapping integer sum and is finalised as (double)sum / count
+        ak = avg_exact_ ? ACC_SUM_I64 : ACC_SUM_F64;
+        if (avg_exact_) guard_vals_ |= 1u << vs;
+        agg_format_.push_back("g");
+        break;
       case ARROYO_B200_AGG_MIN_I64: ak = ACC_MIN_I64; agg_format_.push_back("l"); invertible_ = false; break;
       case ARROYO_B200_AGG_MAX_I64: ak = ACC_MAX_I64; agg_format_.push_back("l"); invertible_ = false; break;
       default:
@@ -1160,6 +1284,76 @@ void WindowAggOp::grow_ids() {
   AB_CUDA(cudaMemcpyAsync((char*)counters_.p + offsetof(Counters, n_keys), &nk, sizeof nk, cudaMemcpyHostToDevice, stream_));
   n_keys_host_ = n_valid;
   AB_CUDA(cudaStreamSynchronize(stream_));
+}
+
+// fsum[id] = (double)(int64)sum[id]
+__global__ void i64_to_f64_kernel(const unsigned long long* __restrict__ src, unsigned long long* __restrict__ dst, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = (unsigned long long)__double_as_longlong((double)(long long)src[i]);
+}
+
+// Re-creates every live block with the current n_acc_; accumulators [0, old_n_acc) are copied, and each
+// (new index, source index) pair in f64_from is filled with the f64 image of the source integer sum.
+void WindowAggOp::relayout_blocks(int old_n_acc, const std::vector<std::pair<int, int>>& f64_from) {
+  std::vector<DevBuf> new_storage;
+  const uint32_t n_valid = (uint32_t)std::min<uint64_t>(n_keys_host_, id_cap_);
+  auto migrate = [&](unsigned long long* old_blk) -> unsigned long long* {
+    if (!old_blk) return nullptr;
+    new_storage.emplace_back((size_t)n_acc_ * id_cap_ * sizeof(unsigned long long));
+    auto* nb = new_storage.back().as<unsigned long long>();
+    init_block(nb, id_cap_);
+    for (int a = 0; a < old_n_acc; ++a)
+      AB_CUDA(cudaMemcpyAsync(nb + (size_t)a * id_cap_, old_blk + (size_t)a * id_cap_,
+                              (size_t)n_valid * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream_));
+    for (auto& pr : f64_from) {
+      int grid = (int)std::min<uint64_t>((n_valid + 255) / 256 + 1, (uint64_t)num_sms_ * 8);
+      i64_to_f64_kernel<<<grid, 256, 0, stream_>>>(old_blk + (size_t)pr.second * id_cap_, nb + (size_t)pr.first * id_cap_, n_valid);
+      AB_CUDA(cudaGetLastError());
+      ++st_.kernel_launches;
+    }
+    return nb;
+  };
+  for (auto& kv : panes_) {
+    kv.second.dev = migrate(kv.second.dev);
+    kv.second.frozen = migrate(kv.second.frozen);
+    if (kv.second.slot >= 0) h_pane_ptrs_[kv.second.slot] = kv.second.dev;
+  }
+  for (auto& kv : zombies_) {
+    kv.second.dev = migrate(kv.second.dev);
+    kv.second.frozen = migrate(kv.second.frozen);
+  }
+  running_ = migrate(running_);
+  AB_CUDA(cudaStreamSynchronize(stream_));
+  free_panes_.clear();
+  pane_storage_ = std::move(new_storage);
+  ring_dirty_ = true;
+}
+
+// Leaves exact-sum AVG: every AVG gets its own f64 accumulator, seeded from the (still exact) integer sums.
+void WindowAggOp::promote_avg() {
+  if (!avg_exact_) return;
+  AB_REQUIRE(in_flight_.empty(), ARROYO_B200_RUNTIME, "promote with launches in flight");
+  const int old_n_acc = n_acc_;
+  std::vector<std::pair<int, int>> f64_from;
+  for (int g = 0; g < n_aggs_; ++g) {
+    if (agg_kind_[g] != ARROYO_B200_AGG_AVG_I64) continue;
+    const int src = agg_acc_[g];
+    int found = -1;
+    for (auto& pr : f64_from)
+      if (pr.second == src) found = pr.first;
+    if (found < 0) {
+      AB_REQUIRE(n_acc_ < MAX_ACC, ARROYO_B200_RUNTIME, "too many accumulators after AVG promotion");
+      found = n_acc_;
+      acc_kind_[n_acc_] = ACC_SUM_F64;
+      acc_val_[n_acc_] = acc_val_[src];
+      ++n_acc_;
+      f64_from.emplace_back(found, src);
+    }
+    agg_acc_[g] = found;
+  }
+  avg_exact_ = false;
+  relayout_blocks(old_n_acc, f64_from);
 }
 
 void WindowAggOp::ensure_pane(int64_t bin) {
@@ -1391,6 +1585,8 @@ void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk
   p.slide = slide_;
   p.late_bin = late_bin_;
   p.late_q = late_bin_ == LLONG_MIN ? 0ull : (unsigned long long)late_bin_ / (unsigned long long)slide_;
+  p.guard_vals = avg_exact_ ? guard_vals_ : 0u;
+  p.combine = (cfg.flags & ARROYO_B200_FLAG_NO_COMBINE) ? 0 : 1;
   p.ring_mask = ring_ - 1;
   p.n_acc = n_acc_;
   p.pane_bins = d_pane_bins_.as<long long>();
@@ -1479,7 +1675,9 @@ void WindowAggOp::absorb(int li) {
   for (uint32_t s = 0; s < ring_; ++s) {
     if (L.h_slot_rows[s]) {
       AB_REQUIRE(h_pane_bins_[s] != FREE_BIN, ARROYO_B200_RUNTIME, "touched a free ring slot");
-      panes_.at(h_pane_bins_[s]).rows += L.h_slot_rows[s];
+      Pane& tp = panes_.at(h_pane_bins_[s]);
+      tp.rows += L.h_slot_rows[s];
+      if (tp.rows >= (1ull << 31)) need_promote_ = true;
       touch(h_pane_bins_[s]);
     }
   }
@@ -1502,6 +1700,7 @@ void WindowAggOp::lookahead() {
 
 void WindowAggOp::sync_all() {
   while (!in_flight_.empty()) absorb(in_flight_.front());
+  if (need_promote_ && avg_exact_) promote_avg();
   drain_deferred();
 }
 
@@ -1529,6 +1728,7 @@ void WindowAggOp::drain_deferred() {
       if (b >= late_bin_) bins.insert(b);
     }
     for (int64_t b : bins) ensure_pane(b);
+    if (last_counters_.big_vals && avg_exact_) promote_avg();
     // dictionary pressure: grow when half full (keeps probes short) or when ids ran out
     while (keyed_ && (uint64_t)last_counters_.n_keys + n / 2 >= id_cap_ / 2 + id_cap_ / 4) {
       n_keys_host_ = (uint32_t)std::min<uint64_t>(last_counters_.n_keys, id_cap_);
@@ -1694,6 +1894,7 @@ void WindowAggOp::export_window(OutSet* os, int64_t n, BatchesPriv* out_host) {
 // (arroyo-planner/src/builder.rs:163-192).  COUNT -> count; SUM -> sum; AVG -> (count u64, sum f64).
 void WindowAggOp::export_partial(OutSet* os, int64_t n, BatchesPriv* out) {
   std::vector<OutColumn> cols;
+  std::vector<size_t> fix_f64;  // AVG state kept as an exact integer sum: the partial schema wants Float64
   if (keyed_) {
     OutColumn k;
     k.name = "key";
@@ -1715,6 +1916,7 @@ void WindowAggOp::export_partial(OutSet* os, int64_t n, BatchesPriv* out) {
       case ARROYO_B200_AGG_AVG_I64:
         add("[count]", "L", os->state[0].p);
         add("[sum]", "g", os->state[agg_acc_[g]].p);
+        if (acc_kind_[agg_acc_[g]] == ACC_SUM_I64) fix_f64.push_back(cols.size() - 1);
         break;
       case ARROYO_B200_AGG_MIN_I64: add("[min]", agg_format_[g].c_str(), os->state[agg_acc_[g]].p); break;
       case ARROYO_B200_AGG_MAX_I64: add("[max]", agg_format_[g].c_str(), os->state[agg_acc_[g]].p); break;
@@ -1726,6 +1928,11 @@ void WindowAggOp::export_partial(OutSet* os, int64_t n, BatchesPriv* out) {
   t.data = d2h_column(os->ts.p, n, stream_, &st_.d2h_bytes);
   cols.push_back(t);
   AB_CUDA(cudaStreamSynchronize(stream_));
+  for (size_t ci : fix_f64) {
+    long long* raw = (long long*)cols[ci].data;
+    double* d = (double*)cols[ci].data;
+    for (int64_t i = 0; i < n; ++i) d[i] = (double)raw[i];
+  }
   out->arrays.emplace_back();
   out->schemas.emplace_back();
   export_batch(cols, n, &out->arrays.back(), &out->schemas.back());
@@ -1737,6 +1944,11 @@ void WindowAggOp::emit_window(int64_t a, int64_t b, size_t out_index, BatchesPri
   std::vector<int64_t> members;
   for (auto it = panes_.lower_bound(a); it != panes_.end() && it->first < b; ++it)
     if (it->second.in_tier) members.push_back(it->first);
+  if (avg_exact_ && guard_vals_) {
+    uint64_t window_rows = 0;
+    for (int64_t m : members) window_rows += panes_.at(m).rows;
+    if (window_rows >= (1ull << 32)) promote_avg();
+  }
   std::vector<const unsigned long long*> blocks;
   int n_add = 0;
   bool use_running = false;
@@ -1979,6 +2191,7 @@ void WindowAggOp::on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, i
     int ci = 0;
     if (keyed_) pp.key = (const long long*)up(cols[ci++].data);
     for (int a = 0; a < MAX_ACC; ++a) pp.state[a] = nullptr;
+    std::vector<std::pair<int, int>> avg_sum_cols;  // (agg, column of its f64 sum)
     for (int g = 0; g < n_aggs_; ++g) {
       switch (agg_kind_[g]) {
         case ARROYO_B200_AGG_COUNT_STAR: {
@@ -1989,12 +2202,29 @@ void WindowAggOp::on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, i
         case ARROYO_B200_AGG_AVG_I64: {
           const unsigned long long* c = up(cols[ci++].data);
           if (!pp.state[0]) pp.state[0] = c;
-          pp.state[agg_acc_[g]] = up(cols[ci++].data);
+          avg_sum_cols.emplace_back(g, ci++);
           break;
         }
         default:
           pp.state[agg_acc_[g]] = up(cols[ci++].data);
           break;
+      }
+    }
+    std::vector<long long> conv;
+    for (auto& pr : avg_sum_cols) {
+      const int acc = agg_acc_[pr.first];
+      if (acc_kind_[acc] == ACC_SUM_F64) {
+        pp.state[acc] = up(cols[pr.second].data);
+      } else if (!pp.state[acc]) {
+        // exact-sum AVG without a SUM over the same column: the checkpoint only has the f64 image of the sum
+        // (exact below 2^53); a SUM column, when present, already restored the integer accumulator above
+        conv.resize((size_t)rows);
+        const double* d = (const double*)cols[pr.second].data;
+        for (int64_t i = 0; i < rows; ++i) conv[(size_t)i] = (long long)__builtin_llround(d[i]);
+        keep.emplace_back((size_t)rows * 8);
+        AB_CUDA(cudaMemcpyAsync(keep.back().p, conv.data(), (size_t)rows * 8, cudaMemcpyHostToDevice, stream_));
+        AB_CUDA(cudaStreamSynchronize(stream_));
+        pp.state[acc] = keep.back().as<unsigned long long>();
       }
     }
     AB_REQUIRE(pp.state[0] != nullptr, ARROYO_B200_UNSUPPORTED,

@@ -148,7 +148,7 @@ def bench(args, torch, dist, rank, world, local):
     part = DevicePartitioner(torch, world, 3, 0, round_rows, local, stream)
     ex = ShuffleExchange(torch, dist, rank, world, part, device, max_recv_rows=2 * round_rows, n_cols=3)
     schema = pa.schema([("key", pa.int64()), ("value", pa.int64()), ("_timestamp", pa.timestamp("ns"))])
-    flags = ffi.FLAG_PROFILE | (ffi.FLAG_REMERGE_ONLY if args.remerge else 0)
+    flags = ffi.FLAG_PROFILE | B.op_flags(args)
     op = native.SlidingAggregatingWindowFunc(B.window_config(), input_schema=schema, device=local, stream=stream,
                                              flags=flags, expected_keys=max(args.keys * 2 // world, 1024),
                                              task_index=rank, parallelism=world)

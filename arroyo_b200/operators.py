@@ -254,3 +254,110 @@ class SlidingAggregatingWindowFunc(_WindowAggregate):
 
     def name(self):
         return "sliding_window"
+
+
+_JOIN_TYPES = {"inner": ffi.JOIN_INNER, "left": ffi.JOIN_LEFT, "right": ffi.JOIN_RIGHT, "full": ffi.JOIN_FULL}
+
+
+class InstantJoin(_NativeOperator):
+    """arroyo-worker/src/arrow/instant_join.rs.  Inputs with index < in_partitions / 2 are the left side
+    (:249-253).  The native operator needs both input layouts, so batches are buffered until each side's
+    schema is known (pass `left_schema` / `right_schema` to skip that)."""
+    kind = ffi.INSTANT_JOIN
+
+    def __init__(self, config, left_schema: Optional[pa.Schema] = None, right_schema: Optional[pa.Schema] = None, **kw):
+        super().__init__(**kw)
+        self.config = config
+        self._schemas = [left_schema, right_schema]
+        self._buffered = []
+        if left_schema is not None and right_schema is not None:
+            self._build()
+
+    def name(self):
+        return "InstantJoin"
+
+    def tables(self):
+        return {"left": 0, "right": 0}  # instant_join.rs:305-328
+
+    def _side_layout(self, side: int):
+        c = self.config
+        names = self._schemas[side].names
+        routing = c.left_routing_keys if side == 0 else c.right_routing_keys
+        on = c.left_on if side == 0 else c.right_on
+        if len(on) != 1:
+            raise ffi.UnsupportedPlan(ffi.UNSUPPORTED, "only single-column equi-joins are supported")
+        if list(names[:len(routing)]) != list(routing):
+            raise ffi.ArroyoB200Error(ffi.INVALID_ARGUMENT, "routing key columns must lead the schema")
+        return len(names), names.index(TIMESTAMP), names.index(on[0]), len(routing)
+
+    def _build(self):
+        cfg = ffi.OpConfig()
+        cfg.kind = self.kind
+        cfg.join_type = _JOIN_TYPES[self.config.join_type]
+        cfg.n_cols, cfg.timestamp_col, cfg.left_key_col, cfg.left_n_routing = self._side_layout(0)
+        cfg.right_n_cols, cfg.right_timestamp_col, cfg.right_key_col, cfg.right_n_routing = self._side_layout(1)
+        self._create(cfg)
+        for index, parts, batch in self._buffered:
+            self._send(index, parts, batch)
+        self._buffered = []
+
+    def output_names(self):
+        out = []
+        for side in (0, 1):
+            names = self._schemas[side].names
+            routing = self.config.left_routing_keys if side == 0 else self.config.right_routing_keys
+            for n in names[len(routing):]:
+                if n == TIMESTAMP:
+                    continue
+                out.append(n if n not in out else n + "_right")
+        return out + [TIMESTAMP]
+
+    def _send(self, index, parts, batch):
+        arr, sch = export_batch(batch)
+        st = self._lib.arroyo_b200_op_process_batch(self._h, index, parts, C.byref(arr), C.byref(sch))
+        if st != ffi.OK and arr.release:
+            C.CFUNCTYPE(None, C.c_void_p)(arr.release)(C.addressof(arr))
+        if sch.release:
+            C.CFUNCTYPE(None, C.c_void_p)(sch.release)(C.addressof(sch))
+        _check(self._lib, self._h, st)
+
+    def process_batch_index(self, index: int, in_partitions: int, batch: pa.RecordBatch, ctx: OperatorContext,
+                            collector: Collector):
+        side = index // (in_partitions // 2)
+        if self._schemas[side] is None:
+            self._schemas[side] = batch.schema
+        if not self.created:
+            if self._schemas[0] is not None and self._schemas[1] is not None:
+                self._build()
+            else:
+                self._buffered.append((index, in_partitions, batch))
+                return
+        self._send(index, in_partitions, batch)
+
+    def handle_watermark(self, watermark, ctx: OperatorContext, collector: Collector):
+        wm = ctx.last_present_watermark()
+        if wm is None:
+            return watermark
+        if not self.created:
+            # one side never produced a row: nothing can match; an inner join emits nothing
+            if self.config.join_type == "inner":
+                self._buffered = []
+                return wm
+            known = 0 if self._schemas[0] is not None else 1
+            self._schemas[1 - known] = pa.schema([("__none", pa.int64()), (TIMESTAMP, pa.timestamp("ns"))])
+            saved = (self.config.left_on, self.config.right_on)
+            if known == 0:
+                self.config.right_on = ["__none"]
+            else:
+                self.config.left_on = ["__none"]
+            try:
+                self._build()
+            finally:
+                self.config.left_on, self.config.right_on = saved
+        out = ffi.Batches()
+        st = self._lib.arroyo_b200_op_handle_watermark(self._h, clamp_watermark(wm), C.byref(out))
+        _check(self._lib, self._h, st)
+        names = self.output_names()
+        for b in import_batches(self._lib, out):
+            collector.collect(pa.RecordBatch.from_arrays(b.columns, names=names))
+        return wm

@@ -45,7 +45,7 @@ KEY_MULT = 0x9E3779B97F4A7C15  # odd => bijection on u64: keys are scattered ove
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=12)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--keys", type=int, default=1 << 20)
@@ -55,13 +55,20 @@ def parse():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--remerge", action="store_true", help="re-merge all panes per slide (reference algorithm)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
+    ap.add_argument("--no-combine", action="store_true", help="measurement knob: no warp-combining of equal keys")
+    ap.add_argument("--avg-f64", action="store_true", help="measurement knob: AVG with its own f64 accumulator")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------
 # synthetic Nexmark-bid-shaped input (generated on the device; seed 42 + rank)
 # ------------------------------------------------------------------------------------------------
+POOL = 8  # distinct (key, value) panes; every step still gets its own timestamps
+
+
 def make_generator(torch, device, rows_per_pane, n_keys, dist, seed):
+    """pane(p) -> (key, value, ts) device tensors of the p-th 1-s pane.  Keys / values cycle through a pool of
+    POOL independently drawn panes (the operator never sees the same timestamps twice)."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     i = torch.arange(rows_per_pane, device=device, dtype=torch.int64)
@@ -71,20 +78,22 @@ def make_generator(torch, device, rows_per_pane, n_keys, dist, seed):
     order = torch.argsort(grp)
     offs = (order * S) // rows_per_pane
     del grp, order, i
-
-    def pane(p):
-        ts = offs + (T0 + p * SLIDE)
-        if dist == "uniform":
-            kid = torch.randint(0, n_keys, (rows_per_pane,), device=device, generator=g, dtype=torch.int64)
-        else:  # 75 % of the rows on the current hot id (nexmark hot_bidders_ratio), the rest uniform
-            kid = torch.randint(0, n_keys, (rows_per_pane,), device=device, generator=g, dtype=torch.int64)
+    pool = []
+    for j in range(POOL):
+        kid = torch.randint(0, n_keys, (rows_per_pane,), device=device, generator=g, dtype=torch.int64)
+        if dist == "hot":  # 75 % of the rows on the current hot id (nexmark hot_bidders_ratio 4 -> 3 of 4 rows)
             hot = torch.rand(rows_per_pane, device=device, generator=g) < 0.75
-            kid = torch.where(hot, torch.full_like(kid, (p // 4) % n_keys), kid)
+            kid = torch.where(hot, torch.full_like(kid, (j // 4) % n_keys), kid)
         key = kid * torch.tensor(KEY_MULT - (1 << 64), dtype=torch.int64, device=device)  # wrapping multiply
         # price = floor(10^U(0,6) * 100)  (nexmark/operator.rs:643-645)
         u = torch.rand(rows_per_pane, device=device, generator=g, dtype=torch.float64) * 6.0
         val = torch.floor(torch.pow(10.0, u) * 100.0).to(torch.int64)
-        return key, val, ts
+        pool.append((key, val))
+        del kid, u
+
+    def pane(p):
+        key, val = pool[p % POOL]
+        return key, val, offs + (T0 + p * SLIDE)
 
     return pane
 
@@ -111,7 +120,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -167,6 +176,12 @@ def ncu_traffic():
         except Exception:
             return None
     return None
+
+
+def op_flags(args):
+    from arroyo_b200 import ffi
+    return ((ffi.FLAG_REMERGE_ONLY if args.remerge else 0) | (ffi.FLAG_NO_COMBINE if args.no_combine else 0) |
+            (ffi.FLAG_AVG_F64 if args.avg_f64 else 0))
 
 
 def window_config():
@@ -294,7 +309,7 @@ def run_ours(args):
 
     import pyarrow as pa
     schema = pa.schema([("key", pa.int64()), ("value", pa.int64()), ("_timestamp", pa.timestamp("ns"))])
-    flags = ffi.FLAG_PROFILE | (ffi.FLAG_REMERGE_ONLY if args.remerge else 0)
+    flags = ffi.FLAG_PROFILE | op_flags(args)
     stream = torch.cuda.current_stream().cuda_stream
     op = native.SlidingAggregatingWindowFunc(window_config(), input_schema=schema, device=local, stream=stream,
                                              flags=flags, expected_keys=args.keys)
@@ -354,6 +369,8 @@ def run_ours(args):
                                   f"batches of {BATCH_ROWS}, 1 step = 1 pane + 1 emitted window",
                       "keys": args.keys, "rows_per_step": rows, "batch_rows": BATCH_ROWS, "width_s": 10, "slide_s": 1,
                       "emission": "remerge" if args.remerge else "running add/evict",
+                      "avg": "f64 accumulator" if args.avg_f64 else "exact integer sum (guarded)",
+                      "combine": not args.no_combine,
                       "l2": "inputs larger than L2 (402 MB per step, never re-read)", "parallelism": "1 gpu"},
            "rows_out_per_step": rows_out / max(K, 1), "gpu_launches": int(d["kernel_launches"]),
            "roofline": roof, "clocks": clocks}
@@ -377,15 +394,20 @@ def run_e2e(args, torch, device, local, gen_pane):
     W = 11
     rows = args.rows_per_pane
     nb = rows // BATCH_ROWS
-    # pinned host panes holding the same synthetic stream
+    # pinned host panes holding the same synthetic stream (key / value pool + per-pane timestamps)
+    host_pool = {}
     host = []
     for p in range(W + K):
-        cols = []
-        for x in gen_pane(p):
-            h = torch.empty(rows, dtype=torch.int64, pin_memory=True)
-            h.copy_(x)
-            cols.append(h)
-        host.append(cols)
+        k, v, t = gen_pane(p)
+        if p % POOL not in host_pool:
+            hk = torch.empty(rows, dtype=torch.int64, pin_memory=True)
+            hv = torch.empty(rows, dtype=torch.int64, pin_memory=True)
+            hk.copy_(k)
+            hv.copy_(v)
+            host_pool[p % POOL] = (hk, hv)
+        ht = torch.empty(rows, dtype=torch.int64, pin_memory=True)
+        ht.copy_(t)
+        host.append([host_pool[p % POOL][0], host_pool[p % POOL][1], ht])
     torch.cuda.synchronize()
     ts_type = pa.timestamp("ns")
 
@@ -404,7 +426,7 @@ def run_e2e(args, torch, device, local, gen_pane):
         mm += list(zip(t.amin(dim=1).tolist(), t.amax(dim=1).tolist()))
     wms = watermark_schedule(mm)
     op = native.SlidingAggregatingWindowFunc(window_config(), device=local, expected_keys=args.keys,
-                                             flags=ffi.FLAG_REMERGE_ONLY if args.remerge else 0)
+                                             flags=op_flags(args))
     ctx = ab.OperatorContext(1)
     col = ab.Collector()
     d2h = 0

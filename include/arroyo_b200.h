@@ -159,8 +159,11 @@ typedef struct ArroyoB200OpConfig {
 #define ARROYO_B200_FLAG_REMERGE_ONLY 2u  /* sliding: always re-merge all panes per slide  */
                                           /* (the reference's algorithm) instead of the    */
                                           /* running add/evict window; same results        */
-#define ARROYO_B200_FLAG_COMBINE 4u       /* warp-combine duplicate keys before the        */
-                                          /* atomics (skewed keys)                          */
+#define ARROYO_B200_FLAG_AVG_F64 8u       /* AVG(Int64) with its own f64 accumulator from the start  */
+                                          /* (default: exact integer sum, promoted on demand)        */
+#define ARROYO_B200_FLAG_COMBINE 4u       /* (default behaviour; kept for ABI stability)   */
+#define ARROYO_B200_FLAG_NO_COMBINE 16u   /* do not warp-combine equal keys before the     */
+                                          /* atomics (measurement knob)                    */
 
 typedef struct ArroyoB200Op ArroyoB200Op;
 

@@ -36,14 +36,17 @@ def _np(arr: pa.Array) -> np.ndarray:
 
 
 def from_arrow(rb: pa.RecordBatch) -> O.Batch:
-    cols = {}
+    cols, valid = {}, {}
     for name, col in zip(rb.schema.names, rb.columns):
         if pa.types.is_struct(col.type):
             cols["window_start"] = _np(col.field(0))
             cols["window_end"] = _np(col.field(1))
+        elif col.null_count:
+            valid[name] = np.asarray(col.is_valid())
+            cols[name] = _np(col.fill_null(0))
         else:
             cols[name] = _np(col)
-    return O.Batch(cols)
+    return O.Batch(cols, valid)
 
 
 class _CollectAdapter(ab.Collector):
@@ -85,9 +88,19 @@ class SlidingAggregatingWindowFunc(_WindowOp):
     native_cls = native.SlidingAggregatingWindowFunc
 
 
-# operators not yet on the GPU fall back to nothing: the cases that need them are not run
+class InstantJoin:
+    def __init__(self, cfg, **kw):
+        self.op = native.InstantJoin(cfg, **kw)
+
+    def process_batch_index(self, index, total_inputs, batch: O.Batch, ctx, collector):
+        self.op.process_batch_index(index, total_inputs, to_arrow(batch), ctx, _CollectAdapter(collector))
+
+    def handle_watermark(self, watermark, ctx, collector):
+        return self.op.handle_watermark(watermark, ctx, _CollectAdapter(collector))
+
+
+# not yet on the GPU: the cases that need it are not run against the CUDA path
 SessionAggregatingWindowFunc = None
-InstantJoin = None
 
 
 def run_single_input(op, batches, delay_ns: int = 1_000_000_000, ctx=None) -> O.Collector:

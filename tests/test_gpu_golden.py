@@ -6,7 +6,9 @@ from tests.golden_cases import CASES, multiset
 pytestmark = pytest.mark.gpu
 
 WINDOW_ONLY = ["sliding_window_end", "hourly_by_event_type", "tight_watermark", "month_loose_watermark",
-               "most_active_driver_last_hour"]
+               "most_active_driver_last_hour",
+               # window aggregates + instant join, both on the GPU
+               "windowed_inner_join", "windowed_outer_join", "offset_impulse_join", "nexmark_q5"]
 
 
 @pytest.fixture(scope="module")

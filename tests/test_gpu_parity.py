@@ -300,3 +300,86 @@ def test_device_resident_batches_and_device_output(G):
             collect(op.handle_watermark_device(wm))
     collect(op.handle_watermark_device(ab.FINAL_WATERMARK))
     assert_same(want, got, float_cols=("avg",))
+
+
+@pytest.mark.parametrize("join_type", ["inner", "left", "right", "full"])
+def test_instant_join_matches_oracle(G, join_type):
+    """q8-shaped windowed join: persons x auctions per 30 s tumbling window, key = person id = seller,
+    duplicates on both sides, unmatched rows on both sides, several instants per watermark, rows that stay
+    buffered across watermarks."""
+    rng = np.random.default_rng(17)
+    W30 = 30 * S
+    left_b, right_b = [], []
+    for w in range(6):
+        ts = T0 + (w + 1) * W30 - 1
+        n_p, n_a = 400 + 37 * w, 1200 + 91 * w
+        pid = rng.integers(0, 500, n_p, dtype=np.int64)
+        left_b.append(O.Batch({"id": pid, "name_code": rng.integers(0, 10**6, n_p, dtype=np.int64),
+                               O.TIMESTAMP: np.full(n_p, ts, dtype=np.int64)}))
+        seller = rng.integers(250, 750, n_a, dtype=np.int64)
+        right_b.append(O.Batch({"seller": seller, "auction": np.arange(n_a, dtype=np.int64) + 1000 * w,
+                                "reserve": rng.integers(1, 10**5, n_a, dtype=np.int64),
+                                O.TIMESTAMP: np.full(n_a, ts, dtype=np.int64)}))
+    # one batch that mixes two instants (general path of process_side, instant_join.rs:149-171)
+    mixed = O.Batch.concat([right_b[4], right_b[5]])
+    right_b = right_b[:4] + [mixed]
+    cfg = O.JoinConfig(left_on=["id"], right_on=["seller"], join_type=join_type)
+
+    def drive(join):
+        ctx, out = O.OperatorContext(2), O.Collector()
+        for step in range(3):  # 2 windows of each side, then a watermark that releases only part of them
+            for b in left_b[2 * step:2 * step + 2]:
+                join.process_batch_index(0, 2, b, ctx, out)
+            for b in right_b[2 * step:2 * step + 2]:
+                join.process_batch_index(1, 2, b, ctx, out)
+            wm = T0 + (2 * step + 1) * W30 + 5  # releases the first of the two windows just sent... and older
+            for side in (0, 1):
+                ctx.watermarks.set(side, wm)
+            join.handle_watermark(wm, ctx, out)
+        for side in (0, 1):
+            ctx.watermarks.set(side, O.FINAL_WATERMARK)
+        join.handle_watermark(O.FINAL_WATERMARK, ctx, out)
+        rows = []
+        for b in out.batches:
+            rows += b.rows()
+        return rows
+
+    want = drive(O.InstantJoin(cfg))
+    got = drive(G.InstantJoin(cfg))
+    assert len(want) > 1000
+    assert multiset(got) == multiset(want)
+
+
+def test_avg_exact_sum_promotes_to_f64_on_large_values(G):
+    """AVG is derived from the exact integer sum while every value is < 2^31 in magnitude; the first larger
+    value parks its row, promotes the operator to f64 AVG accumulators (seeded from the integer sums) and
+    re-ingests it.  Results must match the oracle across the switch, and FLAG_AVG_F64 (f64 from the start)
+    must match too."""
+    from arroyo_b200 import ffi
+    rng = np.random.default_rng(33)
+    batches = gen_stream(rng, 120_000, 700, rate_per_s=10_000, batch=5000)
+    # from the middle of the stream on, sprinkle huge values (some would overflow an i64 sum quickly)
+    for b in batches[len(batches) // 2:]:
+        v = b["value"].copy()
+        v[::211] = (1 << 40) + 12345
+        v[5::499] = -(1 << 61)
+        b.cols["value"] = v
+    cfg = O.WindowAggConfig(width=5 * S, slide=S, key_names=["key"], aggs=SUM_AVG, window_index=1)
+    want = O.run_single_input(O.SlidingAggregatingWindowFunc(cfg), batches, S).batches
+    for flags in (0, ffi.FLAG_AVG_F64, ffi.FLAG_REMERGE_ONLY):
+        gop = G.SlidingAggregatingWindowFunc(cfg, flags=flags)
+        got = G.run_single_input(gop, batches, S).batches
+        assert_same(want, got, float_cols=("avg",))
+        if flags == 0:
+            assert gop.stats()["rows_deferred"] > 0  # the parked rows
+
+
+def test_avg_only_and_avg_with_min_max(G):
+    rng = np.random.default_rng(34)
+    batches = gen_stream(rng, 60_000, 300, rate_per_s=6_000, batch=3000)
+    for aggs in ([O.Agg("avg", "value", "avg")],
+                 [O.Agg("min", "value", "mn"), O.Agg("avg", "value", "avg"), O.Agg("max", "value", "mx")]):
+        cfg = O.WindowAggConfig(width=3 * S, slide=S, key_names=["key"], aggs=aggs, window_index=1)
+        want, got, _ = run_both(G, lambda: O.SlidingAggregatingWindowFunc(cfg),
+                                lambda: G.SlidingAggregatingWindowFunc(cfg), batches)
+        assert_same(want, got, float_cols=("avg",))
