@@ -38,6 +38,7 @@ constexpr int MAX_VALS = 4;
 constexpr int MAX_ACC = ARROYO_B200_MAX_AGGS + 1;
 constexpr int MAX_SEGS = 512;
 constexpr int MAX_RING = 4096;
+constexpr int RING_INLINE = 64;
 constexpr int MAX_MERGE = 4096;
 constexpr uint32_t ID_UNSET = 0xFFFFFFFFu;
 constexpr uint32_t ID_OVERFLOW = 0xFFFFFFFEu;
@@ -110,6 +111,11 @@ struct IngestParams {
   const long long* pane_bins;
   unsigned long long* const* pane_ptrs;
   unsigned long long id_cap;
+  // rings of up to RING_INLINE slots travel in the kernel parameters (constant bank): no table upload
+  int ring_inline;
+  int pad1;
+  long long ring_bins[RING_INLINE];
+  unsigned long long* ring_ptrs[RING_INLINE];
   int acc_kind[MAX_ACC];
   int acc_val[MAX_ACC];
   Counters* counters;
@@ -206,6 +212,14 @@ __device__ __forceinline__ void red_min_s64(unsigned long long* a, long long v) 
 }
 __device__ __forceinline__ void red_max_s64(unsigned long long* a, long long v) {
   asm volatile("red.global.max.s64 [%0], %1;" ::"l"(__cvta_generic_to_global(a)), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ long long ring_bin(const IngestParams& p, uint32_t slot) {
+  return p.ring_inline ? p.ring_bins[slot] : __ldg(p.pane_bins + slot);
+}
+__device__ __forceinline__ unsigned long long* ring_ptr(const IngestParams& p, uint32_t slot) {
+  return p.ring_inline ? p.ring_ptrs[slot]
+                       : reinterpret_cast<unsigned long long*>(__ldg(reinterpret_cast<const unsigned long long*>(p.pane_ptrs + slot)));
 }
 
 // Rows travel through the kernel as scalars (key, ts, up to MAX_VALS values): nothing in the hot loop
@@ -339,7 +353,7 @@ __device__ __noinline__ void slow_row(const IngestParams& p, long long key, long
                                       long long v1, long long v2, long long v3) {
   const uint32_t slot = (uint32_t)q & p.ring_mask;
   uint32_t id = 0;
-  bool ok = __ldg(p.pane_bins + slot) == (long long)(q * (uint64_t)p.slide);
+  bool ok = ring_bin(p, slot) == (long long)(q * (uint64_t)p.slide);
   if (ok && p.keyed) {
     const uint32_t pos = dict_home((uint64_t)key, p.dict.cap);
     const ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(p.dict.slots + pos));
@@ -355,8 +369,7 @@ __device__ __noinline__ void slow_row(const IngestParams& p, long long key, long
     defer_row(p, key, ts, v0, v1, v2, v3);
     return;
   }
-  unsigned long long* pane =
-      reinterpret_cast<unsigned long long*>(__ldg(reinterpret_cast<const unsigned long long*>(p.pane_ptrs + slot)));
+  unsigned long long* pane = ring_ptr(p, slot);
   atomicAdd(p.slot_rows + slot, 1ull);
   accumulate<NV, SIG>(p, v, pane, id);
 }
@@ -542,11 +555,9 @@ __global__ void __launch_bounds__(THREADS, AB_INGEST_MIN_BLOCKS) ingest_kernel(c
         flush_counts(p, pc, lane);
         if (live) {
           const uint32_t slot = (uint32_t)q & p.ring_mask;
-          const bool resident = __ldg(p.pane_bins + slot) == (long long)(q * (uint64_t)p.slide);
+          const bool resident = ring_bin(p, slot) == (long long)(q * (uint64_t)p.slide);
           pc.q = q;
-          pc.ptr = resident ? reinterpret_cast<unsigned long long*>(
-                                  __ldg(reinterpret_cast<const unsigned long long*>(p.pane_ptrs + slot)))
-                            : nullptr;
+          pc.ptr = resident ? ring_ptr(p, slot) : nullptr;
           maxq = max(maxq, q);
         }
       }
@@ -869,7 +880,7 @@ struct LaunchRec {
 
 struct PendingRelease {
   cudaEvent_t ev;
-  ArrowArray arr;  // moved-in copy; released when ev completes
+  std::vector<ArrowArray> arrs;  // moved-in copies; released when ev completes
 };
 
 class WindowAggOp final : public OpBase {
@@ -963,6 +974,7 @@ class WindowAggOp final : public OpBase {
   int next_launch_ = 0;
   std::deque<int> in_flight_;
   std::deque<PendingRelease> releases_;
+  std::vector<ArrowArray> zero_copy_inputs_;  // pinned input batches read in place by the next launch
 
   // deferred rows (two sets: one being filled, one being re-ingested)
   uint64_t defer_cap_ = 0;
@@ -1150,6 +1162,7 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
       AB_CUDA(cudaEventCreate(&launches_[i].t1));
     }
   }
+  if (c.reserved >= 16 && c.reserved <= 26) chunk_rows_ = 1ll << c.reserved;  // rows per ingest launch (default 2^22)
   defer_cap_ = (uint64_t)chunk_rows_ * 2;
   d_emit_panes_.alloc(MAX_MERGE * sizeof(void*));
   d_out_count_.alloc(sizeof(unsigned int));
@@ -1161,9 +1174,12 @@ WindowAggOp::~WindowAggOp() {
   cudaSetDevice(device_);
   cudaStreamSynchronize(stream_);
   for (auto& r : releases_) {
-    if (r.arr.release) r.arr.release(&r.arr);
+    for (auto& a : r.arrs)
+      if (a.release) a.release(&a);
     cudaEventDestroy(r.ev);
   }
+  for (auto& a : zero_copy_inputs_)
+    if (a.release) a.release(&a);
   for (int i = 0; i < NCHUNK; ++i)
     if (chunk_free_[i]) cudaEventDestroy(chunk_free_[i]);
   for (int i = 0; i < NLAUNCH; ++i) {
@@ -1419,7 +1435,8 @@ void WindowAggOp::poll_releases(bool wait) {
       if (e == cudaErrorNotReady) break;
       AB_CUDA(e);
     }
-    if (r.arr.release) r.arr.release(&r.arr);
+    for (auto& a : r.arrs)
+      if (a.release) a.release(&a);
     cudaEventDestroy(r.ev);
     releases_.pop_front();
   }
@@ -1479,6 +1496,42 @@ void WindowAggOp::process_batch(uint32_t, uint32_t, ArrowArray* batch, const Arr
       lookahead();
     }
   }
+  // Pinned (page-locked, device-mapped) Arrow buffers are read in place by the ingest kernel over PCIe:
+  // no staging copy, no extra HBM round trip.  Pageable buffers are staged with cudaMemcpyAsync.
+  if (n > 0) {
+    bool pinned = true;
+    const uint64_t* devp[ARROYO_B200_MAX_COLS] = {nullptr};
+    auto probe = [&](int c) {
+      cudaPointerAttributes at{};
+      if (cudaPointerGetAttributes(&at, cols[c].data) != cudaSuccess) {
+        cudaGetLastError();
+        pinned = false;
+        return;
+      }
+      if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) pinned = false;
+      else devp[c] = (const uint64_t*)at.devicePointer;
+    };
+    if (keyed_) probe(key_col_);
+    probe(ts_col_);
+    for (int v = 0; v < n_vals_; ++v) probe(val_cols_[v]);
+    if (pinned) {
+      int64_t done = 0;
+      while (done < n) {
+        int64_t take = std::min<int64_t>(n - done, chunk_rows_ - pending_rows_);
+        const long long* vals[MAX_VALS];
+        for (int v = 0; v < n_vals_; ++v) vals[v] = (const long long*)devp[val_cols_[v]] + done;
+        add_segment(keyed_ ? (const long long*)devp[key_col_] + done : nullptr, (const long long*)devp[ts_col_] + done,
+                    vals, take);
+        done += take;
+        if (done < n && pending_rows_ >= chunk_rows_) launch_pending();
+      }
+      st_.h2d_bytes += (uint64_t)n * 8 * (uint64_t)((keyed_ ? 1 : 0) + 1 + n_vals_);
+      zero_copy_inputs_.push_back(*batch);
+      batch->release = nullptr;
+      if (pending_rows_ >= chunk_rows_) launch_pending();
+      return;
+    }
+  }
   const int n_used = 2 + n_vals_;
   int64_t done = 0;
   while (done < n) {
@@ -1512,9 +1565,9 @@ void WindowAggOp::process_batch(uint32_t, uint32_t, ArrowArray* batch, const Arr
   PendingRelease r;
   AB_CUDA(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
   AB_CUDA(cudaEventRecord(r.ev, stream_));
-  r.arr = *batch;
+  r.arrs.push_back(*batch);
   batch->release = nullptr;
-  releases_.push_back(r);
+  releases_.push_back(std::move(r));
   if (cur_rows_ == chunk_rows_) {
     launch_pending();
     rotate_chunk();
@@ -1565,7 +1618,7 @@ void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk
     rows += (uint64_t)hs[i].n;
   }
   AB_CUDA(cudaMemcpyAsync(d_segs_[li].p, hs, segs_in.size() * sizeof(Segment), cudaMemcpyHostToDevice, stream_));
-  upload_ring();
+  if (ring_ > RING_INLINE) upload_ring();
   AB_CUDA(cudaMemsetAsync(slot_rows_.p, 0, ring_ * sizeof(unsigned long long), stream_));
   if (!defer_[defer_cur_][0].p) {
     for (int c = 0; c < 2 + n_vals_; ++c) defer_[defer_cur_][c].alloc(defer_cap_ * 8);
@@ -1592,6 +1645,12 @@ void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk
   p.pane_bins = d_pane_bins_.as<long long>();
   p.pane_ptrs = d_pane_ptrs_.as<unsigned long long*>();
   p.id_cap = id_cap_;
+  p.ring_inline = ring_ <= RING_INLINE ? 1 : 0;
+  if (p.ring_inline)
+    for (uint32_t i = 0; i < ring_; ++i) {
+      p.ring_bins[i] = h_pane_bins_[i];
+      p.ring_ptrs[i] = h_pane_ptrs_[i];
+    }
   for (int a = 0; a < n_acc_; ++a) {
     p.acc_kind[a] = acc_kind_[a];
     p.acc_val[a] = acc_val_[a];
@@ -1646,6 +1705,14 @@ void WindowAggOp::launch_pending() {
   int chunk = pending_uses_chunk_ ? cur_chunk_ : -1;
   pending_uses_chunk_ = false;
   launch_segments(segs, chunk);
+  if (!zero_copy_inputs_.empty()) {
+    // the pinned input batches these segments point into may be released once this kernel has run
+    PendingRelease r;
+    AB_CUDA(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
+    AB_CUDA(cudaEventRecord(r.ev, stream_));
+    r.arrs.swap(zero_copy_inputs_);
+    releases_.push_back(std::move(r));
+  }
 }
 
 void WindowAggOp::touch(int64_t bin) {

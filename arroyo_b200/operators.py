@@ -50,7 +50,7 @@ class _NativeOperator:
     kind = 0
 
     def __init__(self, device: int = 0, stream: int = 0, flags: int = 0, expected_keys: int = 0,
-                 task_index: int = 0, parallelism: int = 1):
+                 task_index: int = 0, parallelism: int = 1, chunk_log2: int = 0):
         self._lib = ffi.load()
         self._h = C.c_void_p()
         self._device = device
@@ -59,6 +59,7 @@ class _NativeOperator:
         self._expected_keys = expected_keys
         self._task_index = task_index
         self._parallelism = parallelism
+        self._chunk_log2 = chunk_log2
 
     def _create(self, cfg: ffi.OpConfig):
         cfg.device = self._device
@@ -67,6 +68,7 @@ class _NativeOperator:
         cfg.expected_keys = self._expected_keys
         cfg.task_index = self._task_index
         cfg.parallelism = self._parallelism
+        cfg.reserved = self._chunk_log2
         err = C.create_string_buffer(1024)
         st = self._lib.arroyo_b200_op_create(C.byref(cfg), C.byref(self._h), err, 1024)
         if st != ffi.OK:

@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--no-combine", action="store_true", help="measurement knob: no warp-combining of equal keys")
     ap.add_argument("--avg-f64", action="store_true", help="measurement knob: AVG with its own f64 accumulator")
+    ap.add_argument("--chunk-log2", type=int, default=0, help="rows per ingest launch = 2^n (default 22)")
     return ap.parse_args()
 
 
@@ -312,7 +313,7 @@ def run_ours(args):
     flags = ffi.FLAG_PROFILE | op_flags(args)
     stream = torch.cuda.current_stream().cuda_stream
     op = native.SlidingAggregatingWindowFunc(window_config(), input_schema=schema, device=local, stream=stream,
-                                             flags=flags, expected_keys=args.keys)
+                                             flags=flags, expected_keys=args.keys, chunk_log2=args.chunk_log2)
     rows_out = 0
 
     def step(p):

@@ -383,3 +383,41 @@ def test_avg_only_and_avg_with_min_max(G):
         want, got, _ = run_both(G, lambda: O.SlidingAggregatingWindowFunc(cfg),
                                 lambda: G.SlidingAggregatingWindowFunc(cfg), batches)
         assert_same(want, got, float_cols=("avg",))
+
+
+def test_pinned_host_batches_are_read_in_place(G):
+    """Arrow buffers in page-locked memory take the zero-copy path (no staging memcpy); results and the
+    release of every input batch are the same as for pageable buffers."""
+    import pyarrow as pa
+    import torch
+    import arroyo_b200 as ab
+    from arroyo_b200 import operators as native
+    from tests.gpu_ops import from_arrow
+    rng = np.random.default_rng(8)
+    batches = gen_stream(rng, 150_000, 4_000, rate_per_s=20_000, batch=10_000)
+    cfg = O.WindowAggConfig(width=3 * S, slide=S, key_names=["key"], aggs=SUM_AVG, window_index=1)
+    want = O.run_single_input(O.SlidingAggregatingWindowFunc(cfg), batches, S).batches
+    keep = []
+
+    def pinned_batch(b):
+        arrs = []
+        for name in ("key", "value", O.TIMESTAMP):
+            h = torch.empty(b.num_rows, dtype=torch.int64, pin_memory=True)
+            h.numpy()[:] = b[name]
+            keep.append(h)
+            typ = pa.timestamp("ns") if name == O.TIMESTAMP else pa.int64()
+            arrs.append(pa.Array.from_buffers(typ, b.num_rows, [None, pa.py_buffer(h.numpy())]))
+        return pa.RecordBatch.from_arrays(arrs, names=["key", "value", O.TIMESTAMP])
+
+    op = native.SlidingAggregatingWindowFunc(cfg)
+    ctx, out, gen = ab.OperatorContext(1), ab.Collector(), ab.WatermarkGenerator(S)
+    for b in batches:
+        op.process_batch(pinned_batch(b), ctx, out)
+        wm = gen.on_batch(int(b[O.TIMESTAMP].min()), int(b[O.TIMESTAMP].max()))
+        if wm is not None:
+            ctx.watermarks.set(0, wm)
+            op.handle_watermark(wm, ctx, out)
+    ctx.watermarks.set(0, ab.FINAL_WATERMARK)
+    op.handle_watermark(ab.FINAL_WATERMARK, ctx, out)
+    assert_same(want, [from_arrow(b) for b in out.batches], float_cols=("avg",))
+    assert op.stats()["h2d_bytes"] == 150_000 * 24
