@@ -655,12 +655,13 @@ struct EmitParams {
   uint32_t n_ids;
   int keyed;
   int acc_kind[MAX_ACC];
-  int n_aggs;
-  int agg_kind[ARROYO_B200_MAX_AGGS];
-  int agg_acc[ARROYO_B200_MAX_AGGS];
+  // Output columns are attached to the accumulator they are computed from (no dynamic indexing in the
+  // kernel): out_raw[a] receives the accumulator as is (COUNT(*) from a = 0, SUM / MIN / MAX), out_avg[a]
+  // receives accumulator / rows as f64 (AVG).
+  unsigned long long* out_raw[MAX_ACC];
+  unsigned long long* out_avg[MAX_ACC];
   const long long* id_keys;
   long long* out_key;
-  unsigned long long* out_agg[ARROYO_B200_MAX_AGGS];
   long long* out_wstart;
   long long* out_wend;
   long long* out_ts;
@@ -677,87 +678,127 @@ struct EmitParams {
 
 constexpr int EMIT_THREADS = 256;
 
+__device__ __forceinline__ unsigned long long merge_acc(int kind, unsigned long long a, unsigned long long v) {
+  switch (kind) {
+    case ACC_SUM_F64:
+      return (unsigned long long)__double_as_longlong(__longlong_as_double((long long)a) + __longlong_as_double((long long)v));
+    case ACC_MIN_I64: return (unsigned long long)min((long long)a, (long long)v);
+    case ACC_MAX_I64: return (unsigned long long)max((long long)a, (long long)v);
+    default: return a + v;  // ACC_ROWS, ACC_SUM_I64 (wrapping)
+  }
+}
+__device__ __forceinline__ unsigned long long unmerge_acc(int kind, unsigned long long a, unsigned long long v) {
+  if (kind == ACC_SUM_F64)
+    return (unsigned long long)__double_as_longlong(__longlong_as_double((long long)a) - __longlong_as_double((long long)v));
+  return a - v;
+}
+
+// Finalises and writes one output row (K4 finalise + K5 projection).
+template <int NACC>
+__device__ __forceinline__ void emit_row(const EmitParams& p, unsigned int o, const unsigned long long (&acc)[NACC],
+                                         long long key) {
+  const unsigned long long rows = acc[0];
+  if (p.keyed) p.out_key[o] = key;
+  if (p.partial) {
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+      p.out_state[a][o] = acc[a];
+    p.out_ts[o] = p.ts;
+    return;
+  }
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) {
+    if (p.out_raw[a]) p.out_raw[a][o] = acc[a];
+    if (p.out_avg[a]) {
+      // f64 accumulator: sum of inputs cast to f64 (DataFusion's AVG state); integer accumulator: the exact
+      // sum, converted once (guarded against overflow on ingest)
+      const double num = p.acc_kind[a] == ACC_SUM_F64 ? __longlong_as_double((long long)acc[a]) : (double)(long long)acc[a];
+      p.out_avg[a][o] = (unsigned long long)__double_as_longlong(num / (double)rows);
+    }
+  }
+  if (p.out_wstart) {
+    p.out_wstart[o] = p.wstart;
+    p.out_wend[o] = p.wend;
+  }
+  p.out_ts[o] = p.ts;
+}
+
+// Two consecutive dense ids per thread: every accumulator array is read and written with 128-bit
+// accesses; the block compacts its valid rows with two ballots per warp and one atomic per block.
+template <bool RUNNING, int NACC>
 __global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(const __grid_constant__ EmitParams p) {
   __shared__ unsigned int s_warp[EMIT_THREADS / 32];
   __shared__ unsigned int s_base;
   const int tid = threadIdx.x;
   const int lane = tid & 31, w = tid >> 5;
-  const uint32_t n_iter = (p.n_ids + EMIT_THREADS - 1) / EMIT_THREADS;
+  const uint32_t n_pairs = (p.n_ids + 1) / 2;
+  const uint32_t n_iter = (n_pairs + EMIT_THREADS - 1) / EMIT_THREADS;
   for (uint32_t it = blockIdx.x; it < n_iter; it += gridDim.x) {
-    const uint32_t id = it * EMIT_THREADS + tid;
-    unsigned long long acc[MAX_ACC];
-    unsigned long long rows = 0;
-    if (id < p.n_ids) {
-      if (p.running) {
+    const uint32_t pair = it * EMIT_THREADS + tid;
+    const uint32_t id = pair * 2;
+    unsigned long long acc0[NACC], acc1[NACC];
 #pragma unroll
-        for (int a = 0; a < MAX_ACC; ++a)
-          if (a < p.n_acc) acc[a] = p.running[(unsigned long long)a * p.id_cap + id];
+    for (int a = 0; a < NACC; ++a) {
+      acc0[a] = 0;
+      acc1[a] = 0;
+    }
+    const bool in0 = id < p.n_ids, in1 = id + 1 < p.n_ids;
+    if (in0) {
+      if (RUNNING) {
+#pragma unroll
+        for (int a = 0; a < NACC; ++a)
+          {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p.running + (unsigned long long)a * p.id_cap + id);
+            acc0[a] = v.x;
+            acc1[a] = v.y;
+          }
         for (int k = 0; k < p.n_panes; ++k) {
           const unsigned long long* pane = p.panes[k];
           const bool add = k < p.n_add;
 #pragma unroll
-          for (int a = 0; a < MAX_ACC; ++a) {
-            if (a < p.n_acc) {
-              unsigned long long v = __ldcs(pane + (unsigned long long)a * p.id_cap + id);
-              if (p.acc_kind[a] == ACC_SUM_F64) {
-                double d = __longlong_as_double((long long)acc[a]);
-                double x = __longlong_as_double((long long)v);
-                acc[a] = (unsigned long long)__double_as_longlong(add ? d + x : d - x);
-              } else {
-                acc[a] = add ? acc[a] + v : acc[a] - v;
-              }
+          for (int a = 0; a < NACC; ++a)
+            {
+              const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2*>(pane + (unsigned long long)a * p.id_cap + id));
+              const int kind = p.acc_kind[a];
+              acc0[a] = add ? merge_acc(kind, acc0[a], v.x) : unmerge_acc(kind, acc0[a], v.x);
+              acc1[a] = add ? merge_acc(kind, acc1[a], v.y) : unmerge_acc(kind, acc1[a], v.y);
             }
-          }
         }
-        rows = acc[0];
         // a key that left the window restarts from exactly zero (no f64 drift carried over)
+        const bool z0 = acc0[0] == 0, z1 = acc1[0] == 0;
 #pragma unroll
-        for (int a = 0; a < MAX_ACC; ++a) {
-          if (a < p.n_acc) {
-            if (rows == 0) acc[a] = 0;
-            p.running[(unsigned long long)a * p.id_cap + id] = acc[a];
+        for (int a = 0; a < NACC; ++a)
+          {
+            if (z0) acc0[a] = 0;
+            if (z1) acc1[a] = 0;
+            *reinterpret_cast<ulonglong2*>(p.running + (unsigned long long)a * p.id_cap + id) = make_ulonglong2(acc0[a], acc1[a]);
           }
-        }
       } else {
 #pragma unroll
-        for (int a = 0; a < MAX_ACC; ++a) {
-          if (a < p.n_acc) {
-            acc[a] = 0;
-            if (p.acc_kind[a] == ACC_MIN_I64) acc[a] = (unsigned long long)LLONG_MAX;
-            if (p.acc_kind[a] == ACC_MAX_I64) acc[a] = (unsigned long long)LLONG_MIN;
+        for (int a = 0; a < NACC; ++a)
+          {
+            unsigned long long ident = 0;
+            if (p.acc_kind[a] == ACC_MIN_I64) ident = (unsigned long long)LLONG_MAX;
+            if (p.acc_kind[a] == ACC_MAX_I64) ident = (unsigned long long)LLONG_MIN;
+            acc0[a] = ident;
+            acc1[a] = ident;
           }
-        }
         for (int k = 0; k < p.n_panes; ++k) {
           const unsigned long long* pane = p.panes[k];
 #pragma unroll
-          for (int a = 0; a < MAX_ACC; ++a) {
-            if (a < p.n_acc) {
-              unsigned long long v = __ldcs(pane + (unsigned long long)a * p.id_cap + id);
-              switch (p.acc_kind[a]) {
-                case ACC_ROWS:
-                case ACC_SUM_I64:
-                  acc[a] += v;
-                  break;
-                case ACC_SUM_F64:
-                  acc[a] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)acc[a]) +
-                                                                    __longlong_as_double((long long)v));
-                  break;
-                case ACC_MIN_I64:
-                  acc[a] = (unsigned long long)min((long long)acc[a], (long long)v);
-                  break;
-                case ACC_MAX_I64:
-                  acc[a] = (unsigned long long)max((long long)acc[a], (long long)v);
-                  break;
-              }
+          for (int a = 0; a < NACC; ++a)
+            {
+              const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2*>(pane + (unsigned long long)a * p.id_cap + id));
+              const int kind = p.acc_kind[a];
+              acc0[a] = merge_acc(kind, acc0[a], v.x);
+              acc1[a] = merge_acc(kind, acc1[a], v.y);
             }
-          }
         }
-        rows = acc[0];
       }
     }
-    const bool valid = rows != 0;
-    const unsigned int ballot = __ballot_sync(0xffffffffu, valid);
-    if (lane == 0) s_warp[w] = __popc(ballot);
+    const bool v0 = in0 && acc0[0] != 0, v1 = in1 && acc1[0] != 0;
+    const unsigned int b0 = __ballot_sync(0xffffffffu, v0), b1 = __ballot_sync(0xffffffffu, v1);
+    if (lane == 0) s_warp[w] = __popc(b0) + __popc(b1);
     __syncthreads();
     if (tid == 0) {
       unsigned int total = 0;
@@ -769,46 +810,12 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(const __grid_constan
       s_base = total ? atomicAdd(p.out_count, total) : 0u;
     }
     __syncthreads();
-    if (valid) {
-      const unsigned int o = s_base + s_warp[w] + __popc(ballot & ((1u << lane) - 1u));
-      if (p.keyed) p.out_key[o] = p.id_keys[id];
-      if (p.partial) {
-#pragma unroll
-        for (int a = 0; a < MAX_ACC; ++a)
-          if (a < p.n_acc) p.out_state[a][o] = acc[a];
-        p.out_ts[o] = p.ts;
-      } else {
-#pragma unroll
-        for (int g = 0; g < ARROYO_B200_MAX_AGGS; ++g) {
-          if (g < p.n_aggs) {
-            unsigned long long v;
-            switch (p.agg_kind[g]) {
-              case ARROYO_B200_AGG_COUNT_STAR:
-                v = rows;
-                break;
-              case ARROYO_B200_AGG_AVG_I64: {
-                // f64 accumulator: sum of inputs cast to f64 (DataFusion's AVG state); integer
-                // accumulator: the exact sum, converted once (guarded against overflow on ingest)
-                const unsigned long long s = acc[p.agg_acc[g]];
-                const double num = p.acc_kind[p.agg_acc[g]] == ACC_SUM_F64 ? __longlong_as_double((long long)s)
-                                                                           : (double)(long long)s;
-                v = (unsigned long long)__double_as_longlong(num / (double)rows);
-                break;
-              }
-              default:
-                v = acc[p.agg_acc[g]];
-                break;
-            }
-            p.out_agg[g][o] = v;
-          }
-        }
-        if (p.out_wstart) {
-          p.out_wstart[o] = p.wstart;
-          p.out_wend[o] = p.wend;
-        }
-        p.out_ts[o] = p.ts;
-      }
-    }
+    const unsigned int lt = (1u << lane) - 1u;
+    const unsigned int o0 = s_base + s_warp[w] + __popc(b0 & lt) + __popc(b1 & lt);
+    ulonglong2 keys = make_ulonglong2(0, 0);
+    if ((v0 || v1) && p.keyed) keys = *reinterpret_cast<const ulonglong2*>(p.id_keys + id);
+    if (v0) emit_row<NACC>(p, o0, acc0, (long long)keys.x);
+    if (v1) emit_row<NACC>(p, o0 + (v0 ? 1u : 0u), acc1, (long long)keys.y);
     __syncthreads();
   }
 }
@@ -959,7 +966,7 @@ class WindowAggOp final : public OpBase {
   // staging
   static constexpr int NCHUNK = 3;
   static constexpr int NLAUNCH = 3;
-  int64_t chunk_rows_ = 1 << 22;
+  int64_t chunk_rows_ = 1 << 23;
   DevBuf chunk_[NCHUNK];
   cudaEvent_t chunk_free_[NCHUNK] = {nullptr, nullptr, nullptr};
   int cur_chunk_ = 0;
@@ -1099,7 +1106,13 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
     agg_acc_[g] = found;
   }
   profile_ = (c.flags & ARROYO_B200_FLAG_PROFILE) != 0;
-  running_mode_ = sliding_ && invertible_ && !(c.flags & ARROYO_B200_FLAG_REMERGE_ONLY) && width_ > slide_;
+  // The running window W += entering - leaving is used only while every accumulator is exactly invertible
+  // (row counts, wrapping integer sums).  An f64 accumulator would carry cancellation error from rows that
+  // have left the window (measured: 1e-5 relative after a 2^61 value passed through), so those
+  // configurations re-merge the panes of each window like the reference does.
+  bool has_f64 = false;
+  for (int a = 1; a < n_acc_; ++a) has_f64 = has_f64 || acc_kind_[a] == ACC_SUM_F64;
+  running_mode_ = sliding_ && invertible_ && !has_f64 && !(c.flags & ARROYO_B200_FLAG_REMERGE_ONLY) && width_ > slide_;
 
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -1162,7 +1175,7 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
       AB_CUDA(cudaEventCreate(&launches_[i].t1));
     }
   }
-  if (c.reserved >= 16 && c.reserved <= 26) chunk_rows_ = 1ll << c.reserved;  // rows per ingest launch (default 2^22)
+  if (c.reserved >= 16 && c.reserved <= 26) chunk_rows_ = 1ll << c.reserved;  // rows per ingest launch (default 2^23)
   defer_cap_ = (uint64_t)chunk_rows_ * 2;
   d_emit_panes_.alloc(MAX_MERGE * sizeof(void*));
   d_out_count_.alloc(sizeof(unsigned int));
@@ -1369,6 +1382,18 @@ void WindowAggOp::promote_avg() {
     agg_acc_[g] = found;
   }
   avg_exact_ = false;
+  // f64 accumulators are not exactly invertible: leave running mode (see the constructor)
+  if (running_mode_) {
+    running_mode_ = false;
+    in_running_.clear();
+    for (auto& z : zombies_) {
+      release_block(z.second.dev);
+      release_block(z.second.frozen);
+    }
+    zombies_.clear();
+    release_block(running_);
+    running_ = nullptr;
+  }
   relayout_blocks(old_n_acc, f64_from);
 }
 
@@ -1496,9 +1521,10 @@ void WindowAggOp::process_batch(uint32_t, uint32_t, ArrowArray* batch, const Arr
       lookahead();
     }
   }
-  // Pinned (page-locked, device-mapped) Arrow buffers are read in place by the ingest kernel over PCIe:
-  // no staging copy, no extra HBM round trip.  Pageable buffers are staged with cudaMemcpyAsync.
-  if (n > 0) {
+  // ARROYO_B200_FLAG_ZERO_COPY: pinned (page-locked, device-mapped) Arrow buffers are read in place by the
+  // ingest kernel over PCIe: no staging memory.  Measured slower than DMA staging on this pool's hosts
+  // (0.96 vs 1.22 G rows/s end to end: SM loads over PCIe ~23 GB/s vs copy engine ~29 GB/s), hence opt-in.
+  if (n > 0 && (cfg.flags & ARROYO_B200_FLAG_ZERO_COPY)) {
     bool pinned = true;
     const uint64_t* devp[ARROYO_B200_MAX_COLS] = {nullptr};
     auto probe = [&](int c) {
@@ -1859,11 +1885,20 @@ int64_t WindowAggOp::run_emit(const std::vector<const unsigned long long*>& bloc
   p.n_ids = n_ids;
   p.keyed = keyed_ ? 1 : 0;
   for (int a = 0; a < n_acc_; ++a) p.acc_kind[a] = acc_kind_[a];
-  p.n_aggs = n_aggs_;
-  for (int g = 0; g < n_aggs_; ++g) {
-    p.agg_kind[g] = agg_kind_[g];
-    p.agg_acc[g] = agg_acc_[g];
-    p.out_agg[g] = os->agg[g].as<unsigned long long>();
+  std::vector<std::pair<unsigned long long*, unsigned long long*>> dup_cols;  // (src, dst): same output twice
+  for (int a = 0; a < MAX_ACC; ++a) {
+    p.out_raw[a] = nullptr;
+    p.out_avg[a] = nullptr;
+  }
+  if (!partial) {
+    for (int g = 0; g < n_aggs_; ++g) {
+      unsigned long long* col = os->agg[g].as<unsigned long long>();
+      const bool avg = agg_kind_[g] == ARROYO_B200_AGG_AVG_I64;
+      const int a = agg_kind_[g] == ARROYO_B200_AGG_COUNT_STAR ? 0 : agg_acc_[g];
+      unsigned long long*& slot = avg ? p.out_avg[a] : p.out_raw[a];
+      if (slot) dup_cols.emplace_back(slot, col);
+      else slot = col;
+    }
   }
   p.id_keys = id_keys_.as<long long>();
   p.out_key = os->key.as<long long>();
@@ -1884,7 +1919,7 @@ int64_t WindowAggOp::run_emit(const std::vector<const unsigned long long*>& bloc
       p.out_state[a] = os->state[a].as<unsigned long long>();
     }
   }
-  const uint32_t n_iter = (n_ids + EMIT_THREADS - 1) / EMIT_THREADS;
+  const uint32_t n_iter = ((n_ids + 1) / 2 + EMIT_THREADS - 1) / EMIT_THREADS;
   int grid = (int)std::min<uint32_t>(std::max<uint32_t>(n_iter, 1u), (uint32_t)num_sms_ * 8);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (profile_) {
@@ -1892,7 +1927,24 @@ int64_t WindowAggOp::run_emit(const std::vector<const unsigned long long*>& bloc
     AB_CUDA(cudaEventCreate(&e1));
     AB_CUDA(cudaEventRecord(e0, stream_));
   }
-  emit_kernel<<<grid, EMIT_THREADS, 0, stream_>>>(p);
+#define AB_EMIT(N)                                                               \
+  do {                                                                          \
+    if (use_running) emit_kernel<true, N><<<grid, EMIT_THREADS, 0, stream_>>>(p); \
+    else emit_kernel<false, N><<<grid, EMIT_THREADS, 0, stream_>>>(p);            \
+  } while (0)
+  switch (n_acc_) {
+    case 1: AB_EMIT(1); break;
+    case 2: AB_EMIT(2); break;
+    case 3: AB_EMIT(3); break;
+    case 4: AB_EMIT(4); break;
+    case 5: AB_EMIT(5); break;
+    case 6: AB_EMIT(6); break;
+    case 7: AB_EMIT(7); break;
+    case 8: AB_EMIT(8); break;
+    default: AB_EMIT(9); break;
+  }
+  static_assert(MAX_ACC == 9, "emit_kernel instantiations cover 1..MAX_ACC accumulators");
+#undef AB_EMIT
   AB_CUDA(cudaGetLastError());
   if (profile_) {
     AB_CUDA(cudaEventRecord(e1, stream_));
@@ -1903,7 +1955,10 @@ int64_t WindowAggOp::run_emit(const std::vector<const unsigned long long*>& bloc
   ++st_.emit_launches;
   AB_CUDA(cudaMemcpyAsync(h_out_count_.p, d_out_count_.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream_));
   AB_CUDA(cudaStreamSynchronize(stream_));
-  return (int64_t)*h_out_count_.as<unsigned int>();
+  const int64_t n_out = (int64_t)*h_out_count_.as<unsigned int>();
+  for (auto& d : dup_cols)
+    if (n_out) AB_CUDA(cudaMemcpyAsync(d.second, d.first, (size_t)n_out * 8, cudaMemcpyDeviceToDevice, stream_));
+  return n_out;
 }
 
 static void* d2h_column(const void* dev, int64_t n, cudaStream_t s, uint64_t* bytes) {

@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--no-combine", action="store_true", help="measurement knob: no warp-combining of equal keys")
     ap.add_argument("--avg-f64", action="store_true", help="measurement knob: AVG with its own f64 accumulator")
-    ap.add_argument("--chunk-log2", type=int, default=0, help="rows per ingest launch = 2^n (default 22)")
+    ap.add_argument("--chunk-log2", type=int, default=0, help="rows per ingest launch = 2^n (default 23)")
     return ap.parse_args()
 
 

@@ -152,7 +152,7 @@ typedef struct ArroyoB200OpConfig {
 
   uint64_t expected_keys;   /* capacity hint for the key dictionary (0 = default)         */
   uint32_t flags;           /* ARROYO_B200_FLAG_*                                         */
-  uint32_t reserved;        /* 0, or log2(rows per ingest launch) in [16, 26] (default 22)     */
+  uint32_t reserved;        /* 0, or log2(rows per ingest launch) in [16, 26] (default 23)     */
 } ArroyoB200OpConfig;
 
 #define ARROYO_B200_FLAG_PROFILE 1u       /* time kernels with CUDA events (op_stats)      */
@@ -162,6 +162,8 @@ typedef struct ArroyoB200OpConfig {
 #define ARROYO_B200_FLAG_AVG_F64 8u       /* AVG(Int64) with its own f64 accumulator from the start  */
                                           /* (default: exact integer sum, promoted on demand)        */
 #define ARROYO_B200_FLAG_COMBINE 4u       /* (default behaviour; kept for ABI stability)   */
+#define ARROYO_B200_FLAG_ZERO_COPY 32u    /* read pinned host batches in place over PCIe  */
+                                          /* instead of staging them with the copy engine */
 #define ARROYO_B200_FLAG_NO_COMBINE 16u   /* do not warp-combine equal keys before the     */
                                           /* atomics (measurement knob)                    */
 

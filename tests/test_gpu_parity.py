@@ -386,8 +386,8 @@ def test_avg_only_and_avg_with_min_max(G):
 
 
 def test_pinned_host_batches_are_read_in_place(G):
-    """Arrow buffers in page-locked memory take the zero-copy path (no staging memcpy); results and the
-    release of every input batch are the same as for pageable buffers."""
+    """FLAG_ZERO_COPY: Arrow buffers in page-locked memory are read in place (no staging memcpy); results
+    and the release of every input batch are the same as for staged buffers."""
     import pyarrow as pa
     import torch
     import arroyo_b200 as ab
@@ -409,7 +409,8 @@ def test_pinned_host_batches_are_read_in_place(G):
             arrs.append(pa.Array.from_buffers(typ, b.num_rows, [None, pa.py_buffer(h.numpy())]))
         return pa.RecordBatch.from_arrays(arrs, names=["key", "value", O.TIMESTAMP])
 
-    op = native.SlidingAggregatingWindowFunc(cfg)
+    from arroyo_b200 import ffi
+    op = native.SlidingAggregatingWindowFunc(cfg, flags=ffi.FLAG_ZERO_COPY)
     ctx, out, gen = ab.OperatorContext(1), ab.Collector(), ab.WatermarkGenerator(S)
     for b in batches:
         op.process_batch(pinned_batch(b), ctx, out)
