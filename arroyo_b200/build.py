@@ -39,8 +39,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     ]
     if verbose:
         flags += ["-Xptxas", "-v"]
-    if os.environ.get("AB_INGEST_MIN_BLOCKS"):  # tuning knob for experiments
-        flags += ["-DAB_INGEST_MIN_BLOCKS=" + os.environ["AB_INGEST_MIN_BLOCKS"]]
+    for knob in ("AB_INGEST_MIN_BLOCKS", "AB_INGEST_PREFETCH"):  # tuning knobs for experiments
+        if os.environ.get(knob):
+            flags += [f"-D{knob}=" + os.environ[knob]]
     build_dir = os.path.join(HERE, "build")
     os.makedirs(build_dir, exist_ok=True)
     procs = []

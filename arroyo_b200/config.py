@@ -24,6 +24,9 @@ class WindowAggConfig:
     aggs: List[Agg] = field(default_factory=list)
     final_projection: bool = True
     window_index: int = 0
+    # final stage of a partial -> shuffle -> final plan: name of the input column that carries how many
+    # original rows each (partial-aggregate) input row stands for; None = inputs are raw rows
+    partial_count_col: Optional[str] = None
 
 
 @dataclass

@@ -100,6 +100,19 @@ class WatermarkGenerator:
         self.max_watermark = 0
         self.idle = False
 
+    def process_device_batch(self, ts_ptr: int, n_rows: int, device: int = 0, stream: int = 0) -> Optional[int]:
+        """The generator's two reductions run on the device (arroyo_b200_ts_minmax), then the emission rule."""
+        import ctypes as C
+
+        from . import ffi
+        mn, mx = C.c_int64(0), C.c_int64(0)
+        st = ffi.load().arroyo_b200_ts_minmax(device, stream, ts_ptr, n_rows, C.byref(mn), C.byref(mx))
+        if st != ffi.OK:
+            raise ffi.ArroyoB200Error(st, "ts_minmax failed")
+        if n_rows == 0:
+            return None
+        return self.on_batch(mn.value, mx.value)
+
     def on_batch(self, min_ts: int, max_ts: int) -> Optional[int]:
         watermark = min_ts - self.delay
         self.max_watermark = max(self.max_watermark, watermark)

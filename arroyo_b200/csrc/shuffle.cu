@@ -5,6 +5,8 @@
 // (hash / (u64::MAX / n)) % n, bucket rows per destination.  The reference sorts the whole batch by
 // destination and gathers every column (K2/K6); here it is histogram -> scan -> scatter, and the
 // per-destination segments are the send buffers of the NCCL all-to-all.
+#include <climits>
+
 #include "common.cuh"
 
 namespace ab {
@@ -71,6 +73,30 @@ __global__ void scan_kernel(unsigned int* __restrict__ block_hist, uint32_t n_bl
   }
 }
 
+// WatermarkGenerator::process_batch (arroyo-worker/src/arrow/watermark_generator.rs:150-197): the two
+// reductions it runs on every batch -- max(_timestamp) and min(_timestamp) (the watermark expression is
+// `_timestamp - delay`, so its minimum is min(_timestamp) - delay).
+__global__ void __launch_bounds__(256) minmax_kernel(const long long* __restrict__ ts, long long n,
+                                                     long long* __restrict__ out /* [min, max] */) {
+  long long mn = LLONG_MAX, mx = LLONG_MIN;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const long long t = __ldcs(ts + i);
+    mn = min(mn, t);
+    mx = max(mx, t);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0 && mn != LLONG_MAX) {
+    atomicMin(out, mn);
+    atomicMax(out + 1, mx);
+  }
+}
+
 struct ScatterParams {
   const long long* in[MAX_PCOLS];
   long long* out[MAX_PCOLS];
@@ -118,6 +144,38 @@ struct ArroyoB200Partitioner {
 };
 
 extern "C" {
+
+int32_t arroyo_b200_ts_minmax(int32_t device, uint64_t stream, uint64_t ts_dev, int64_t n_rows, int64_t* out_min,
+                               int64_t* out_max) {
+  if (!ts_dev || n_rows < 0 || !out_min || !out_max) return ARROYO_B200_INVALID_ARGUMENT;
+  try {
+    AB_CUDA(cudaSetDevice(device));
+    static thread_local long long* d_out = nullptr;
+    static thread_local int d_dev = -1;
+    if (!d_out || d_dev != device) {
+      AB_CUDA(cudaMalloc(&d_out, 2 * sizeof(long long)));
+      d_dev = device;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long init[2] = {LLONG_MAX, LLONG_MIN};
+    AB_CUDA(cudaMemcpyAsync(d_out, init, sizeof init, cudaMemcpyHostToDevice, st));
+    if (n_rows > 0) {
+      int grid = (int)std::min<int64_t>((n_rows + 255) / 256, 148 * 8);
+      minmax_kernel<<<grid, 256, 0, st>>>((const long long*)ts_dev, n_rows, d_out);
+      AB_CUDA(cudaGetLastError());
+    }
+    long long h[2];
+    AB_CUDA(cudaMemcpyAsync(h, d_out, sizeof h, cudaMemcpyDeviceToHost, st));
+    AB_CUDA(cudaStreamSynchronize(st));
+    *out_min = h[0];
+    *out_max = h[1];
+    return ARROYO_B200_OK;
+  } catch (const Error& e) {
+    return e.status;
+  } catch (...) {
+    return ARROYO_B200_RUNTIME;
+  }
+}
 
 int32_t arroyo_b200_partitioner_create(int32_t device, uint64_t stream, int32_t n_dest, int32_t n_cols,
                                        int32_t key_col, int64_t max_rows, ArroyoB200Partitioner** out) {

@@ -106,6 +106,8 @@ struct IngestParams {
   unsigned long long late_q;  // late_bin / slide (0 when there is no watermark yet)
   unsigned int guard_vals;    // bit x set: value slot x must satisfy |v| < 2^31 (exact-sum AVG, see avg_exact_)
   int combine;                // warp-combine equal (pane, id) before the REDs
+  int rows_slot;              // value slot carrying the row count of a partial-aggregate input row, or -1
+  int pad2;
   uint32_t ring_mask;
   int n_acc;
   const long long* pane_bins;
@@ -318,10 +320,17 @@ __device__ __forceinline__ void red_kind(int kind, unsigned long long* dst, long
   }
 }
 
+// How many original rows an input row stands for: 1, or the carried count of a partial-aggregate row.
+__device__ __forceinline__ unsigned long long rows_of(const IngestParams& p, const Vals& v) {
+  const int x = p.rows_slot;
+  if (x < 0) return 1ull;
+  return (unsigned long long)(x == 0 ? v.v0 : x == 1 ? v.v1 : x == 2 ? v.v2 : v.v3);
+}
+
 // The RED updates of one row into pane block `pane` (K3: partial aggregate).
 template <int NV, int SIG>
 __device__ __forceinline__ void accumulate(const IngestParams& p, const Vals& v, unsigned long long* pane, uint32_t id) {
-  red_add_u64(pane + id, 1ull);
+  red_add_u64(pane + id, rows_of(p, v));
   if (SIG == GENERIC_SIG) {
 #pragma unroll
     for (int a = 1; a < MAX_ACC; ++a) {
@@ -462,7 +471,12 @@ __device__ __forceinline__ void combine_accumulate(const IngestParams& p, const 
   const unsigned peers = __match_any_sync(0xffffffffu, gkey);
   const bool leader = (__ffs(peers) - 1) == lane;
   unsigned long long* pane = pc.ptr;
-  if (fast && leader) red_add_u64(pane + id, (unsigned long long)__popc(peers));
+  if (p.rows_slot < 0) {
+    if (fast && leader) red_add_u64(pane + id, (unsigned long long)__popc(peers));
+  } else {
+    const long long r = group_reduce(ACC_SUM_I64, peers, (long long)rows_of(p, v));
+    if (fast && leader) red_add_u64(pane + id, (unsigned long long)r);
+  }
   if (SIG == GENERIC_SIG) {
 #pragma unroll
     for (int a = 1; a < MAX_ACC; ++a) {
@@ -492,6 +506,9 @@ __device__ __forceinline__ void combine_accumulate(const IngestParams& p, const 
   }
 }
 
+#ifndef AB_INGEST_PREFETCH
+#define AB_INGEST_PREFETCH 1
+#endif
 #ifndef AB_INGEST_MIN_BLOCKS
 #define AB_INGEST_MIN_BLOCKS 5
 #endif
@@ -526,24 +543,37 @@ __global__ void __launch_bounds__(THREADS, AB_INGEST_MIN_BLOCKS) ingest_kernel(c
     const int cnt = nrem < TILE ? (int)nrem : TILE;
 
     // One row per lane per iteration: a warp instruction covers 256 contiguous bytes per column, and
-    // with eight resident blocks per SM there are 2048 independent probe chains in flight per SM
-    // (profiles/r01_probe2.txt: occupancy beats rows-per-thread for the scattered part).
-    // The trip count is uniform so that the warp votes below stay convergent in tail tiles.
+    // with several resident blocks per SM there are well over a thousand independent probe chains in
+    // flight per SM (profiles/r01_probe2.txt: occupancy beats rows-per-thread for the scattered part).
+    // The next row's columns are requested before the current row is processed, so the streaming loads
+    // overlap the dependent probe -> RED chain.  The trip count is uniform so that the warp votes below
+    // stay convergent in tail tiles.
+    long long nkey = 0, nts = 0;
+    long long nv[NV > 0 ? NV : 1] = {0};
+    if (tid < cnt) {
+      if (keyed) nkey = __ldcs(ldg_ptr(&sg->key) + base + tid);
+      nts = __ldcs(ldg_ptr(&sg->ts) + base + tid);
+#pragma unroll
+      for (int x = 0; x < NV; ++x) nv[x] = __ldcs(ldg_ptr(&sg->val[x]) + base + tid);
+    }
 #pragma unroll 1
     for (int i = tid; i < TILE; i += THREADS) {
       const bool valid = i < cnt;
-      long long key = 0, ts = 0;
-      long long v[NV > 0 ? NV : 1] = {0};
-      ulonglong2 raw = {0, 0};
-      if (valid) {
-        if (keyed) {
-          key = __ldcs(ldg_ptr(&sg->key) + base + i);
-          raw = __ldcg(reinterpret_cast<const ulonglong2*>(p.dict.slots + dict_home((uint64_t)key, p.dict.cap)));
-        }
-        ts = __ldcs(ldg_ptr(&sg->ts) + base + i);
+      const long long key = nkey, ts = nts;
+      long long v[NV > 0 ? NV : 1];
 #pragma unroll
-        for (int x = 0; x < NV; ++x) v[x] = __ldcs(ldg_ptr(&sg->val[x]) + base + i);
+      for (int x = 0; x < (NV > 0 ? NV : 1); ++x) v[x] = nv[x];
+      ulonglong2 raw = {0, 0};
+      if (valid && keyed)
+        raw = __ldcg(reinterpret_cast<const ulonglong2*>(p.dict.slots + dict_home((uint64_t)key, p.dict.cap)));
+#if AB_INGEST_PREFETCH
+      if (i + THREADS < cnt) {
+        if (keyed) nkey = __ldcs(ldg_ptr(&sg->key) + base + i + THREADS);
+        nts = __ldcs(ldg_ptr(&sg->ts) + base + i + THREADS);
+#pragma unroll
+        for (int x = 0; x < NV; ++x) nv[x] = __ldcs(ldg_ptr(&sg->val[x]) + base + i + THREADS);
       }
+#endif
       // K1: pane = ts / slide, i.e. bin = ts - ts % slide (tumbling_aggregating_window.rs:65-73)
       const uint64_t q = sd.div((uint64_t)ts);
       // K7: late bins are dropped (tumbling :282-291, sliding :631-633)
@@ -568,6 +598,14 @@ __global__ void __launch_bounds__(THREADS, AB_INGEST_MIN_BLOCKS) ingest_kernel(c
       if (fast) ++pc.cnt;
       if (p.combine) combine_accumulate<NV, SIG>(p, pc, fast, id, pv, lane);
       else if (fast) accumulate<NV, SIG>(p, pv, pc.ptr, id);
+#if !AB_INGEST_PREFETCH
+      if (i + THREADS < cnt) {
+        if (keyed) nkey = __ldcs(ldg_ptr(&sg->key) + base + i + THREADS);
+        nts = __ldcs(ldg_ptr(&sg->ts) + base + i + THREADS);
+#pragma unroll
+        for (int x = 0; x < NV; ++x) nv[x] = __ldcs(ldg_ptr(&sg->val[x]) + base + i + THREADS);
+      }
+#endif
     }
   }
 
@@ -926,6 +964,7 @@ class WindowAggOp final : public OpBase {
   // DataFusion's running f64 sum by at most n * 2^-53 relative (north-star tolerance: 1e-6).
   bool avg_exact_ = true;
   unsigned int guard_vals_ = 0;
+  int rows_slot_ = -1;  // value slot of the carried row count (partial-aggregate inputs)
   bool running_mode_ = false;
   bool profile_;
   std::string key_format_ = "l";
@@ -1104,6 +1143,22 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
       ++n_acc_;
     }
     agg_acc_[g] = found;
+  }
+  if (c.partial_count_col_plus1 > 0) {
+    const int col = c.partial_count_col_plus1 - 1;
+    AB_REQUIRE(col < c.n_cols, ARROYO_B200_INVALID_ARGUMENT, "partial count column out of range");
+    int vs = -1;
+    for (int v = 0; v < n_vals_; ++v)
+      if (val_cols_[v] == col) vs = v;
+    if (vs < 0) {
+      AB_REQUIRE(n_vals_ < MAX_VALS, ARROYO_B200_UNSUPPORTED, "more than 4 distinct aggregate input columns");
+      vs = n_vals_;
+      val_cols_[n_vals_++] = col;
+    }
+    rows_slot_ = vs;
+    // partial sums are not bounded by 2^31: exactness of the integer AVG path rests on the upstream
+    // (raw-row) stage's guard and on the window row bound checked at emission
+    guard_vals_ = 0;
   }
   profile_ = (c.flags & ARROYO_B200_FLAG_PROFILE) != 0;
   // The running window W += entering - leaving is used only while every accumulator is exactly invertible
@@ -1666,6 +1721,7 @@ void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk
   p.late_q = late_bin_ == LLONG_MIN ? 0ull : (unsigned long long)late_bin_ / (unsigned long long)slide_;
   p.guard_vals = avg_exact_ ? guard_vals_ : 0u;
   p.combine = (cfg.flags & ARROYO_B200_FLAG_NO_COMBINE) ? 0 : 1;
+  p.rows_slot = rows_slot_;
   p.ring_mask = ring_ - 1;
   p.n_acc = n_acc_;
   p.pane_bins = d_pane_bins_.as<long long>();

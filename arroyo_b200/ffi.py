@@ -56,6 +56,7 @@ class OpConfig(C.Structure):
         ("join_type", C.c_int32), ("right_n_cols", C.c_int32), ("right_timestamp_col", C.c_int32),
         ("left_key_col", C.c_int32), ("right_key_col", C.c_int32),
         ("left_n_routing", C.c_int32), ("right_n_routing", C.c_int32),
+        ("partial_count_col_plus1", C.c_int32), ("reserved2", C.c_int32),
         ("expected_keys", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
@@ -115,6 +116,8 @@ SYMBOLS = [
     ("arroyo_b200_partitioner_destroy", None, [_VP]),
     ("arroyo_b200_partition", C.c_int32, [_VP, C.POINTER(C.c_uint64), C.c_int64, C.POINTER(C.c_uint64),
                                           C.c_uint64, C.c_uint64]),
+    ("arroyo_b200_ts_minmax", C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, C.c_int64, C.POINTER(C.c_int64),
+                                          C.POINTER(C.c_int64)]),
     ("arroyo_b200_hash_key", C.c_uint64, [C.c_int64]),
     ("arroyo_b200_server_for_hash", C.c_uint32, [C.c_uint64, C.c_uint32]),
     ("arroyo_b200_bin_start", C.c_int64, [C.c_int64, C.c_int64]),

@@ -130,6 +130,8 @@ class _WindowAggregate(_NativeOperator):
                 raise ffi.UnsupportedPlan(ffi.UNSUPPORTED, f"aggregate {a.kind}")
             cfg.aggs[i].kind = _AGG_KINDS[a.kind]
             cfg.aggs[i].input_col = names.index(a.col) if a.col is not None else 0
+        pc = getattr(c, "partial_count_col", None)
+        cfg.partial_count_col_plus1 = names.index(pc) + 1 if pc else 0
         cfg.final_projection = 1 if c.final_projection else 0
         cfg.window_index = int(c.window_index)
         self._create(cfg)

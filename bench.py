@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--no-combine", action="store_true", help="measurement knob: no warp-combining of equal keys")
     ap.add_argument("--avg-f64", action="store_true", help="measurement knob: AVG with its own f64 accumulator")
     ap.add_argument("--chunk-log2", type=int, default=0, help="rows per ingest launch = 2^n (default 23)")
+    ap.add_argument("--shuffle", default="partials", choices=["partials", "rows"],
+                    help="N>1: what crosses the all-to-all (per-pane partial aggregates, or raw rows)")
     return ap.parse_args()
 
 

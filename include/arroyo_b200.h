@@ -150,6 +150,13 @@ typedef struct ArroyoB200OpConfig {
   int32_t left_n_routing;   /* leading `_key_*` routing copies stripped from each side    */
   int32_t right_n_routing;  /* (arroyo-rpc/src/df.rs:359-367)                             */
 
+  /* Window aggregates fed with PARTIAL aggregates (the final stage of a partial -> shuffle -> final
+   * plan: each upstream row stands for `count` original rows).  0 = inputs are raw rows; otherwise
+   * 1 + the index of the input column that carries the row count.  SUM / MIN / MAX then merge the
+   * upstream partial columns, COUNT(*) and AVG use the carried count. */
+  int32_t partial_count_col_plus1;
+  int32_t reserved2;
+
   uint64_t expected_keys;   /* capacity hint for the key dictionary (0 = default)         */
   uint32_t flags;           /* ARROYO_B200_FLAG_*                                         */
   uint32_t reserved;        /* 0, or log2(rows per ingest launch) in [16, 26] (default 23)     */
@@ -307,6 +314,10 @@ int32_t arroyo_b200_partitioner_create(int32_t device, uint64_t stream, int32_t 
 void arroyo_b200_partitioner_destroy(ArroyoB200Partitioner* p);
 int32_t arroyo_b200_partition(ArroyoB200Partitioner* p, const uint64_t* in_cols, int64_t n_rows,
                               const uint64_t* out_cols, uint64_t counts_dev, uint64_t offsets_dev);
+/* WatermarkGenerator::process_batch's reductions (arroyo-worker/src/arrow/watermark_generator.rs:160,176:
+ * kernels::aggregate::max / min over the timestamp column) for a device-resident batch. Synchronous. */
+int32_t arroyo_b200_ts_minmax(int32_t device, uint64_t stream, uint64_t ts_dev, int64_t n_rows, int64_t* out_min,
+                               int64_t* out_max);
 /* The hash used for routing (host-callable restatement for tests). */
 uint64_t arroyo_b200_hash_key(int64_t key);
 /* dest = (h / (u64::MAX / n)) % n -- arroyo-operator/src/lib.rs:30-41. */

@@ -422,3 +422,42 @@ def test_pinned_host_batches_are_read_in_place(G):
     op.handle_watermark(ab.FINAL_WATERMARK, ctx, out)
     assert_same(want, [from_arrow(b) for b in out.batches], float_cols=("avg",))
     assert op.stats()["h2d_bytes"] == 150_000 * 24
+
+
+def test_partial_then_final_equals_direct(G):
+    """partial -> (shuffle) -> final: a per-pane tumbling stage emits (key, sum, count) partial rows; a
+    sliding operator declared with `partial_count_col` merges them.  The windows must equal the direct
+    sliding aggregate of the raw rows (the plan shape the N>1 benchmark uses)."""
+    import arroyo_b200 as ab
+    rng = np.random.default_rng(77)
+    batches = gen_stream(rng, 160_000, 3_000, rate_per_s=16_000, batch=8000, key_dist="hot")
+    direct = O.WindowAggConfig(width=4 * S, slide=S, key_names=["key"], aggs=SUM_AVG, window_index=1)
+    want = O.run_single_input(O.SlidingAggregatingWindowFunc(direct), batches, S).batches
+
+    local = G.TumblingAggregatingWindowFunc(
+        ab.WindowAggConfig(width=S, key_names=["key"], aggs=[ab.Agg("sum", "value", "psum"), ab.Agg("count", None, "pcount")],
+                           final_projection=False))
+    final = G.SlidingAggregatingWindowFunc(
+        ab.WindowAggConfig(width=4 * S, slide=S, key_names=["key"],
+                           aggs=[ab.Agg("sum", "psum", "sum"), ab.Agg("avg", "psum", "avg"), ab.Agg("count", None, "count")],
+                           window_index=1, partial_count_col="pcount"))
+    ctx = O.OperatorContext(1)
+    out = O.Collector()
+    gen = O.WatermarkGenerator(S)
+
+    def forward(wm):
+        mid = O.Collector()
+        local.handle_watermark(wm, ctx, mid)
+        for b in mid.batches:
+            final.process_batch(b, ctx, out)
+        final.handle_watermark(wm, ctx, out)
+
+    for b in batches:
+        local.process_batch(b, ctx, out)
+        wm = gen.process_batch(b[O.TIMESTAMP])
+        if wm is not None:
+            ctx.watermarks.set(0, wm)
+            forward(wm)
+    ctx.watermarks.set(0, O.FINAL_WATERMARK)
+    forward(O.FINAL_WATERMARK)
+    assert_same(want, out.batches, float_cols=("avg",))
