@@ -461,3 +461,43 @@ def test_partial_then_final_equals_direct(G):
     ctx.watermarks.set(0, O.FINAL_WATERMARK)
     forward(O.FINAL_WATERMARK)
     assert_same(want, out.batches, float_cols=("avg",))
+
+
+def test_watermark_generator_device_reductions(G):
+    """K7: the WatermarkGenerator's per-batch min / max on the device equals the oracle's generator."""
+    import torch
+    import arroyo_b200 as ab
+    rng = np.random.default_rng(2)
+    batches = gen_stream(rng, 50_000, 10, rate_per_s=5_000, disorder=2_000, batch=777)
+    og, gg = O.WatermarkGenerator(S), ab.WatermarkGenerator(S)
+    for b in batches:
+        t = torch.from_numpy(np.ascontiguousarray(b[O.TIMESTAMP])).cuda()
+        assert gg.process_device_batch(t.data_ptr(), b.num_rows) == og.process_batch(b[O.TIMESTAMP])
+
+
+@pytest.mark.parametrize("n_dest", [1, 2, 3, 8])
+def test_device_partitioner_matches_repartition(G, n_dest):
+    """K6: hash -> dest = (h / (u64::MAX / n)) % n -> per-destination segments, against the oracle's
+    restatement of ArrowCollector::repartition (context.rs:506-541): same rows in every segment."""
+    import torch
+    from arroyo_b200.multi_gpu import DevicePartitioner
+    rng = np.random.default_rng(n_dest)
+    for n in (0, 1, 2047, 2048, 100_003):
+        key = rng.integers(-2**63, 2**63 - 1, n, dtype=np.int64)
+        val = rng.integers(0, 10**9, n, dtype=np.int64)
+        ts = T0 + np.arange(n, dtype=np.int64)
+        want = {d: b for d, b in O.repartition(O.Batch({"key": key, "value": val, O.TIMESTAMP: ts}), ["key"], n_dest)}
+        part = DevicePartitioner(torch, n_dest, 3, 0, max(n, 1), 0, torch.cuda.current_stream().cuda_stream)
+        cols = [torch.from_numpy(x).cuda() for x in (key, val, ts)]
+        out, counts = part(cols, n)
+        torch.cuda.synchronize()
+        counts = counts.cpu().numpy()
+        assert counts.sum() == n
+        off = 0
+        for d in range(n_dest):
+            c = int(counts[d])
+            got = sorted(zip(*(o[off:off + c].cpu().numpy().tolist() for o in out)))
+            exp = sorted(zip(want[d]["key"].tolist(), want[d]["value"].tolist(), want[d][O.TIMESTAMP].tolist())) if d in want else []
+            assert got == exp
+            off += c
+        part.close()
