@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libarroyo_b200.so")
 SOURCES = ["abi.cu", "window_agg.cu", "shuffle.cu", "join.cu", "session.cu"]
-HEADERS = ["common.cuh", "planner.h", "arrow_io.h", "op.h", os.path.join("..", "..", "include", "arroyo_b200.h")]
+HEADERS = ["common.cuh", "dict.cuh", "scan.cuh", "planner.h", "arrow_io.h", "op.h", os.path.join("..", "..", "include", "arroyo_b200.h")]
 
 
 def nvcc_path() -> str:

@@ -28,6 +28,7 @@
 #include <memory>
 #include <set>
 
+#include "dict.cuh"
 #include "op.h"
 #include "planner.h"
 
@@ -40,21 +41,11 @@ constexpr int MAX_SEGS = 512;
 constexpr int MAX_RING = 4096;
 constexpr int RING_INLINE = 64;
 constexpr int MAX_MERGE = 4096;
-constexpr uint32_t ID_UNSET = 0xFFFFFFFFu;
-constexpr uint32_t ID_OVERFLOW = 0xFFFFFFFEu;
-constexpr long long EMPTY_KEY = LLONG_MIN;
 constexpr long long FREE_BIN = LLONG_MIN;
-constexpr int MAX_PROBE = 4096;
 
 constexpr int THREADS = 256;
 constexpr int PAIRS = 2;
 constexpr int TILE = THREADS * PAIRS * 2;  // rows per tile
-
-struct alignas(16) Slot {
-  long long key;
-  uint32_t id;
-  uint32_t pad;
-};
 
 enum AccKind : int { ACC_ROWS = 0, ACC_SUM_I64 = 1, ACC_SUM_F64 = 2, ACC_MIN_I64 = 3, ACC_MAX_I64 = 4 };
 
@@ -78,21 +69,6 @@ struct Segment {
   int vec_ok;
   int pad;
 };
-
-struct DictView {
-  Slot* slots;
-  long long* id_keys;
-  unsigned int* n_keys;
-  uint32_t cap;  // number of slots (any value: placement is multiply-shift, not a mask)
-  uint32_t id_cap;
-};
-
-__host__ __device__ __forceinline__ uint32_t dict_home(uint64_t key, uint32_t cap) {
-  return (uint32_t)(((mix64(key) >> 32) * (uint64_t)cap) >> 32);
-}
-__host__ __device__ __forceinline__ uint32_t dict_next(uint32_t pos, uint32_t cap) {
-  return pos + 1 == cap ? 0u : pos + 1;
-}
 
 struct IngestParams {
   const Segment* segs;
@@ -127,47 +103,6 @@ struct IngestParams {
   long long* d_val[MAX_VALS];
   unsigned long long defer_cap;
 };
-
-// -------------------------------------------------------------------------------------------
-// dictionary
-// -------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t wait_id(const Slot* s) {
-  uint32_t id;
-  do {
-    __nanosleep(20);
-    id = *(volatile const uint32_t*)&s->id;
-  } while (id == ID_UNSET);
-  return id;
-}
-
-__global__ void dict_init_kernel(Slot* slots, uint64_t n) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    slots[i].key = EMPTY_KEY;
-    slots[i].id = ID_UNSET;
-    slots[i].pad = 0;
-  }
-}
-
-// re-insert ids [1, n) after the slot array was replaced
-__global__ void dict_rebuild_kernel(Slot* slots, uint32_t cap, const long long* id_keys, uint32_t n) {
-  uint32_t id = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  uint32_t stride = gridDim.x * blockDim.x;
-  for (; id < n; id += stride) {
-    long long key = id_keys[id];
-    uint32_t pos = dict_home((uint64_t)key, cap);
-    while (true) {
-      unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&slots[pos].key),
-                                         (unsigned long long)EMPTY_KEY, (unsigned long long)key);
-      if (old == (unsigned long long)EMPTY_KEY) {
-        slots[pos].id = id;
-        break;
-      }
-      pos = dict_next(pos, cap);
-    }
-  }
-}
 
 // -------------------------------------------------------------------------------------------
 // pane blocks
@@ -252,56 +187,6 @@ __device__ __noinline__ void defer_row(const IngestParams& p, long long key, lon
   } else {
     atomicAdd(&p.counters->lost, 1ull);
   }
-}
-
-// First sighting of a key: claim the empty slot found at `pos` (or keep walking if somebody else took it).
-__device__ __noinline__ uint32_t dict_insert(const DictView& d, long long key, uint32_t pos) {
-#pragma unroll 1
-  for (int probe = 0; probe < MAX_PROBE; ++probe) {
-    Slot* sp = d.slots + pos;
-    ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(sp));
-    long long k = (long long)raw.x;
-    uint32_t id = (uint32_t)raw.y;
-    if (k == key) {
-      if (id == ID_UNSET) id = wait_id(sp);
-      return id;
-    }
-    if (k == EMPTY_KEY) {
-      unsigned long long old =
-          atomicCAS(reinterpret_cast<unsigned long long*>(&sp->key), (unsigned long long)EMPTY_KEY, (unsigned long long)key);
-      if (old == (unsigned long long)EMPTY_KEY) {
-        uint32_t nid = atomicAdd(d.n_keys, 1u);
-        if (nid >= d.id_cap) {
-          nid = ID_OVERFLOW;
-        } else {
-          d.id_keys[nid] = key;
-        }
-        __threadfence();
-        atomicExch(&sp->id, nid);
-        return nid;
-      }
-      if ((long long)old == key) return wait_id(sp);
-    }
-    pos = dict_next(pos, d.cap);
-  }
-  return ID_OVERFLOW;
-}
-
-// Dense id of `key` given its home slot contents `raw` (already loaded).  Existing keys resolve with
-// read-only probes inline; the insert path is out of line.
-__device__ __forceinline__ uint32_t resolve_id(const DictView& d, long long key, unsigned long long k0, uint32_t id0) {
-  if ((long long)k0 == key && id0 < ID_OVERFLOW) return id0;
-  if (key == EMPTY_KEY) return 0;  // id 0 is reserved for the one key that equals the empty sentinel
-  uint32_t pos = dict_home((uint64_t)key, d.cap);
-  if ((long long)k0 == EMPTY_KEY || (long long)k0 == key) return dict_insert(d, key, pos);
-#pragma unroll 1
-  for (int probe = 1; probe < MAX_PROBE; ++probe) {
-    pos = dict_next(pos, d.cap);
-    const ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(d.slots + pos));
-    if ((long long)raw.x == key && (uint32_t)raw.y < ID_OVERFLOW) return (uint32_t)raw.y;
-    if ((long long)raw.x == EMPTY_KEY || (long long)raw.x == key) return dict_insert(d, key, pos);
-  }
-  return ID_OVERFLOW;
 }
 
 // Accumulator signature: the kinds of accumulators 1..3 packed 3 bits each (0 = none); GENERIC_SIG =
@@ -1262,18 +1147,13 @@ WindowAggOp::~WindowAggOp() {
   if (own_stream_ && stream_) cudaStreamDestroy(stream_);
 }
 
-// slot count: 3.5 x ids => load factor 0.25 at the expected key count (0.29 when every id is used).
-// Measured (profiles/r01_probe2.txt): the random 16-byte probe runs at 92 G/s at load 0.25 vs 72 G/s at
-// 0.5 -- shorter chains mean fewer divergent replays per warp.
-static uint64_t slots_for(uint64_t ids) { return std::max<uint64_t>(1024, ids * 7 / 2); }
-
 void WindowAggOp::alloc_dictionary(uint64_t id_cap) {
   id_cap_ = id_cap;
   id_keys_.alloc(id_cap_ * sizeof(long long));
   long long k0 = EMPTY_KEY;
   AB_CUDA(cudaMemcpyAsync(id_keys_.p, &k0, sizeof k0, cudaMemcpyHostToDevice, stream_));
   if (keyed_) {
-    dict_cap_ = slots_for(id_cap_);
+    dict_cap_ = dict_slots_for(id_cap_);
     AB_REQUIRE(dict_cap_ <= (1ull << 31), ARROYO_B200_RUNTIME, "key dictionary too large");
     slots_.alloc(dict_cap_ * sizeof(Slot));
     dict_init_kernel<<<num_sms_ * 4, 256, 0, stream_>>>(slots_.as<Slot>(), dict_cap_);
@@ -1350,7 +1230,7 @@ void WindowAggOp::grow_ids() {
   id_keys_ = std::move(new_keys);
   ring_dirty_ = true;
   if (keyed_) {
-    dict_cap_ = slots_for(new_cap);
+    dict_cap_ = dict_slots_for(new_cap);
     AB_REQUIRE(dict_cap_ <= (1ull << 31), ARROYO_B200_RUNTIME, "key dictionary too large");
     slots_.alloc(dict_cap_ * sizeof(Slot));
     dict_init_kernel<<<num_sms_ * 4, 256, 0, stream_>>>(slots_.as<Slot>(), dict_cap_);

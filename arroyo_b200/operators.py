@@ -260,6 +260,86 @@ class SlidingAggregatingWindowFunc(_WindowAggregate):
         return "sliding_window"
 
 
+
+class SessionAggregatingWindowFunc(_NativeOperator):
+    """arroyo-worker/src/arrow/session_aggregating_window.rs.  Output = [key cols...] with the window struct
+    inserted at `window_index`, [agg cols...], `_timestamp = window.end - 1 ns` (:316-382)."""
+    kind = ffi.SESSION_AGGREGATE
+
+    def __init__(self, config, input_schema: Optional[pa.Schema] = None, **kw):
+        super().__init__(**kw)
+        self.config = config
+        if input_schema is not None:
+            self._build(input_schema.names)
+
+    def name(self):
+        return "session_window"
+
+    def tables(self):
+        # "s": raw sorted input batches, retention gap x 100; "e": earliest start per subtask (:927-941)
+        return {"s": int(self.config.gap) * 100, "e": 0}
+
+    def _build(self, names: List[str]):
+        c = self.config
+        cfg = ffi.OpConfig()
+        cfg.kind = self.kind
+        cfg.gap_ns = int(c.gap)
+        cfg.n_cols = len(names)
+        cfg.timestamp_col = names.index(TIMESTAMP)
+        if len(c.key_names) > 1:
+            raise ffi.UnsupportedPlan(ffi.UNSUPPORTED, "more than one group-by key column")
+        cfg.n_key_cols = len(c.key_names)
+        cfg.key_col = names.index(c.key_names[0]) if c.key_names else 0
+        cfg.n_aggs = len(c.aggs)
+        for i, a in enumerate(c.aggs):
+            if a.kind not in _AGG_KINDS:
+                raise ffi.UnsupportedPlan(ffi.UNSUPPORTED, f"aggregate {a.kind}")
+            cfg.aggs[i].kind = _AGG_KINDS[a.kind]
+            cfg.aggs[i].input_col = names.index(a.col) if a.col is not None else 0
+        cfg.window_index = int(c.window_index)
+        self._create(cfg)
+
+    def output_names(self) -> List[str]:
+        c = self.config
+        names = list(c.key_names)
+        names.insert(min(max(c.window_index, 0), len(names)), "window")
+        return names + [a.name for a in c.aggs] + [TIMESTAMP]
+
+    def process_batch(self, batch: pa.RecordBatch, ctx: OperatorContext, collector: Collector):
+        if not self.created:
+            self._build(batch.schema.names)
+        arr, sch = export_batch(batch)
+        st = self._lib.arroyo_b200_op_process_batch(self._h, 0, 1, C.byref(arr), C.byref(sch))
+        if st != ffi.OK and arr.release:
+            C.CFUNCTYPE(None, C.c_void_p)(arr.release)(C.addressof(arr))
+        if sch.release:
+            C.CFUNCTYPE(None, C.c_void_p)(sch.release)(C.addressof(sch))
+        _check(self._lib, self._h, st)
+
+    def process_device_batch(self, cols: List[int], n_rows: int):
+        arr = (C.c_uint64 * len(cols))(*cols)
+        _check(self._lib, self._h, self._lib.arroyo_b200_op_process_device_batch(self._h, 0, 1, arr, len(cols), n_rows))
+
+    def handle_watermark(self, watermark, ctx: OperatorContext, collector: Collector):
+        wm = ctx.last_present_watermark()
+        if wm is None or not self.created:
+            return watermark
+        out = ffi.Batches()
+        st = self._lib.arroyo_b200_op_handle_watermark(self._h, clamp_watermark(wm), C.byref(out))
+        _check(self._lib, self._h, st)
+        names = self.output_names()
+        for b in import_batches(self._lib, out):
+            collector.collect(pa.RecordBatch.from_arrays(b.columns, names=names))
+        return watermark
+
+    def handle_watermark_device(self, wm: int, max_out: int = 4):
+        out = (ffi.DeviceBatch * max_out)()
+        n = C.c_int64(0)
+        st = self._lib.arroyo_b200_op_handle_watermark_device(self._h, clamp_watermark(wm), out, max_out, C.byref(n))
+        _check(self._lib, self._h, st)
+        return [(out[i].n_rows, [out[i].cols[c] for c in range(out[i].n_cols)]) for i in range(n.value)]
+
+
 _JOIN_TYPES = {"inner": ffi.JOIN_INNER, "left": ffi.JOIN_LEFT, "right": ffi.JOIN_RIGHT, "full": ffi.JOIN_FULL}
 
 

@@ -99,8 +99,8 @@ class InstantJoin:
         return self.op.handle_watermark(watermark, ctx, _CollectAdapter(collector))
 
 
-# not yet on the GPU: the cases that need it are not run against the CUDA path
-SessionAggregatingWindowFunc = None
+class SessionAggregatingWindowFunc(_WindowOp):
+    native_cls = native.SessionAggregatingWindowFunc
 
 
 def run_single_input(op, batches, delay_ns: int = 1_000_000_000, ctx=None) -> O.Collector:

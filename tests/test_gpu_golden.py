@@ -8,7 +8,9 @@ pytestmark = pytest.mark.gpu
 WINDOW_ONLY = ["sliding_window_end", "hourly_by_event_type", "tight_watermark", "month_loose_watermark",
                "most_active_driver_last_hour",
                # window aggregates + instant join, both on the GPU
-               "windowed_inner_join", "windowed_outer_join", "offset_impulse_join", "nexmark_q5"]
+               "windowed_inner_join", "windowed_outer_join", "offset_impulse_join", "nexmark_q5",
+               # session windows (per-key state machines on the GPU)
+               "session_window", "global_session_window"]
 
 
 @pytest.fixture(scope="module")

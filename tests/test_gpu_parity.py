@@ -501,3 +501,86 @@ def test_device_partitioner_matches_repartition(G, n_dest):
             assert got == exp
             off += c
         part.close()
+
+
+def session_stream(rng, n_keys, n_bursts, gap, batch, jitter=0):
+    """Per key: bursts of 1..6 events less than `gap` apart, bursts more than `gap` apart; events of all keys
+    are merged in (roughly) time order and cut into batches.  Some gaps are exactly `gap` (the strict `<`)."""
+    rows = []
+    for k in range(n_keys):
+        t = T0 + int(rng.integers(0, 3 * gap))
+        for _ in range(n_bursts):
+            for _ in range(int(rng.integers(1, 7))):
+                rows.append((t, k * 31 + 5, int(rng.integers(-1000, 1000))))
+                t += int(rng.integers(1, gap)) if rng.random() > 0.05 else gap
+            t += gap + int(rng.integers(1, 4 * gap))
+    rows.sort(key=lambda r: r[0] + (int(rng.integers(-jitter, jitter + 1)) if jitter else 0))
+    ts = np.array([r[0] for r in rows], dtype=np.int64)
+    key = np.array([r[1] for r in rows], dtype=np.int64)
+    val = np.array([r[2] for r in rows], dtype=np.int64)
+    return O.source_batches({"key": key, "value": val, O.TIMESTAMP: ts}, batch)
+
+
+SESSION_AGGS = [O.Agg("count", None, "rows"), O.Agg("sum", "value", "sum"), O.Agg("min", "value", "mn"),
+                O.Agg("max", "value", "mx"), O.Agg("avg", "value", "avg")]
+
+
+@pytest.mark.parametrize("case", ["in_order", "small_batches", "multi_row_runs", "disorder", "no_watermark_until_end"])
+def test_session_windows_match_oracle(G, case):
+    """Per-key session state machines against the oracle's statement-by-statement restatement of the reference
+    (including the rows its scan assigns to the 'wrong' session when one batch holds a key's session boundary)."""
+    rng = np.random.default_rng({"in_order": 1, "small_batches": 2, "multi_row_runs": 3, "disorder": 4,
+                                 "no_watermark_until_end": 5}[case])
+    gap = 5 * S
+    kw = dict(n_keys=300, n_bursts=6, gap=gap, batch=500)
+    delay = S
+    if case == "small_batches":
+        kw.update(batch=37)
+    if case == "multi_row_runs":  # few keys, big batches: one batch spans several bursts of a key
+        kw.update(n_keys=12, n_bursts=25, batch=400)
+    if case == "disorder":
+        kw.update(jitter=2 * S)
+        delay = 3 * S
+    batches = session_stream(rng, **kw)
+    cfg = O.SessionConfig(gap=gap, key_names=["key"], aggs=SESSION_AGGS, window_index=0)
+    if case == "no_watermark_until_end":
+        def run(op, runner_ctx):
+            ctx, out = runner_ctx(1), O.Collector()
+            for b in batches:
+                op.process_batch(b, ctx, out)
+            ctx.watermarks.set(0, O.FINAL_WATERMARK)
+            op.handle_watermark(O.FINAL_WATERMARK, ctx, out)
+            return out.batches
+        want = run(O.SessionAggregatingWindowFunc(cfg), O.OperatorContext)
+        got = run(G.SessionAggregatingWindowFunc(cfg), O.OperatorContext)
+    else:
+        want = O.run_single_input(O.SessionAggregatingWindowFunc(cfg), batches, delay).batches
+        got = G.run_single_input(G.SessionAggregatingWindowFunc(cfg), batches, delay).batches
+    assert sum(b.num_rows for b in want) > 300
+    assert_same(want, got, float_cols=("avg",))
+
+
+def test_session_unkeyed_and_device_batches(G):
+    import torch
+    import arroyo_b200 as ab
+    from arroyo_b200 import operators as native
+    rng = np.random.default_rng(4)
+    batches = session_stream(rng, n_keys=1, n_bursts=40, gap=2 * S, batch=64)
+    ub = [O.Batch({"value": b["value"], O.TIMESTAMP: b[O.TIMESTAMP]}) for b in batches]
+    cfg = O.SessionConfig(gap=2 * S, key_names=[], aggs=[O.Agg("count", None, "rows"), O.Agg("sum", "value", "sum")],
+                          window_index=0)
+    want = O.run_single_input(O.SessionAggregatingWindowFunc(cfg), ub, S).batches
+    got = G.run_single_input(G.SessionAggregatingWindowFunc(cfg), ub, S).batches
+    assert_same(want, got)
+
+
+def test_session_pool_compaction(G, monkeypatch):
+    """Long stream with a tiny compaction threshold: the run / row pools are rebuilt from the per-key lists many
+    times without changing any result."""
+    monkeypatch.setenv("ARROYO_B200_SESSION_COMPACT_MIN", "64")
+    rng = np.random.default_rng(12)
+    batches = session_stream(rng, n_keys=200, n_bursts=12, gap=3 * S, batch=300, jitter=S)
+    cfg = O.SessionConfig(gap=3 * S, key_names=["key"], aggs=SESSION_AGGS, window_index=1)
+    want = O.run_single_input(O.SessionAggregatingWindowFunc(cfg), batches, 2 * S).batches
+    got = G.run_single_input(G.SessionAggregatingWindowFunc(cfg), batches, 2 * S).batches
+    assert_same(want, got, float_cols=("avg",))
