@@ -76,7 +76,9 @@ struct SessCtx {
   int keyed;
 };
 
-enum : unsigned long long { ERR_POOL = 1, ERR_ADD_FLUSHED = 2, ERR_BEFORE_START = 4, ERR_OUT = 8 };
+enum : unsigned long long { ERR_POOL = 1, ERR_ADD_FLUSHED = 2, ERR_BEFORE_START = 4, ERR_OUT = 8, ERR_LOOP = 16 };
+// every device loop over the linked lists is bounded: a corrupted list must surface as an error, never as a hang
+constexpr int LOOP_GUARD = 1 << 24;
 
 struct RowsRef {
   const long long* ts;
@@ -178,9 +180,14 @@ __device__ void pending_insert(const SessCtx& c, uint32_t id, int node) {
   if (node < 0) return;
   const long long start = c.n_start[node];
   int prev = -1, cur = c.head[id];
+  int guard = 0;
   while (cur >= 0 && c.n_start[cur] <= start) {
     prev = cur;
     cur = c.n_next[cur];
+    if (++guard > LOOP_GUARD) {
+      set_err(c, ERR_LOOP);
+      return;
+    }
   }
   c.n_next[node] = cur;
   if (prev < 0) c.head[id] = node;
@@ -198,17 +205,32 @@ __device__ RowsRef pool_rows(const SessCtx& c, int node) {
 
 // KeyComputingHolder::fill_active_session (:610-643)
 __device__ void fill_active_session(const SessCtx& c, uint32_t id) {
+  int guard = 0;
   while (true) {
+    if (++guard > LOOP_GUARD) {
+      set_err(c, ERR_LOOP);
+      return;
+    }
     int h = c.head[id];
     if (h < 0) break;
     const long long first = c.n_start[h];
     if (c.data_end[id] + c.gap < first) break;
     // pop_first(): every run stored under this start time, in insertion order
     int tail = h;
-    while (c.n_next[tail] >= 0 && c.n_start[c.n_next[tail]] == first) tail = c.n_next[tail];
+    while (c.n_next[tail] >= 0 && c.n_start[c.n_next[tail]] == first) {
+      tail = c.n_next[tail];
+      if (++guard > LOOP_GUARD) {
+        set_err(c, ERR_LOOP);
+        return;
+      }
+    }
     c.head[id] = c.n_next[tail];
     c.n_next[tail] = -1;
     for (int node = h; node >= 0;) {
+      if (++guard > LOOP_GUARD) {
+        set_err(c, ERR_LOOP);
+        return;
+      }
       const int next = c.n_next[node];
       RowsRef r = pool_rows(c, node);
       int rem_lo = 0;
@@ -256,7 +278,12 @@ __device__ void finish_session(const SessCtx& c, uint32_t id) {
 
 // KeyComputingHolder::watermark_update (:557-603)
 __device__ void watermark_update(const SessCtx& c, uint32_t id, long long wm, bool in_add) {
+  int guard = 0;
   while (true) {
+    if (++guard > LOOP_GUARD) {
+      set_err(c, ERR_LOOP);
+      return;
+    }
     if (c.active[id]) {
       if (c.data_end[id] + c.gap < wm) {
         if (in_add) set_err(c, ERR_ADD_FLUSHED);  // "should not have flushed batches when adding a batch" (:672-675)
@@ -860,6 +887,7 @@ void SessionOp::check_err() {
     throw Error(ARROYO_B200_RUNTIME, "received a batch that starts before the current data_start - gap (session_aggregating_window.rs:452-456)");
   if (e & ERR_ADD_FLUSHED)
     throw Error(ARROYO_B200_RUNTIME, "should not have flushed batches when adding a batch (session_aggregating_window.rs:672-675)");
+  if (e & ERR_LOOP) throw Error(ARROYO_B200_RUNTIME, "session operator: per-key list walk exceeded its bound (corrupted state)");
   throw Error(ARROYO_B200_RUNTIME, "session operator pool / output capacity exceeded");
 }
 
@@ -883,6 +911,7 @@ void SessionOp::prep(const long long* key, const long long* ts, const long long*
   if (n <= 0) return;
   // a launch never mixes rows that arrived under different watermarks, and is cut at 4 Mi rows
   if (arena_rows_bound_ + (uint64_t)n > (1ull << 22) && arena_rows_bound_ > 0) apply_pending();
+  if (arena_rows_bound_ + (uint64_t)n > arena_cap_ && arena_rows_bound_ > 0) apply_pending();
   ensure_arena(arena_rows_bound_ + (uint64_t)n);
   if (keyed_) grow_keys((uint64_t)n);
   PrepParams p{};

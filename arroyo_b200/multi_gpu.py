@@ -139,6 +139,92 @@ class _Ptr:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
 
 
+def _e2e_partials(args, torch, dist, B, ab, native, rank, world, local, device, gen_pane, part, ex):
+    """End to end at N GPUs: every rank feeds its shard as pinned host Arrow batches through
+    arroyo_b200_op_process_batch (host -> device copies inside the timed region), partial aggregates cross the
+    all-to-all, and each rank reads the windows of its keys back as host Arrow batches."""
+    import time
+
+    import pyarrow as pa
+    rows = args.rows_per_pane
+    nb = rows // B.BATCH_ROWS
+    K = args.e2e_steps or min(args.steps, 6)
+    W = 13
+    batches, wms, _keep = B.host_feed(torch, gen_pane, range(W + K), rows)
+    stream = torch.cuda.current_stream().cuda_stream
+    local_cfg = ab.WindowAggConfig(width=B.SLIDE, key_names=["key"],
+                                   aggs=[ab.Agg("sum", "value", "sum"), ab.Agg("count", None, "count")],
+                                   final_projection=False)
+    local_op = native.TumblingAggregatingWindowFunc(local_cfg, device=local, stream=stream, flags=B.op_flags(args),
+                                                    expected_keys=args.keys, task_index=rank, parallelism=world)
+    owner_cfg = ab.WindowAggConfig(width=B.WIDTH, slide=B.SLIDE, key_names=["key"],
+                                   aggs=[ab.Agg("sum", "sum", "sum"), ab.Agg("avg", "sum", "avg"),
+                                         ab.Agg("count", None, "count")], window_index=1, partial_count_col="count")
+    p_schema = pa.schema([("key", pa.int64()), ("sum", pa.int64()), ("count", pa.int64()), ("_timestamp", pa.timestamp("ns"))])
+    owner_op = native.SlidingAggregatingWindowFunc(owner_cfg, input_schema=p_schema, device=local, stream=stream,
+                                                   flags=B.op_flags(args), expected_keys=max(2 * args.keys // world, 1024),
+                                                   task_index=rank, parallelism=world)
+    ex.holder = type(ex.holder)(world)  # fresh watermark state for this pass
+    lctx, octx, col = ab.OperatorContext(1), ab.OperatorContext(1), ab.Collector()
+    empty_cols = [torch.empty(0, dtype=torch.int64, device=device) for _ in range(4)]
+    part_rows = part.out[0].numel()
+    d2h = 0
+
+    def step(p):
+        nonlocal d2h
+        for b in range(nb):
+            local_op.process_batch(batches[p][b], lctx, col)
+            wm = wms[p * nb + b]
+            if wm is None:
+                continue
+            eff = ex.exchange_watermark(wm)
+            if eff is None:
+                continue
+            chunks = []
+            for n, cols in local_op.handle_watermark_device(eff):
+                for o in range(0, n, part_rows):
+                    m = min(part_rows, n - o)
+                    chunks.append(([torch.as_tensor(_Ptr(c + 8 * o, m), device=device) for c in cols], m))
+            n_rounds = torch.tensor([len(chunks)], dtype=torch.int64, device=device)
+            dist.all_reduce(n_rounds, op=dist.ReduceOp.MAX)
+            for r in range(int(n_rounds.item())):
+                tc, m = chunks[r] if r < len(chunks) else (empty_cols, 0)
+                rc, n_recv, _ = ex.round(tc, m, None)
+                if n_recv:
+                    owner_op.process_device_batch([c.data_ptr() for c in rc], n_recv)
+                    owner_op.flush()
+            octx.watermarks.set(0, eff)
+            owner_op.handle_watermark(eff, octx, col)
+            for rb in col.batches:
+                d2h += rb.num_rows * 48
+            col.batches.clear()
+
+    for p in range(W):
+        step(p)
+    owner_op.flush()
+    torch.cuda.synchronize()
+    dist.barrier()
+    d2h = 0
+    t0 = time.perf_counter()
+    for p in range(W, W + K):
+        step(p)
+    owner_op.flush()
+    local_op.flush()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    tot = torch.tensor([d2h], dtype=torch.int64, device=device)
+    dist.all_reduce(tot)
+    owner_op.close()
+    local_op.close()
+    dt = float(dt.item())
+    return {"value": world * K * rows / dt, "unit": "rows/s", "h2d_bytes_per_step": world * rows * 24,
+            "d2h_bytes_per_step": int(tot.item()) // max(K, 1), "steps": K, "ms_per_step": 1e3 * dt / K,
+            "path": "per GPU: pinned host Arrow batches -> arroyo_b200_op_process_batch -> partials over NCCL all-to-all "
+                    "-> host Arrow windows"}
+
+
 def bench(args, torch, dist, rank, world, local):
     """Weak scaling: every GPU ingests its own 16 Mi-row/pane shard of the stream.
 
@@ -300,6 +386,9 @@ def bench(args, torch, dist, rank, world, local):
     owner_op.close()
     if local_op is not None:
         local_op.close()
+    e2e = None
+    if mode == "partials" and not args.skip_e2e:
+        e2e = _e2e_partials(args, torch, dist, B, ab, native, rank, world, local, device, gen_pane, part, ex)
     part.close()
     if rank == 0:
         peak, peak_kind = B.measured_peak()
@@ -321,7 +410,7 @@ def bench(args, torch, dist, rank, world, local):
                             "peak_kind": peak_kind, "unit": "GB/s",
                             "frac": round(ingest_gbs / peak, 4) if ingest_gbs else None, "traffic": None,
                             "note": "rank 0's raw-row ingest kernel"},
-               "e2e": None, "clocks": clocks,
+               "e2e": e2e, "clocks": clocks,
                "shuffle_bytes_sent_per_step_per_gpu": sent // max(K, 1)}
         print(json.dumps(out), flush=True)
     dist.barrier()

@@ -388,19 +388,14 @@ def run_ours(args):
     print(json.dumps(out), flush=True)
 
 
-def run_e2e(args, torch, device, local, gen_pane):
+def host_feed(torch, gen_pane, pane_ids, rows):
+    """Pinned host copies of the given panes as Arrow batches of BATCH_ROWS rows (zero copy: the Arrow buffers
+    *are* the pinned memory) and the watermark each batch triggers (fresh WatermarkGenerator)."""
     import pyarrow as pa
-
-    import arroyo_b200 as ab
-    from arroyo_b200 import ffi, operators as native
-    K = args.e2e_steps or min(args.steps, 10)
-    W = 11
-    rows = args.rows_per_pane
     nb = rows // BATCH_ROWS
-    # pinned host panes holding the same synthetic stream (key / value pool + per-pane timestamps)
     host_pool = {}
     host = []
-    for p in range(W + K):
+    for p in pane_ids:
         k, v, t = gen_pane(p)
         if p % POOL not in host_pool:
             hk = torch.empty(rows, dtype=torch.int64, pin_memory=True)
@@ -418,8 +413,7 @@ def run_e2e(args, torch, device, local, gen_pane):
         arrs = []
         for ci, h in enumerate(cols):
             a = h.numpy()[b * BATCH_ROWS:(b + 1) * BATCH_ROWS]
-            buf = pa.py_buffer(a)  # zero copy: the Arrow buffer *is* the pinned memory
-            arrs.append(pa.Array.from_buffers(ts_type if ci == 2 else pa.int64(), BATCH_ROWS, [None, buf]))
+            arrs.append(pa.Array.from_buffers(ts_type if ci == 2 else pa.int64(), BATCH_ROWS, [None, pa.py_buffer(a)]))
         return pa.RecordBatch.from_arrays(arrs, names=["key", "value", "_timestamp"])
 
     batches = [[arrow_batch(cols, b) for b in range(nb)] for cols in host]
@@ -427,7 +421,19 @@ def run_e2e(args, torch, device, local, gen_pane):
     for cols in host:
         t = cols[2].view(nb, BATCH_ROWS)
         mm += list(zip(t.amin(dim=1).tolist(), t.amax(dim=1).tolist()))
-    wms = watermark_schedule(mm)
+    return batches, watermark_schedule(mm), host
+
+
+def run_e2e(args, torch, device, local, gen_pane):
+    import pyarrow as pa
+
+    import arroyo_b200 as ab
+    from arroyo_b200 import ffi, operators as native
+    K = args.e2e_steps or min(args.steps, 10)
+    W = 11
+    rows = args.rows_per_pane
+    nb = rows // BATCH_ROWS
+    batches, wms, _keep = host_feed(torch, gen_pane, range(W + K), rows)
     op = native.SlidingAggregatingWindowFunc(window_config(), device=local, expected_keys=args.keys,
                                              flags=op_flags(args))
     ctx = ab.OperatorContext(1)
