@@ -78,7 +78,7 @@ struct SessCtx {
 
 enum : unsigned long long { ERR_POOL = 1, ERR_ADD_FLUSHED = 2, ERR_BEFORE_START = 4, ERR_OUT = 8, ERR_LOOP = 16 };
 // every device loop over the linked lists is bounded: a corrupted list must surface as an error, never as a hang
-constexpr int LOOP_GUARD = 1 << 24;
+constexpr int LOOP_GUARD = 1 << 20;
 
 struct RowsRef {
   const long long* ts;
@@ -251,7 +251,11 @@ __device__ void fill_active_session(const SessCtx& c, uint32_t id) {
 __device__ void finish_session(const SessCtx& c, uint32_t id) {
   const unsigned long long o = atomicAdd(c.ctr + 4, 1ull);
   if (o >= c.out_cap) {
+    // cannot happen (the host sizes the output for one session per live row): still close the session so the
+    // caller's loop makes progress, and report
     set_err(c, ERR_OUT);
+    c.active[id] = 0;
+    atomicAdd(c.ctr + 7, (unsigned long long)-1ll);
     return;
   }
   const long long start = c.data_start[id], end = c.data_end[id] + c.gap;
@@ -1012,7 +1016,12 @@ void SessionOp::apply_pending() {
   unsigned long long zero = 0;
   AB_CUDA(cudaMemcpyAsync(ctr_.as<unsigned long long>() + 6, &zero, 8, cudaMemcpyHostToDevice, stream_));
   if (n == 0) return;
-  ensure_pools(2 * n + 16, n);
+  {
+    // one node per new run, plus at most one remainder per row that can still be merged (new or already pending)
+    const unsigned long long* hh = h_ctr_.as<unsigned long long>();
+    const uint64_t live_rows = hh[1] - hh[3];
+    ensure_pools(2 * n + live_rows + 16, n);
+  }
   device_exclusive_scan(count_.as<unsigned int>(), n_keys_, offset_.as<unsigned long long>(),
                         ctr_.as<unsigned long long>() + 6 /* scratch: re-zeroed below */, scan_sums_, stream_);
   AB_CUDA(cudaMemcpyAsync(ctr_.as<unsigned long long>() + 6, &zero, 8, cudaMemcpyHostToDevice, stream_));
@@ -1116,7 +1125,10 @@ void SessionOp::handle_watermark(int64_t wm, BatchesPriv* out_host, std::vector<
   // every session that can close: one per open session plus one per pending run at most
   read_ctr();
   const unsigned long long* h = h_ctr_.as<unsigned long long>();
-  const uint64_t bound = h[7] + (h[0] - h[2]) + 16;
+  // every closed session holds at least one row: open sessions + pending rows bound the output, and every
+  // remainder run created while filling consumes at least one pending row
+  const uint64_t live_rows = h[1] - h[3];
+  const uint64_t bound = h[7] + live_rows + 16;
   if (bound > out_cap_) {
     out_cap_ = std::max<uint64_t>(bound, out_cap_ * 2);
     o_key_.alloc(out_cap_ * 8);
@@ -1125,7 +1137,7 @@ void SessionOp::handle_watermark(int64_t wm, BatchesPriv* out_host, std::vector<
     o_ts_.alloc(out_cap_ * 8);
     for (int g = 0; g < n_aggs_; ++g) o_agg_[g].alloc(out_cap_ * 8);
   }
-  ensure_pools((h[0] - h[2]) + 16, 0);  // remainders created while filling
+  ensure_pools(live_rows + 16, 0);  // remainders created while filling
   unsigned long long zero = 0;
   AB_CUDA(cudaMemcpyAsync(ctr_.as<unsigned long long>() + 4, &zero, 8, cudaMemcpyHostToDevice, stream_));
   AdvanceParams a{};
