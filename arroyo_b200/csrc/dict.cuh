@@ -5,6 +5,7 @@
 #pragma once
 
 #include <climits>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -129,7 +130,16 @@ __device__ __forceinline__ uint32_t resolve_id(const DictView& d, long long key,
 
 // slot count: 3.5 x ids => load factor 0.25 at the expected key count (0.29 when every id is used).
 // Measured (profiles/r01_probe2.txt): the random 16-byte probe runs at 92 G/s at load 0.25 vs 72 G/s at
-// 0.5 -- shorter chains mean fewer divergent replays per warp.
-inline uint64_t dict_slots_for(uint64_t ids) { return ids * 7 / 2 > 1024 ? ids * 7 / 2 : 1024; }
+// 0.5 -- shorter chains mean fewer divergent replays per warp.  ARROYO_B200_DICT_QUARTER_SLOTS_PER_ID
+// (default 14 = 3.5 slots per id) trades chain length against L2 footprint for experiments.
+inline uint64_t dict_slots_for(uint64_t ids) {
+  static const uint64_t q = [] {
+    const char* e = getenv("ARROYO_B200_DICT_QUARTER_SLOTS_PER_ID");
+    uint64_t v = e ? strtoull(e, nullptr, 10) : 14;
+    return v < 5 ? 5 : (v > 64 ? 64 : v);
+  }();
+  const uint64_t n = ids * q / 4;
+  return n > 1024 ? n : 1024;
+}
 
 }  // namespace ab

@@ -395,7 +395,7 @@ __device__ __forceinline__ void combine_accumulate(const IngestParams& p, const 
 #define AB_INGEST_PREFETCH 1
 #endif
 #ifndef AB_INGEST_MIN_BLOCKS
-#define AB_INGEST_MIN_BLOCKS 5
+#define AB_INGEST_MIN_BLOCKS 4
 #endif
 template <int NV, int SIG>
 __global__ void __launch_bounds__(THREADS, AB_INGEST_MIN_BLOCKS) ingest_kernel(const __grid_constant__ IngestParams p) {
@@ -934,6 +934,7 @@ class WindowAggOp final : public OpBase {
   void set_device() { AB_CUDA(cudaSetDevice(device_)); }
   void alloc_dictionary(uint64_t id_cap);
   void grow_ids();
+  void apply_l2_policy();
   void promote_avg();
   void relayout_blocks(int old_n_acc, const std::vector<std::pair<int, int>>& f64_from);
   unsigned long long* acquire_block();
@@ -1159,7 +1160,29 @@ void WindowAggOp::alloc_dictionary(uint64_t id_cap) {
     dict_init_kernel<<<num_sms_ * 4, 256, 0, stream_>>>(slots_.as<Slot>(), dict_cap_);
     AB_CUDA(cudaGetLastError());
     ++st_.kernel_launches;
+    apply_l2_policy();
   }
+}
+
+// ARROYO_B200_L2_PERSIST=1: ask L2 to keep the key dictionary resident (persisting access-policy window on the
+// operator's stream); everything else the stream touches is treated as streaming.
+void WindowAggOp::apply_l2_policy() {
+  const char* e = getenv("ARROYO_B200_L2_PERSIST");
+  if (!e || atoi(e) == 0 || !slots_.p) return;
+  int max_persist = 0, max_window = 0;
+  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device_);
+  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device_);
+  size_t bytes = std::min<size_t>(dict_cap_ * sizeof(Slot), (size_t)std::max(max_window, 0));
+  if (bytes == 0 || max_persist <= 0) return;
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(bytes, (size_t)max_persist));
+  cudaStreamAttrValue attr{};
+  attr.accessPolicyWindow.base_ptr = slots_.p;
+  attr.accessPolicyWindow.num_bytes = bytes;
+  attr.accessPolicyWindow.hitRatio = std::min(1.0f, (float)max_persist / (float)bytes);
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  cudaStreamSetAttribute(stream_, cudaStreamAttributeAccessPolicyWindow, &attr);
+  cudaGetLastError();
 }
 
 void WindowAggOp::init_block(unsigned long long* blk, uint64_t n_ids) {
@@ -1242,6 +1265,7 @@ void WindowAggOp::grow_ids() {
       AB_CUDA(cudaGetLastError());
     }
     st_.kernel_launches += 2;
+    apply_l2_policy();
   }
   // ids handed out beyond the old capacity were never usable: clamp the device counter
   unsigned int nk = n_valid;
