@@ -1,5 +1,6 @@
 // extern "C" entry points of libarroyo_b200.so (see include/arroyo_b200.h for the contract and the
 // reference interfaces each one replaces).  Nothing unwinds across this boundary.
+#include <chrono>
 #include <new>
 
 #include "op.h"
@@ -9,7 +10,17 @@ using namespace ab;
 
 struct ArroyoB200Op {
   OpBase* impl;
+  double host_process_ms = 0, host_watermark_ms = 0;
 };
+
+namespace {
+struct WallTimer {
+  double& acc;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  explicit WallTimer(double& a) : acc(a) {}
+  ~WallTimer() { acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+}  // namespace
 
 namespace {
 
@@ -91,7 +102,8 @@ int32_t arroyo_b200_op_create(const ArroyoB200OpConfig* config, ArroyoB200Op** o
         set_err(err, err_len, "unknown operator kind");
         return ARROYO_B200_INVALID_ARGUMENT;
     }
-    auto* h = new ArroyoB200Op{impl};
+    auto* h = new ArroyoB200Op();
+    h->impl = impl;
     *out = h;
     return ARROYO_B200_OK;
   } catch (const Error& e) {
@@ -132,6 +144,8 @@ int32_t arroyo_b200_op_on_start(ArroyoB200Op* op, struct ArrowArray* state, stru
 
 int32_t arroyo_b200_op_process_batch(ArroyoB200Op* op, uint32_t input_index, uint32_t in_partitions,
                                      struct ArrowArray* batch, const struct ArrowSchema* schema) {
+  if (!op) return ARROYO_B200_INVALID_ARGUMENT;
+  WallTimer wt(op->host_process_ms);
   return guarded(op, [&](OpBase* o) { o->process_batch(input_index, in_partitions, batch, schema); });
 }
 
@@ -146,6 +160,8 @@ int32_t arroyo_b200_op_process_device_batch(ArroyoB200Op* op, uint32_t input_ind
 int32_t arroyo_b200_op_process_device_batches(ArroyoB200Op* op, uint32_t input_index, uint32_t in_partitions,
                                               const uint64_t* cols, int32_t n_cols, const int64_t* n_rows,
                                               int64_t n_batches) {
+  if (!op) return ARROYO_B200_INVALID_ARGUMENT;
+  WallTimer wt(op->host_process_ms);
   return guarded(op, [&](OpBase* o) {
     AB_REQUIRE(cols != nullptr && n_rows != nullptr && n_cols > 0 && n_batches >= 0, ARROYO_B200_INVALID_ARGUMENT,
                "null batch list");
@@ -156,6 +172,8 @@ int32_t arroyo_b200_op_process_device_batches(ArroyoB200Op* op, uint32_t input_i
 
 int32_t arroyo_b200_op_handle_watermark(ArroyoB200Op* op, int64_t watermark_ns, ArroyoB200Batches* out) {
   if (out) memset(out, 0, sizeof *out);
+  if (!op) return ARROYO_B200_INVALID_ARGUMENT;
+  WallTimer wt(op->host_watermark_ms);
   return guarded(op, [&](OpBase* o) {
     AB_REQUIRE(out != nullptr, ARROYO_B200_INVALID_ARGUMENT, "null out");
     auto* priv = new BatchesPriv();
@@ -174,6 +192,8 @@ int32_t arroyo_b200_op_handle_watermark(ArroyoB200Op* op, int64_t watermark_ns, 
 int32_t arroyo_b200_op_handle_watermark_device(ArroyoB200Op* op, int64_t watermark_ns, ArroyoB200DeviceBatch* out,
                                                int64_t max_out, int64_t* n_out) {
   if (n_out) *n_out = 0;
+  if (!op) return ARROYO_B200_INVALID_ARGUMENT;
+  WallTimer wt(op->host_watermark_ms);
   return guarded(op, [&](OpBase* o) {
     AB_REQUIRE(n_out != nullptr && (out != nullptr || max_out == 0), ARROYO_B200_INVALID_ARGUMENT, "null out");
     std::vector<ArroyoB200DeviceBatch> v;
@@ -233,6 +253,8 @@ int32_t arroyo_b200_op_stats(ArroyoB200Op* op, ArroyoB200Stats* out) {
   return guarded(op, [&](OpBase* o) {
     AB_REQUIRE(out != nullptr, ARROYO_B200_INVALID_ARGUMENT, "null out");
     o->stats(out);
+    out->host_process_ms = op->host_process_ms;
+    out->host_watermark_ms = op->host_watermark_ms;
   });
 }
 

@@ -78,6 +78,7 @@ class Stats(C.Structure):
         ("ingest_launches", C.c_uint64), ("emit_launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
         ("d2h_bytes", C.c_uint64), ("ingest_ms", C.c_double), ("emit_ms", C.c_double),
         ("ingest_rows_timed", C.c_uint64), ("emit_rows_timed", C.c_uint64),
+        ("host_process_ms", C.c_double), ("host_watermark_ms", C.c_double),
     ]
 
     def as_dict(self):

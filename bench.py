@@ -362,7 +362,9 @@ def run_ours(args):
             "algorithmic_bytes_per_launch": 24.0 * d["ingest_rows_timed"] / max(d["ingest_launches"], 1),
             "ingest_ms_per_step": d["ingest_ms"] / K, "emit_ms_per_step": d["emit_ms"] / K,
             "ingest_share_of_step": round(d["ingest_ms"] / ms, 3), "emit_share_of_step": round(emit_share, 3),
-            "pipeline_frac": round(step_bytes * K / (ms * 1e-3) / 1e9 / peak, 4)}
+            "pipeline_frac": round(step_bytes * K / (ms * 1e-3) / 1e9 / peak, 4),
+            "host_process_ms_per_step": round(d["host_process_ms"] / K, 4),
+            "host_watermark_ms_per_step": round(d["host_watermark_ms"] / K, 4)}
 
     out = {"metric": "rows/sec sliding-window SUM (1M keys)", "value": value, "unit": "rows/s", "n_gpus": 1,
            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",

@@ -212,6 +212,8 @@ typedef struct ArroyoB200Stats {
   double emit_ms;
   uint64_t ingest_rows_timed; /* rows covered by ingest_ms                             */
   uint64_t emit_rows_timed;   /* key slots scanned during emit_ms                      */
+  double host_process_ms;     /* wall clock spent inside process_batch* calls          */
+  double host_watermark_ms;   /* wall clock spent inside handle_watermark* calls       */
 } ArroyoB200Stats;
 
 /* ---- library ---- */
