@@ -60,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(f"--- nvcc {s} ---\n{out}\n")
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    cmd = [nvcc_path(), "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart"]
     subprocess.check_call(cmd)
     return LIB
 

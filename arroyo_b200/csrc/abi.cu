@@ -247,6 +247,10 @@ int32_t arroyo_b200_op_flush(ArroyoB200Op* op) {
   return guarded(op, [&](OpBase* o) { o->flush(); });
 }
 
+int32_t arroyo_b200_op_submit(ArroyoB200Op* op) {
+  return guarded(op, [&](OpBase* o) { o->submit(); });
+}
+
 void arroyo_b200_release_batches(ArroyoB200Batches* batches) { batches_release(batches); }
 
 int32_t arroyo_b200_op_stats(ArroyoB200Op* op, ArroyoB200Stats* out) {

@@ -28,7 +28,15 @@ struct DictView {
   unsigned int* n_keys;
   uint32_t cap;  // number of slots (any value: placement is multiply-shift, not a mask)
   uint32_t id_cap;
+  // direct-mapped range: keys in [dbase, dbase + dn) own the ids [1, dn] without touching the slot array
+  // (dense integer keys -- Nexmark's auction / bidder ids -- need no hashing at all); dn = 0 disables it
+  long long dbase;
+  uint32_t dn;
 };
+
+__device__ __forceinline__ bool dict_is_direct(const DictView& d, long long key) {
+  return ((unsigned long long)key - (unsigned long long)d.dbase) < (unsigned long long)d.dn;
+}
 
 __host__ __device__ __forceinline__ uint32_t dict_home(uint64_t key, uint32_t cap) {
   return (uint32_t)(((mix64(key) >> 32) * (uint64_t)cap) >> 32);
@@ -59,9 +67,10 @@ static __global__ void dict_init_kernel(Slot* slots, uint64_t n) {
   }
 }
 
-// re-insert ids [1, n) after the slot array was replaced
-static __global__ void dict_rebuild_kernel(Slot* slots, uint32_t cap, const long long* id_keys, uint32_t n) {
-  uint32_t id = blockIdx.x * blockDim.x + threadIdx.x + 1;
+// re-insert ids [first, n) after the slot array was replaced (ids below `first` are direct-mapped)
+static __global__ void dict_rebuild_kernel(Slot* slots, uint32_t cap, const long long* id_keys, uint32_t n,
+                                           uint32_t first) {
+  uint32_t id = blockIdx.x * blockDim.x + threadIdx.x + first;
   uint32_t stride = gridDim.x * blockDim.x;
   for (; id < n; id += stride) {
     long long key = id_keys[id];
@@ -114,6 +123,7 @@ static __device__ __noinline__ uint32_t dict_insert(const DictView& d, long long
 // Dense id of `key` given its home slot contents `raw` (already loaded).  Existing keys resolve with
 // read-only probes inline; the insert path is out of line.
 __device__ __forceinline__ uint32_t resolve_id(const DictView& d, long long key, unsigned long long k0, uint32_t id0) {
+  if (dict_is_direct(d, key)) return (uint32_t)((unsigned long long)key - (unsigned long long)d.dbase) + 1u;
   if ((long long)k0 == key && id0 < ID_OVERFLOW) return id0;
   if (key == EMPTY_KEY) return 0;  // id 0 is reserved for the one key that equals the empty sentinel
   uint32_t pos = dict_home((uint64_t)key, d.cap);
@@ -126,6 +136,13 @@ __device__ __forceinline__ uint32_t resolve_id(const DictView& d, long long key,
     if ((long long)raw.x == EMPTY_KEY || (long long)raw.x == key) return dict_insert(d, key, pos);
   }
   return ID_OVERFLOW;
+}
+
+// Id of `key`, inserting it on first sight (cold paths: restore, partial-state merge, sessions).
+static __device__ __forceinline__ uint32_t dict_lookup_or_insert(const DictView& d, long long key) {
+  if (dict_is_direct(d, key)) return (uint32_t)((unsigned long long)key - (unsigned long long)d.dbase) + 1u;
+  if (key == EMPTY_KEY) return 0u;
+  return dict_insert(d, key, dict_home((uint64_t)key, d.cap));
 }
 
 // slot count: 3.5 x ids => load factor 0.25 at the expected key count (0.29 when every id is used).

@@ -26,6 +26,8 @@ class OpBase {
   virtual void handle_checkpoint(int64_t watermark, BatchesPriv* out) = 0;
   virtual void on_close(int end_of_data, BatchesPriv* out) = 0;
   virtual void flush() = 0;
+  // enqueue whatever input is still being batched on the host side; does not wait
+  virtual void submit() {}
   virtual void stats(ArroyoB200Stats* out) = 0;
 };
 

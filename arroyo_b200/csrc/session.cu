@@ -792,7 +792,7 @@ void SessionOp::grow_keys(uint64_t need) {
     AB_CUDA(cudaGetLastError());
     if (nv > 1) {
       dict_rebuild_kernel<<<grid_for(nv, 256), 256, 0, stream_>>>(slots_.as<Slot>(), (uint32_t)dict_cap_,
-                                                                  id_keys_.as<long long>(), (uint32_t)nv);
+                                                                  id_keys_.as<long long>(), (uint32_t)nv, 1u);
       AB_CUDA(cudaGetLastError());
     }
   }
@@ -933,6 +933,8 @@ void SessionOp::prep(const long long* key, const long long* ts, const long long*
   p.dict.n_keys = n_keys_dev_.as<unsigned int>();
   p.dict.cap = keyed_ ? (uint32_t)dict_cap_ : 1;
   p.dict.id_cap = (uint32_t)std::min<uint64_t>(id_cap_, 0xFFFFFFF0ull);
+  p.dict.dbase = 0;
+  p.dict.dn = 0;  // sessions keep every key in the slot array
   p.a_id = a_id_.as<unsigned int>();
   p.a_seq = a_seq_.as<unsigned int>();
   p.a_ts = a_ts_.as<long long>();

@@ -107,14 +107,25 @@ struct ScatterParams {
   uint32_t n_dest;
   const unsigned int* block_off;
   const long long* offsets;
+  // packed layout (one all-to-all instead of one per column): destination d owns the element range
+  // [n_cols * offsets[d], n_cols * (offsets[d] + counts[d])) of `packed`, its columns back to back
+  long long* packed;
+  const long long* counts;
 };
 
 __global__ void __launch_bounds__(PT_THREADS) scatter_kernel(const __grid_constant__ ScatterParams p) {
   __shared__ unsigned int s_cursor[MAX_DEST];
   __shared__ long long s_base[MAX_DEST];
+  __shared__ long long s_count[MAX_DEST];
   for (int i = threadIdx.x; i < (int)p.n_dest; i += PT_THREADS) {
     s_cursor[i] = 0;
-    s_base[i] = p.offsets[i] + (long long)p.block_off[(size_t)i * gridDim.x + blockIdx.x];
+    const long long in_seg = (long long)p.block_off[(size_t)i * gridDim.x + blockIdx.x];
+    if (p.packed) {
+      s_base[i] = (long long)p.n_cols * p.offsets[i] + in_seg;
+      s_count[i] = p.counts[i];
+    } else {
+      s_base[i] = p.offsets[i] + in_seg;
+    }
   }
   __syncthreads();
   const long long base = (long long)blockIdx.x * PT_ROWS;
@@ -123,8 +134,14 @@ __global__ void __launch_bounds__(PT_THREADS) scatter_kernel(const __grid_consta
     if (r < p.n) {
       uint32_t d = dest_of(__ldcs(p.in[p.key_col] + r), p.range, p.n_dest);
       long long o = s_base[d] + (long long)atomicAdd(&s_cursor[d], 1u);
+      if (p.packed) {
+        const long long stride = s_count[d];
 #pragma unroll 4
-      for (int c = 0; c < p.n_cols; ++c) p.out[c][o] = __ldcs(p.in[c] + r);
+        for (int c = 0; c < p.n_cols; ++c) p.packed[o + c * stride] = __ldcs(p.in[c] + r);
+      } else {
+#pragma unroll 4
+        for (int c = 0; c < p.n_cols; ++c) p.out[c][o] = __ldcs(p.in[c] + r);
+      }
     }
   }
 }
@@ -223,9 +240,11 @@ void arroyo_b200_partitioner_destroy(ArroyoB200Partitioner* p) {
   delete p;
 }
 
-int32_t arroyo_b200_partition(ArroyoB200Partitioner* p, const uint64_t* in_cols, int64_t n_rows,
-                              const uint64_t* out_cols, uint64_t counts_dev, uint64_t offsets_dev) {
-  if (!p || !in_cols || !out_cols || !counts_dev || !offsets_dev || n_rows < 0 || n_rows > p->max_rows)
+static int32_t partition_impl(ArroyoB200Partitioner* p, const uint64_t* in_cols, int64_t n_rows,
+                              const uint64_t* out_cols, uint64_t packed_dev, uint64_t counts_dev,
+                              uint64_t offsets_dev) {
+  if (!p || !in_cols || (!out_cols && !packed_dev) || !counts_dev || !offsets_dev || n_rows < 0 ||
+      n_rows > p->max_rows)
     return ARROYO_B200_INVALID_ARGUMENT;
   try {
     AB_CUDA(cudaSetDevice(p->device));
@@ -240,8 +259,10 @@ int32_t arroyo_b200_partition(ArroyoB200Partitioner* p, const uint64_t* in_cols,
     ScatterParams sp{};
     for (int c = 0; c < p->n_cols; ++c) {
       sp.in[c] = (const long long*)in_cols[c];
-      sp.out[c] = (long long*)out_cols[c];
+      sp.out[c] = out_cols ? (long long*)out_cols[c] : nullptr;
     }
+    sp.packed = (long long*)packed_dev;
+    sp.counts = (const long long*)counts_dev;
     sp.n_cols = p->n_cols;
     sp.key_col = p->key_col;
     sp.n = n_rows;
@@ -257,6 +278,18 @@ int32_t arroyo_b200_partition(ArroyoB200Partitioner* p, const uint64_t* in_cols,
   } catch (...) {
     return ARROYO_B200_RUNTIME;
   }
+}
+
+int32_t arroyo_b200_partition(ArroyoB200Partitioner* p, const uint64_t* in_cols, int64_t n_rows,
+                              const uint64_t* out_cols, uint64_t counts_dev, uint64_t offsets_dev) {
+  if (!out_cols) return ARROYO_B200_INVALID_ARGUMENT;
+  return partition_impl(p, in_cols, n_rows, out_cols, 0, counts_dev, offsets_dev);
+}
+
+int32_t arroyo_b200_partition_packed(ArroyoB200Partitioner* p, const uint64_t* in_cols, int64_t n_rows,
+                                     uint64_t packed_dev, uint64_t counts_dev, uint64_t offsets_dev) {
+  if (!packed_dev) return ARROYO_B200_INVALID_ARGUMENT;
+  return partition_impl(p, in_cols, n_rows, nullptr, packed_dev, counts_dev, offsets_dev);
 }
 
 }  // extern "C"

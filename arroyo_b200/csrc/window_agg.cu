@@ -249,8 +249,9 @@ __device__ __noinline__ void slow_row(const IngestParams& p, long long key, long
   uint32_t id = 0;
   bool ok = ring_bin(p, slot) == (long long)(q * (uint64_t)p.slide);
   if (ok && p.keyed) {
-    const uint32_t pos = dict_home((uint64_t)key, p.dict.cap);
-    const ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(p.dict.slots + pos));
+    ulonglong2 raw = {0, 0};
+    if (!dict_is_direct(p.dict, key))
+      raw = __ldcg(reinterpret_cast<const ulonglong2*>(p.dict.slots + dict_home((uint64_t)key, p.dict.cap)));
     id = resolve_id(p.dict, key, raw.x, (uint32_t)raw.y);
     ok = id < ID_OVERFLOW;
   }
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(THREADS, AB_INGEST_MIN_BLOCKS) ingest_kernel(c
 #pragma unroll
       for (int x = 0; x < (NV > 0 ? NV : 1); ++x) v[x] = nv[x];
       ulonglong2 raw = {0, 0};
-      if (valid && keyed)
+      if (valid && keyed && !dict_is_direct(p.dict, key))
         raw = __ldcg(reinterpret_cast<const ulonglong2*>(p.dict.slots + dict_home((uint64_t)key, p.dict.cap)));
 #if AB_INGEST_PREFETCH
       if (i + THREADS < cnt) {
@@ -539,7 +540,7 @@ __global__ void ingest_partial_kernel(const __grid_constant__ PartialParams p) {
   for (; i < p.n; i += stride) {
     uint32_t id = 0;
     if (p.keyed) {
-      id = p.key[i] == EMPTY_KEY ? 0u : dict_insert(p.dict, p.key[i], dict_home((uint64_t)p.key[i], p.dict.cap));
+      id = dict_lookup_or_insert(p.dict, p.key[i]);
       if (id >= ID_OVERFLOW) {
         atomicAdd(&p.counters->lost, 1ull);
         continue;
@@ -825,6 +826,7 @@ class WindowAggOp final : public OpBase {
   void handle_checkpoint(int64_t wm, BatchesPriv* out) override;
   void on_close(int, BatchesPriv*) override { flush(); }
   void flush() override;
+  void submit() override;
   void stats(ArroyoB200Stats* out) override;
 
  private:
@@ -865,6 +867,11 @@ class WindowAggOp final : public OpBase {
   uint64_t dict_cap_ = 0;
   DevBuf slots_, id_keys_, counters_, slot_rows_;
   uint32_t n_keys_host_ = 1;
+  // direct-mapped key range (dict.cuh): decided once, from the first rows, before any id exists
+  bool direct_decided_ = false;
+  long long direct_base_ = 0;
+  uint32_t direct_n_ = 0;
+  void decide_direct(const std::vector<Segment>& segs);
 
   // ring
   uint32_t ring_ = 16;
@@ -1261,7 +1268,7 @@ void WindowAggOp::grow_ids() {
     if (n_valid > 1) {
       int blocks = (int)std::min<uint32_t>((n_valid + 255) / 256, (uint32_t)num_sms_ * 8);
       dict_rebuild_kernel<<<blocks, 256, 0, stream_>>>(slots_.as<Slot>(), (uint32_t)dict_cap_,
-                                                       id_keys_.as<long long>(), n_valid);
+                                                       id_keys_.as<long long>(), n_valid, direct_n_ + 1);
       AB_CUDA(cudaGetLastError());
     }
     st_.kernel_launches += 2;
@@ -1576,6 +1583,72 @@ void WindowAggOp::process_device_batch(uint32_t, uint32_t, const uint64_t* cols,
   }
 }
 
+// min / max of a key column (direct-range decision)
+__global__ void __launch_bounds__(256) key_minmax_kernel(const long long* __restrict__ key, long long n,
+                                                         long long* __restrict__ out /* [min, max] */) {
+  long long mn = LLONG_MAX, mx = LLONG_MIN;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long k = key[i];
+    mn = min(mn, k);
+    mx = max(mx, k);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0 && mn <= mx) {
+    atomicMin(out, mn);
+    atomicMax(out + 1, mx);
+  }
+}
+
+__global__ void fill_direct_keys_kernel(long long* __restrict__ id_keys, long long base, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (; i < n; i += stride) id_keys[1 + i] = (long long)((unsigned long long)base + i);
+}
+
+// Dense integer keys (Nexmark's auction / bidder ids, most surrogate keys) need no hash table: if the keys
+// of the first rows span less than the id space that is already allocated, [min, min + span) is mapped
+// straight onto the ids [1, span].  Keys outside the range -- now or later -- go through the slot array as
+// before, so this only ever removes probes.  Decided once, before any id exists.
+void WindowAggOp::decide_direct(const std::vector<Segment>& segs) {
+  direct_decided_ = true;
+  if (!keyed_ || n_keys_host_ != 1 || !in_flight_.empty() || (cfg.flags & ARROYO_B200_FLAG_NO_DIRECT)) return;
+  const char* e = getenv("ARROYO_B200_NO_DIRECT");
+  if (e && atoi(e) != 0) return;
+  DevBuf mm(2 * sizeof(long long));
+  const long long init[2] = {LLONG_MAX, LLONG_MIN};
+  AB_CUDA(cudaMemcpyAsync(mm.p, init, sizeof init, cudaMemcpyHostToDevice, stream_));
+  const size_t step = std::max<size_t>(segs.size() / 32, 1);  // a sample of the launch is enough
+  for (size_t i = 0; i < segs.size(); i += step) {
+    if (segs[i].n <= 0) continue;
+    int grid = (int)std::min<long long>((segs[i].n + 255) / 256, (long long)num_sms_ * 4);
+    key_minmax_kernel<<<grid, 256, 0, stream_>>>(segs[i].key, segs[i].n, mm.as<long long>());
+    AB_CUDA(cudaGetLastError());
+    ++st_.kernel_launches;
+  }
+  long long h[2];
+  AB_CUDA(cudaMemcpyAsync(h, mm.p, sizeof h, cudaMemcpyDeviceToHost, stream_));
+  AB_CUDA(cudaStreamSynchronize(stream_));
+  if (h[0] > h[1]) return;
+  const unsigned long long span = (unsigned long long)h[1] - (unsigned long long)h[0] + 1ull;  // 0 = the whole i64 range
+  const uint64_t room = id_cap_ - id_cap_ / 16 - 1;  // leave ids for keys outside the range
+  if (span == 0 || span > room) return;
+  const uint64_t dn = std::min<uint64_t>((span + 1023) / 1024 * 1024, room);
+  direct_base_ = h[0];
+  direct_n_ = (uint32_t)dn;
+  int grid = (int)std::min<uint64_t>((dn + 255) / 256, (uint64_t)num_sms_ * 8);
+  fill_direct_keys_kernel<<<grid, 256, 0, stream_>>>(id_keys_.as<long long>(), direct_base_, direct_n_);
+  AB_CUDA(cudaGetLastError());
+  ++st_.kernel_launches;
+  const unsigned int nk = direct_n_ + 1;
+  AB_CUDA(cudaMemcpyAsync((char*)counters_.p + offsetof(Counters, n_keys), &nk, sizeof nk, cudaMemcpyHostToDevice, stream_));
+  AB_CUDA(cudaStreamSynchronize(stream_));
+  n_keys_host_ = nk;
+}
+
 void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk) {
   // At most two launches (each <= chunk_rows_ rows) are ever in flight, so the deferred buffer
   // (2 * chunk_rows_ rows) cannot overflow; as soon as a finished launch reports deferrals they are
@@ -1585,6 +1658,7 @@ void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk
     while (!in_flight_.empty()) absorb(in_flight_.front());
     drain_deferred();
   }
+  if (!direct_decided_) decide_direct(segs_in);
   const int li = next_launch_;
   next_launch_ = (next_launch_ + 1) % NLAUNCH;
   LaunchRec& L = launches_[li];
@@ -1619,6 +1693,8 @@ void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk
   p.dict.n_keys = (unsigned int*)((char*)counters_.p + offsetof(Counters, n_keys));
   p.dict.cap = keyed_ ? (uint32_t)dict_cap_ : 1;
   p.dict.id_cap = (uint32_t)std::min<uint64_t>(id_cap_, 0xFFFFFFF0ull);
+  p.dict.dbase = direct_base_;
+  p.dict.dn = direct_n_;
   p.slide_div = FastDivU64::make((uint64_t)slide_);
   p.slide = slide_;
   p.late_bin = late_bin_;
@@ -1783,7 +1859,8 @@ void WindowAggOp::drain_deferred() {
     for (int64_t b : bins) ensure_pane(b);
     if (last_counters_.big_vals && avg_exact_) promote_avg();
     // dictionary pressure: grow when half full (keeps probes short) or when ids ran out
-    while (keyed_ && (uint64_t)last_counters_.n_keys + n / 2 >= id_cap_ / 2 + id_cap_ / 4) {
+    while (keyed_ && ((uint64_t)last_counters_.n_keys - direct_n_ + n / 2 >= id_cap_ / 2 + id_cap_ / 4 ||
+                      (uint64_t)last_counters_.n_keys + n / 2 >= id_cap_)) {
       n_keys_host_ = (uint32_t)std::min<uint64_t>(last_counters_.n_keys, id_cap_);
       grow_ids();
       last_counters_.n_keys = n_keys_host_;
@@ -1811,6 +1888,11 @@ void WindowAggOp::flush() {
   launch_pending();
   sync_all();
   poll_releases(true);
+}
+
+void WindowAggOp::submit() {
+  set_device();
+  launch_pending();
 }
 
 WindowAggOp::OutSet* WindowAggOp::out_set(size_t i, uint64_t cap) {
@@ -2311,6 +2393,7 @@ void WindowAggOp::on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, i
     }
     AB_REQUIRE(pp.state[0] != nullptr, ARROYO_B200_UNSUPPORTED,
                "restore needs a COUNT(*) or AVG state column to recover per-key row counts");
+    direct_decided_ = true;  // ids are being handed out by the restore: too late to reserve a direct range
     while (keyed_ && (uint64_t)n_keys_host_ + (uint64_t)rows >= id_cap_ / 2) {
       AB_CUDA(cudaStreamSynchronize(stream_));
       grow_ids();
@@ -2320,6 +2403,8 @@ void WindowAggOp::on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, i
     pp.dict.n_keys = (unsigned int*)((char*)counters_.p + offsetof(Counters, n_keys));
     pp.dict.cap = keyed_ ? (uint32_t)dict_cap_ : 1;
     pp.dict.id_cap = (uint32_t)id_cap_;
+    pp.dict.dbase = direct_base_;
+    pp.dict.dn = direct_n_;
     pp.pane = panes_.at(bin).frozen;
     pp.id_cap = id_cap_;
     pp.counters = counters_.as<Counters>();

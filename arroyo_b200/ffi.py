@@ -16,6 +16,7 @@ TUMBLING_AGGREGATE, SLIDING_AGGREGATE, SESSION_AGGREGATE, INSTANT_JOIN = 1, 2, 3
 AGG_COUNT_STAR, AGG_SUM_I64, AGG_AVG_I64, AGG_MIN_I64, AGG_MAX_I64 = 1, 2, 3, 4, 5
 JOIN_INNER, JOIN_LEFT, JOIN_RIGHT, JOIN_FULL = 0, 1, 2, 3
 FLAG_PROFILE, FLAG_REMERGE_ONLY, FLAG_COMBINE, FLAG_AVG_F64, FLAG_NO_COMBINE, FLAG_ZERO_COPY = 1, 2, 4, 8, 16, 32
+FLAG_NO_DIRECT = 64
 INT64_MIN = -(1 << 63)
 INT64_MAX = (1 << 63) - 1
 
@@ -110,6 +111,7 @@ SYMBOLS = [
     ("arroyo_b200_op_handle_checkpoint", C.c_int32, [_VP, C.c_int64, C.POINTER(Batches)]),
     ("arroyo_b200_op_on_close", C.c_int32, [_VP, C.c_int32, C.POINTER(Batches)]),
     ("arroyo_b200_op_flush", C.c_int32, [_VP]),
+    ("arroyo_b200_op_submit", C.c_int32, [_VP]),
     ("arroyo_b200_release_batches", None, [C.POINTER(Batches)]),
     ("arroyo_b200_op_stats", C.c_int32, [_VP, C.POINTER(Stats)]),
     ("arroyo_b200_partitioner_create", C.c_int32, [C.c_int32, C.c_uint64, C.c_int32, C.c_int32, C.c_int32,
@@ -117,6 +119,8 @@ SYMBOLS = [
     ("arroyo_b200_partitioner_destroy", None, [_VP]),
     ("arroyo_b200_partition", C.c_int32, [_VP, C.POINTER(C.c_uint64), C.c_int64, C.POINTER(C.c_uint64),
                                           C.c_uint64, C.c_uint64]),
+    ("arroyo_b200_partition_packed", C.c_int32, [_VP, C.POINTER(C.c_uint64), C.c_int64, C.c_uint64, C.c_uint64,
+                                                 C.c_uint64]),
     ("arroyo_b200_ts_minmax", C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, C.c_int64, C.POINTER(C.c_int64),
                                           C.POINTER(C.c_int64)]),
     ("arroyo_b200_hash_key", C.c_uint64, [C.c_int64]),

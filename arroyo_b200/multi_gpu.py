@@ -44,6 +44,9 @@ class DevicePartitioner:
         self.counts = torch.zeros(world, dtype=torch.int64, device=dev)
         self.offsets = torch.zeros(world, dtype=torch.int64, device=dev)
         self.n_cols = n_cols
+        self.max_rows = max_rows
+        self._packed = None
+        self._dev = dev
 
     def __call__(self, cols: Sequence, n_rows: int):
         inp = (C.c_uint64 * self.n_cols)(*[c.data_ptr() for c in cols])
@@ -52,6 +55,18 @@ class DevicePartitioner:
         if st != ffi.OK:
             raise ffi.ArroyoB200Error(st, "partition failed")
         return [o[:n_rows] for o in self.out], self.counts
+
+    def pack(self, col_ptrs: Sequence[int], n_rows: int):
+        """arroyo_b200_partition_packed: `col_ptrs` are raw device pointers; returns (packed buffer,
+        counts[world] device tensor).  Destination d's block holds its n_cols columns back to back."""
+        if self._packed is None:
+            self._packed = self.torch.empty(self.max_rows * self.n_cols, dtype=self.torch.int64, device=self._dev)
+        inp = (C.c_uint64 * self.n_cols)(*col_ptrs)
+        st = self.lib.arroyo_b200_partition_packed(self.h, inp, n_rows, self._packed.data_ptr(), self.counts.data_ptr(),
+                                                   self.offsets.data_ptr())
+        if st != ffi.OK:
+            raise ffi.ArroyoB200Error(st, "partition_packed failed")
+        return self._packed[:n_rows * self.n_cols], self.counts
 
     def close(self):
         if self.h:
@@ -74,9 +89,14 @@ class ShuffleExchange:
         self.torch, self.dist, self.rank, self.world = torch, dist, rank, world
         self.partition_fn = partition_fn
         self.device = device
-        self.ctrl = torch.zeros(world + 1, dtype=torch.int64, device=device)
-        self.ctrl_all = torch.zeros(world * (world + 1), dtype=torch.int64, device=device)
-        self.recv = [torch.empty(max_recv_rows, dtype=torch.int64, device=device) for _ in range(n_cols)]
+        # one control record per sender and round: rows for every destination, the sender's watermark (or none),
+        # and whether the sender has more rounds queued behind this one
+        self.ctrl = torch.zeros(world + 2, dtype=torch.int64, device=device)
+        self.ctrl_all = torch.zeros(world * (world + 2), dtype=torch.int64, device=device)
+        self._recv = None
+        self._recv_packed = None
+        self._flip = 0
+        self.n_cols = n_cols
         self.max_recv_rows = max_recv_rows
         self.holder = WatermarkHolder(world)
         self.bytes_sent = 0
@@ -85,10 +105,10 @@ class ShuffleExchange:
         """Broadcasts this sender's watermark (or none) and returns the min-merged effective watermark if it
         advanced (signals go to every downstream queue, context.rs:663-677; merge = WatermarkHolder)."""
         torch, dist, W = self.torch, self.dist, self.world
-        self.ctrl[:W] = 0
+        self.ctrl.zero_()
         self.ctrl[W] = NO_WM if watermark is None else int(min(watermark, (1 << 63) - 1))
         dist.all_gather_into_tensor(self.ctrl_all, self.ctrl)
-        m = self.ctrl_all.view(W, W + 1)[:, W].cpu().tolist()
+        m = self.ctrl_all.view(W, W + 2)[:, W].cpu().tolist()
         before = self.holder.last_present_watermark
         for s, wm in enumerate(m):
             if wm != NO_WM:
@@ -107,15 +127,19 @@ class ShuffleExchange:
             send_cols = [c[:0] for c in cols]
             self.ctrl[:W] = 0
         self.ctrl[W] = NO_WM if watermark is None else int(min(watermark, (1 << 63) - 1))
+        self.ctrl[W + 1] = 0
         dist.all_gather_into_tensor(self.ctrl_all, self.ctrl)
-        m = self.ctrl_all.view(W, W + 1).cpu()  # the one host sync of the round: split sizes
+        m = self.ctrl_all.view(W, W + 2).cpu()  # the one host sync of the round: split sizes
         send_splits = m[self.rank, :W].tolist()
         recv_splits = m[:, self.rank].tolist()
         n_recv = int(sum(recv_splits))
         if n_recv > self.max_recv_rows:
             raise RuntimeError(f"shuffle receive buffer too small: {n_recv} > {self.max_recv_rows}")
+        if self._recv is None:
+            self._recv = [torch.empty(self.max_recv_rows, dtype=torch.int64, device=self.device)
+                          for _ in range(self.n_cols)]
         out = []
-        for c, r in zip(send_cols, self.recv):
+        for c, r in zip(send_cols, self._recv):
             o = r[:n_recv]
             dist.all_to_all_single(o, c, recv_splits, send_splits)
             out.append(o)
@@ -128,6 +152,49 @@ class ShuffleExchange:
         after = self.holder.last_present_watermark
         return out, n_recv, (after if after is not None and after != before else None)
 
+    def round_packed(self, packed, counts, n_rows: int, watermark: Optional[int], more: bool = False):
+        """One round over the packed layout of arroyo_b200_partition_packed: a single all-to-all carries every
+        column.  Returns (batches, effective watermark or None, any sender has more rounds) where batches =
+        [([device pointer per column], rows)] -- one columnar batch per sender that sent rows.  The receive
+        buffer alternates between two allocations, so a batch stays valid until the round after next."""
+        torch, dist, W, nc = self.torch, self.dist, self.world, self.n_cols
+        if n_rows > 0:
+            self.ctrl[:W] = counts
+        else:
+            self.ctrl[:W] = 0
+        self.ctrl[W] = NO_WM if watermark is None else int(min(watermark, (1 << 63) - 1))
+        self.ctrl[W + 1] = 1 if more else 0
+        dist.all_gather_into_tensor(self.ctrl_all, self.ctrl)
+        m = self.ctrl_all.view(W, W + 2).cpu()
+        send_rows = m[self.rank, :W].tolist()
+        recv_rows = m[:, self.rank].tolist()
+        n_recv = int(sum(recv_rows))
+        if n_recv > self.max_recv_rows:
+            raise RuntimeError(f"shuffle receive buffer too small: {n_recv} > {self.max_recv_rows}")
+        if self._recv_packed is None:
+            self._recv_packed = [torch.empty(self.max_recv_rows * nc, dtype=torch.int64, device=self.device)
+                                 for _ in range(2)]
+        buf = self._recv_packed[self._flip]
+        self._flip ^= 1
+        o = buf[:n_recv * nc]
+        src = packed[:n_rows * nc] if n_rows > 0 else buf[:0]
+        dist.all_to_all_single(o, src, [nc * int(r) for r in recv_rows], [nc * int(r) for r in send_rows])
+        self.bytes_sent += 8 * nc * (n_rows - int(send_rows[self.rank]))
+        batches, off, base = [], 0, o.data_ptr()
+        for sdr in range(W):
+            r = int(recv_rows[sdr])
+            if r:
+                batches.append(([base + 8 * (off + c * r) for c in range(nc)], r))
+            off += nc * r
+        before = self.holder.last_present_watermark
+        for sdr in range(W):
+            wm = int(m[sdr, W])
+            if wm != NO_WM:
+                self.holder.set(sdr, wm)
+        after = self.holder.last_present_watermark
+        any_more = bool(m[:, W + 1].any())
+        return batches, (after if after is not None and after != before else None), any_more
+
 
 # ------------------------------------------------------------------------------------------------
 # N > 1 benchmark (called from bench.py under torchrun)
@@ -139,85 +206,146 @@ class _Ptr:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
 
 
-def _e2e_partials(args, torch, dist, B, ab, native, rank, world, local, device, gen_pane, part, ex):
+class PartialsPlan:
+    """partial -> shuffle -> final on one rank (the combiner plan).
+
+    local stage  : tumbling pre-aggregate of width = slide over this rank's shard, on its own CUDA stream;
+                   when the min-merged watermark passes a pane its partial rows (key, sum, count, _timestamp)
+                   leave as one device batch.
+    shuffle edge : arroyo_b200_partition_packed -> control all-gather -> one NCCL all-to-all.
+    owner stage  : sliding operator over partial rows (`partial_count_col`), on the caller's stream.
+
+    The two stages are separate operators of the dataflow: `close_panes` (local) returns the batches and the
+    watermark the owner stage must see, `owner_stage` consumes them in order.  Callers enqueue the local stage's
+    next input before running the owner stage, so the exchange and the owner's kernels overlap the local ingest."""
+
+    N_COLS = 4
+
+    def __init__(self, torch, dist, B, ab, native, args, rank, world, local, device, local_flags, owner_flags,
+                 raw_schema=None):
+        import pyarrow as pa
+        self.torch, self.dist, self.world = torch, dist, world
+        self.part_rows = 1 << 22
+        stream = torch.cuda.current_stream().cuda_stream
+        local_cfg = ab.WindowAggConfig(width=B.SLIDE, key_names=["key"],
+                                       aggs=[ab.Agg("sum", "value", "sum"), ab.Agg("count", None, "count")],
+                                       final_projection=False)
+        # stream=0: the operator creates its own non-blocking stream
+        self.local_op = native.TumblingAggregatingWindowFunc(local_cfg, input_schema=raw_schema, device=local, stream=0,
+                                                             flags=local_flags, expected_keys=args.keys,
+                                                             task_index=rank, parallelism=world)
+        owner_cfg = ab.WindowAggConfig(width=B.WIDTH, slide=B.SLIDE, key_names=["key"],
+                                       aggs=[ab.Agg("sum", "sum", "sum"), ab.Agg("avg", "sum", "avg"),
+                                             ab.Agg("count", None, "count")], window_index=1, partial_count_col="count")
+        p_schema = pa.schema([("key", pa.int64()), ("sum", pa.int64()), ("count", pa.int64()),
+                              ("_timestamp", pa.timestamp("ns"))])
+        self.owner_op = native.SlidingAggregatingWindowFunc(owner_cfg, input_schema=p_schema, device=local, stream=stream,
+                                                            flags=owner_flags,
+                                                            expected_keys=max(2 * args.keys // world, 1024),
+                                                            task_index=rank, parallelism=world)
+        self.part = DevicePartitioner(torch, world, self.N_COLS, 0, self.part_rows, local, stream)
+        self.ex = ShuffleExchange(torch, dist, rank, world, None, device, max_recv_rows=2 * self.part_rows,
+                                  n_cols=self.N_COLS)
+
+    def close_panes(self, watermark: Optional[int]):
+        """Local stage at a watermark point.  Every rank calls this the same number of times (ranks without a
+        new watermark pass None).  Returns (effective watermark or None, partial-row batches that left)."""
+        eff = self.ex.exchange_watermark(watermark)
+        if eff is None:
+            return None, []
+        chunks = []
+        for n, cols in self.local_op.handle_watermark_device(eff):
+            for o in range(0, n, self.part_rows):
+                chunks.append(([c + 8 * o for c in cols], min(self.part_rows, n - o)))
+        return eff, chunks
+
+    def owner_stage(self, eff: int, chunks, sink):
+        """Shuffle edge + owner stage for what `close_panes` returned; `sink(owner_op, eff)` emits."""
+        i = 0
+        while True:
+            if i < len(chunks):
+                cols, m = chunks[i]
+                packed, counts = self.part.pack(cols, m)
+            else:
+                packed, counts, m = None, None, 0
+            i += 1
+            batches, _, any_more = self.ex.round_packed(packed, counts, m, None, more=i < len(chunks))
+            if batches:
+                flat = (C.c_uint64 * (self.N_COLS * len(batches)))(*[p for cols, _ in batches for p in cols])
+                nr = (C.c_int64 * len(batches))(*[r for _, r in batches])
+                self.owner_op.process_device_batches(flat, nr, self.N_COLS)
+            if not any_more:
+                break
+            self.owner_op.flush()  # more rounds follow: the receive buffers come round again
+        sink(self.owner_op, eff)
+
+    def close(self):
+        self.owner_op.close()
+        self.local_op.close()
+        self.part.close()
+
+
+def _wm_point(wms, p, nb):
+    """(batch index inside pane p after which this rank reports to the watermark exchange, watermark or None):
+    the batch whose arrival made the WatermarkGenerator emit, else the pane's last batch."""
+    found = [(b, wms[p * nb + b]) for b in range(nb) if wms[p * nb + b] is not None]
+    if not found:
+        return nb - 1, None
+    return found[0][0], found[-1][1]
+
+
+def _e2e_partials(args, torch, dist, B, ab, native, rank, world, local, device, gen_pane):
     """End to end at N GPUs: every rank feeds its shard as pinned host Arrow batches through
     arroyo_b200_op_process_batch (host -> device copies inside the timed region), partial aggregates cross the
     all-to-all, and each rank reads the windows of its keys back as host Arrow batches."""
     import time
 
-    import pyarrow as pa
     rows = args.rows_per_pane
     nb = rows // B.BATCH_ROWS
     K = args.e2e_steps or min(args.steps, 6)
     W = 13
     batches, wms, _keep = B.host_feed(torch, gen_pane, range(W + K), rows)
-    stream = torch.cuda.current_stream().cuda_stream
-    local_cfg = ab.WindowAggConfig(width=B.SLIDE, key_names=["key"],
-                                   aggs=[ab.Agg("sum", "value", "sum"), ab.Agg("count", None, "count")],
-                                   final_projection=False)
-    local_op = native.TumblingAggregatingWindowFunc(local_cfg, device=local, stream=stream, flags=B.op_flags(args),
-                                                    expected_keys=args.keys, task_index=rank, parallelism=world)
-    owner_cfg = ab.WindowAggConfig(width=B.WIDTH, slide=B.SLIDE, key_names=["key"],
-                                   aggs=[ab.Agg("sum", "sum", "sum"), ab.Agg("avg", "sum", "avg"),
-                                         ab.Agg("count", None, "count")], window_index=1, partial_count_col="count")
-    p_schema = pa.schema([("key", pa.int64()), ("sum", pa.int64()), ("count", pa.int64()), ("_timestamp", pa.timestamp("ns"))])
-    owner_op = native.SlidingAggregatingWindowFunc(owner_cfg, input_schema=p_schema, device=local, stream=stream,
-                                                   flags=B.op_flags(args), expected_keys=max(2 * args.keys // world, 1024),
-                                                   task_index=rank, parallelism=world)
-    ex.holder = type(ex.holder)(world)  # fresh watermark state for this pass
+    plan = PartialsPlan(torch, dist, B, ab, native, args, rank, world, local, device, B.op_flags(args), B.op_flags(args))
     lctx, octx, col = ab.OperatorContext(1), ab.OperatorContext(1), ab.Collector()
-    empty_cols = [torch.empty(0, dtype=torch.int64, device=device) for _ in range(4)]
-    part_rows = part.out[0].numel()
     d2h = 0
 
-    def step(p):
+    def sink(owner_op, eff):
         nonlocal d2h
-        for b in range(nb):
-            local_op.process_batch(batches[p][b], lctx, col)
-            wm = wms[p * nb + b]
-            if wm is None:
-                continue
-            eff = ex.exchange_watermark(wm)
-            if eff is None:
-                continue
-            chunks = []
-            for n, cols in local_op.handle_watermark_device(eff):
-                for o in range(0, n, part_rows):
-                    m = min(part_rows, n - o)
-                    chunks.append(([torch.as_tensor(_Ptr(c + 8 * o, m), device=device) for c in cols], m))
-            n_rounds = torch.tensor([len(chunks)], dtype=torch.int64, device=device)
-            dist.all_reduce(n_rounds, op=dist.ReduceOp.MAX)
-            for r in range(int(n_rounds.item())):
-                tc, m = chunks[r] if r < len(chunks) else (empty_cols, 0)
-                rc, n_recv, _ = ex.round(tc, m, None)
-                if n_recv:
-                    owner_op.process_device_batch([c.data_ptr() for c in rc], n_recv)
-                    owner_op.flush()
-            octx.watermarks.set(0, eff)
-            owner_op.handle_watermark(eff, octx, col)
-            for rb in col.batches:
-                d2h += rb.num_rows * 48
-            col.batches.clear()
+        octx.watermarks.set(0, eff)
+        owner_op.handle_watermark(eff, octx, col)
+        for rb in col.batches:
+            d2h += rb.num_rows * 48
+        col.batches.clear()
+
+    def step(p):
+        b0, wm = _wm_point(wms, p, nb)
+        for b in range(b0 + 1):
+            plan.local_op.process_batch(batches[p][b], lctx, col)
+        eff, chunks = plan.close_panes(wm)
+        for b in range(b0 + 1, nb):
+            plan.local_op.process_batch(batches[p][b], lctx, col)
+        if eff is not None:
+            plan.owner_stage(eff, chunks, sink)
 
     for p in range(W):
         step(p)
-    owner_op.flush()
+    plan.owner_op.flush()
+    plan.local_op.flush()
     torch.cuda.synchronize()
     dist.barrier()
     d2h = 0
     t0 = time.perf_counter()
     for p in range(W, W + K):
         step(p)
-    owner_op.flush()
-    local_op.flush()
+    plan.owner_op.flush()
+    plan.local_op.flush()
     torch.cuda.synchronize()
     dist.barrier()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     tot = torch.tensor([d2h], dtype=torch.int64, device=device)
     dist.all_reduce(tot)
-    owner_op.close()
-    local_op.close()
+    plan.close()
     dt = float(dt.item())
     return {"value": world * K * rows / dt, "unit": "rows/s", "h2d_bytes_per_step": world * rows * 24,
             "d2h_bytes_per_step": int(tot.item()) // max(K, 1), "steps": K, "ms_per_step": 1e3 * dt / K,
@@ -247,7 +375,7 @@ def bench(args, torch, dist, rank, world, local):
     W, K = max(args.warmup, 3), args.steps
     rows = args.rows_per_pane
     nb = rows // B.BATCH_ROWS
-    gen_pane = B.make_generator(torch, device, rows, args.keys, args.dist, 42 + rank)
+    gen_pane = B.make_generator(torch, device, rows, args.keys, args.dist, 42 + rank, args.keyspace)
     panes = [gen_pane(p) for p in range(W + K)]
     mins, maxs = [], []
     for (_, _, t) in panes:
@@ -263,23 +391,11 @@ def bench(args, torch, dist, rank, world, local):
     mode = args.shuffle
     flags = ffi.FLAG_PROFILE | B.op_flags(args)
     raw_schema = pa.schema([("key", pa.int64()), ("value", pa.int64()), ("_timestamp", pa.timestamp("ns"))])
+    plan = part = ex = None
     if mode == "partials":
-        part_rows = 1 << 22
-        local_cfg = ab.WindowAggConfig(width=B.SLIDE, key_names=["key"],
-                                       aggs=[ab.Agg("sum", "value", "sum"), ab.Agg("count", None, "count")],
-                                       final_projection=False)
-        local_op = native.TumblingAggregatingWindowFunc(local_cfg, input_schema=raw_schema, device=local, stream=stream,
-                                                        flags=flags, expected_keys=args.keys, task_index=rank,
-                                                        parallelism=world)
-        owner_cfg = ab.WindowAggConfig(width=B.WIDTH, slide=B.SLIDE, key_names=["key"],
-                                       aggs=[ab.Agg("sum", "sum", "sum"), ab.Agg("avg", "sum", "avg"),
-                                             ab.Agg("count", None, "count")], window_index=1, partial_count_col="count")
-        p_schema = pa.schema([("key", pa.int64()), ("sum", pa.int64()), ("count", pa.int64()),
-                              ("_timestamp", pa.timestamp("ns"))])
-        owner_op = native.SlidingAggregatingWindowFunc(owner_cfg, input_schema=p_schema, device=local, stream=stream,
-                                                       flags=B.op_flags(args), expected_keys=max(2 * args.keys // world, 1024),
-                                                       task_index=rank, parallelism=world)
-        n_cols = 4
+        plan = PartialsPlan(torch, dist, B, ab, native, args, rank, world, local, device, flags, B.op_flags(args),
+                            raw_schema=raw_schema)
+        local_op, owner_op, ex = plan.local_op, plan.owner_op, plan.ex
     else:
         part_rows = 64 * B.BATCH_ROWS
         local_op = None
@@ -287,11 +403,9 @@ def bench(args, torch, dist, rank, world, local):
                                                        stream=stream, flags=flags,
                                                        expected_keys=max(2 * args.keys // world, 1024), task_index=rank,
                                                        parallelism=world)
-        n_cols = 3
-    part = DevicePartitioner(torch, world, n_cols, 0, part_rows, local, stream)
-    ex = ShuffleExchange(torch, dist, rank, world, part, device, max_recv_rows=2 * part_rows, n_cols=n_cols)
+        part = DevicePartitioner(torch, world, 3, 0, part_rows, local, stream)
+        ex = ShuffleExchange(torch, dist, rank, world, part, device, max_recv_rows=2 * part_rows, n_cols=3)
     rows_out = 0
-    empty_cols = [torch.empty(0, dtype=torch.int64, device=device) for _ in range(n_cols)]
 
     def emit(eff):
         nonlocal rows_out
@@ -300,35 +414,17 @@ def bench(args, torch, dist, rank, world, local):
 
     def step_partials(p):
         k, v, t = panes[p]
-        start = 0
-        for b in range(nb):
-            wm = wms[p * nb + b]
-            if wm is None and b != nb - 1:
-                continue
-            s, e = start * B.BATCH_ROWS, (b + 1) * B.BATCH_ROWS
-            local_op.process_device_batch([k.data_ptr() + 8 * s, v.data_ptr() + 8 * s, t.data_ptr() + 8 * s], e - s)
-            start = b + 1
-            if wm is None:
-                continue
-            eff = ex.exchange_watermark(wm)
-            if eff is None:
-                continue
-            # panes that can no longer receive rows leave the local stage as partial rows; every rank takes
-            # part in the same number of exchange rounds (ranks with nothing left send empty segments)
-            chunks = []
-            for n, cols in local_op.handle_watermark_device(eff):
-                for o in range(0, n, part_rows):
-                    m = min(part_rows, n - o)
-                    chunks.append(([torch.as_tensor(_Ptr(c + 8 * o, m), device=device) for c in cols], m))
-            n_rounds = torch.tensor([len(chunks)], dtype=torch.int64, device=device)
-            dist.all_reduce(n_rounds, op=dist.ReduceOp.MAX)
-            for r in range(int(n_rounds.item())):
-                tc, m = chunks[r] if r < len(chunks) else (empty_cols, 0)
-                rc, n_recv, _ = ex.round(tc, m, None)
-                if n_recv:
-                    owner_op.process_device_batch([c.data_ptr() for c in rc], n_recv)
-                    owner_op.flush()  # receive buffers are reused
-            emit(eff)
+        b0, wm = _wm_point(wms, p, nb)
+        e = (b0 + 1) * B.BATCH_ROWS
+        local_op.process_device_batch([k.data_ptr(), v.data_ptr(), t.data_ptr()], e)
+        eff, chunks = plan.close_panes(wm)
+        if e < rows:
+            # the rest of this pane's input is enqueued on the local stage's stream before the owner stage runs,
+            # so the exchange and the owner's kernels overlap it
+            local_op.process_device_batch([k.data_ptr() + 8 * e, v.data_ptr() + 8 * e, t.data_ptr() + 8 * e], rows - e)
+            local_op.submit()
+        if eff is not None:
+            plan.owner_stage(eff, chunks, lambda op, w: emit(w))
 
     def step_rows(p):
         k, v, t = panes[p]
@@ -383,13 +479,14 @@ def bench(args, torch, dist, rank, world, local):
     tot = torch.tensor([launches, rows_out, d["rows_in"]], dtype=torch.int64, device=device)
     dist.all_reduce(tot)
     sent = ex.bytes_sent - sent0
-    owner_op.close()
-    if local_op is not None:
-        local_op.close()
+    if plan is not None:
+        plan.close()
+    else:
+        owner_op.close()
+        part.close()
     e2e = None
     if mode == "partials" and not args.skip_e2e:
-        e2e = _e2e_partials(args, torch, dist, B, ab, native, rank, world, local, device, gen_pane, part, ex)
-    part.close()
+        e2e = _e2e_partials(args, torch, dist, B, ab, native, rank, world, local, device, gen_pane)
     if rank == 0:
         peak, peak_kind = B.measured_peak()
         ingest_gbs = 24.0 * d["ingest_rows_timed"] / (d["ingest_ms"] * 1e-3) / 1e9 if d["ingest_ms"] else None

@@ -95,6 +95,11 @@ class _NativeOperator:
     def flush(self):
         _check(self._lib, self._h, self._lib.arroyo_b200_op_flush(self._h))
 
+    def submit(self):
+        """Enqueue the rows accepted so far without waiting (arroyo_b200_op_submit)."""
+        if self.created:
+            _check(self._lib, self._h, self._lib.arroyo_b200_op_submit(self._h))
+
     def stats(self) -> dict:
         s = ffi.Stats()
         _check(self._lib, self._h, self._lib.arroyo_b200_op_stats(self._h, C.byref(s)))

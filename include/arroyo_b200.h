@@ -173,6 +173,8 @@ typedef struct ArroyoB200OpConfig {
                                           /* instead of staging them with the copy engine */
 #define ARROYO_B200_FLAG_NO_COMBINE 16u   /* do not warp-combine equal keys before the     */
                                           /* atomics (measurement knob)                    */
+#define ARROYO_B200_FLAG_NO_DIRECT 64u    /* never map a dense key range straight onto ids */
+                                          /* (every key goes through the hash dictionary)  */
 
 typedef struct ArroyoB200Op ArroyoB200Op;
 
@@ -299,6 +301,12 @@ int32_t arroyo_b200_op_on_close(ArroyoB200Op* op, int32_t end_of_data, ArroyoB20
  * have been released. */
 int32_t arroyo_b200_op_flush(ArroyoB200Op* op);
 
+/* The operators batch input rows into launches of 2^reserved rows.  `submit` enqueues the rows
+ * accepted so far without waiting for them (no reference counterpart: the reference's operators
+ * run each batch to completion inside process_batch).  A host that knows its input queue is
+ * empty calls it so that the device works while the host is idle. */
+int32_t arroyo_b200_op_submit(ArroyoB200Op* op);
+
 void arroyo_b200_release_batches(ArroyoB200Batches* batches);
 
 int32_t arroyo_b200_op_stats(ArroyoB200Op* op, ArroyoB200Stats* out);
@@ -316,6 +324,12 @@ int32_t arroyo_b200_partitioner_create(int32_t device, uint64_t stream, int32_t 
 void arroyo_b200_partitioner_destroy(ArroyoB200Partitioner* p);
 int32_t arroyo_b200_partition(ArroyoB200Partitioner* p, const uint64_t* in_cols, int64_t n_rows,
                               const uint64_t* out_cols, uint64_t counts_dev, uint64_t offsets_dev);
+/* Same bucketing, one output buffer (`packed_dev`, n_rows * n_cols int64): destination d owns the
+ * element range [n_cols * offsets[d], n_cols * (offsets[d] + counts[d])), holding its n_cols columns
+ * back to back (counts[d] values each).  One all-to-all with element splits n_cols * counts then
+ * carries every column of the edge; the receiver reads each sender's block as a columnar batch. */
+int32_t arroyo_b200_partition_packed(ArroyoB200Partitioner* p, const uint64_t* in_cols, int64_t n_rows,
+                                     uint64_t packed_dev, uint64_t counts_dev, uint64_t offsets_dev);
 /* WatermarkGenerator::process_batch's reductions (arroyo-worker/src/arrow/watermark_generator.rs:160,176:
  * kernels::aggregate::max / min over the timestamp column) for a device-resident batch. Synchronous. */
 int32_t arroyo_b200_ts_minmax(int32_t device, uint64_t stream, uint64_t ts_dev, int64_t n_rows, int64_t* out_min,

@@ -205,6 +205,38 @@ def test_dictionary_growth_and_far_future_rows(G):
     assert st["rows_deferred"] > 0 and st["n_keys"] >= 50_000
 
 
+@pytest.mark.parametrize("direct", [True, False])
+def test_dense_key_range_is_direct_mapped_and_outsiders_still_hash(G, direct):
+    """Nexmark-shaped dense ids (1000 + n): the first rows' key range is mapped straight onto dense ids; keys
+    that show up later outside that range -- just below, just above, far away, the dictionary's empty
+    sentinel -- go through the hash dictionary.  Same results either way, and with the feature disabled."""
+    from arroyo_b200 import ffi
+    rng = np.random.default_rng(77)
+    batches = gen_stream(rng, 120_000, 10, rate_per_s=20_000, batch=4096)
+    out = []
+    outsiders = np.array([999, 2024, 2100, -5, 10**15, -2**63, 2**63 - 1], dtype=np.int64)
+    for i, b in enumerate(batches):
+        n = b.num_rows
+        key = 1000 + rng.integers(0, 1000, n, dtype=np.int64)
+        key[0], key[1] = 1000, 1999  # every batch spans the whole dense range
+        if i >= 2:
+            key[:: 11] = outsiders[rng.integers(0, len(outsiders), len(key[:: 11]))]
+            key[1:: 97] = 2023  # inside the rounded-up direct range, never seen in the first rows
+        out.append(O.Batch({"key": key, "value": b["value"], O.TIMESTAMP: b[O.TIMESTAMP]}))
+    flags = 0 if direct else ffi.FLAG_NO_DIRECT
+    for cfg, mk_o, mk_g, fc in (
+            (O.WindowAggConfig(width=4 * S, slide=S, key_names=["key"], aggs=SUM_AVG, window_index=1),
+             O.SlidingAggregatingWindowFunc, G.SlidingAggregatingWindowFunc, ("avg",)),
+            (O.WindowAggConfig(width=2 * S, key_names=["key"], window_index=1,
+                               aggs=[O.Agg("min", "value", "mn"), O.Agg("max", "value", "mx"), O.Agg("count", None, "n")]),
+             O.TumblingAggregatingWindowFunc, G.TumblingAggregatingWindowFunc, ())):
+        want, got, gop = run_both(G, lambda: mk_o(cfg), lambda: mk_g(cfg, flags=flags), out)
+        assert_same(want, got, float_cols=fc)
+        n_ids = gop.stats()["n_keys"]
+        # 1000 dense keys + 7 outsiders; the direct range reserves ids for [1000, 1000 + 1024)
+        assert n_ids == (1024 + 6 if direct else 1007), n_ids
+
+
 def test_unsupported_inputs_fail_loudly(G):
     import pyarrow as pa
     from arroyo_b200 import ffi, operators as native
@@ -498,6 +530,19 @@ def test_device_partitioner_matches_repartition(G, n_dest):
         for d in range(n_dest):
             c = int(counts[d])
             got = sorted(zip(*(o[off:off + c].cpu().numpy().tolist() for o in out)))
+            exp = sorted(zip(want[d]["key"].tolist(), want[d]["value"].tolist(), want[d][O.TIMESTAMP].tolist())) if d in want else []
+            assert got == exp
+            off += c
+        # packed layout: destination d's block = its three columns back to back
+        packed, counts2 = part.pack([c.data_ptr() for c in cols], n)
+        torch.cuda.synchronize()
+        assert counts2.cpu().numpy().tolist() == counts.tolist()
+        flat = packed.cpu().numpy()
+        off = 0
+        for d in range(n_dest):
+            c = int(counts[d])
+            blk = flat[3 * off:3 * (off + c)].reshape(3, c)
+            got = sorted(zip(*(blk[j].tolist() for j in range(3))))
             exp = sorted(zip(want[d]["key"].tolist(), want[d]["value"].tolist(), want[d][O.TIMESTAMP].tolist())) if d in want else []
             assert got == exp
             off += c

@@ -123,6 +123,94 @@ def worker(rank, port, outdir):
     dist.destroy_process_group()
 
 
+def np_pack(batch, names):
+    """arroyo_b200_partition_packed restated with the oracle's partition function: destination d's block holds
+    its columns back to back."""
+    counts = np.zeros(WORLD, dtype=np.int64)
+    parts = {d: sb for d, sb in O.repartition(batch, ["key"], WORLD)}
+    blocks = []
+    for d in range(WORLD):
+        if d in parts:
+            counts[d] = parts[d].num_rows
+            blocks += [np.ascontiguousarray(parts[d][c]).astype(np.int64) for c in names]
+    flat = np.concatenate(blocks) if blocks else np.empty(0, dtype=np.int64)
+    return torch.from_numpy(flat), torch.from_numpy(counts)
+
+
+def read_ptr(ptr, n):
+    import ctypes
+    return np.ctypeslib.as_array((ctypes.c_int64 * n).from_address(ptr)).copy() if n else np.empty(0, dtype=np.int64)
+
+
+def combiner_worker(rank, port, outdir):
+    """partial -> shuffle -> final (SURVEY 8(e) combiner) over ShuffleExchange.round_packed: the local stage is a
+    tumbling pre-aggregate of width = slide whose late filter follows the min-merged watermark, the owner merges
+    partial rows (SUM of sums, SUM of counts)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(WORLD))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    from arroyo_b200.multi_gpu import ShuffleExchange
+    names = ("key", "sum", "n", O.TIMESTAMP)
+    ex = ShuffleExchange(torch, dist, rank, WORLD, None, torch.device("cpu"), max_recv_rows=1 << 16, n_cols=4)
+    batches = shard(rank)
+    gen = O.WatermarkGenerator()
+    local = O.TumblingAggregatingWindowFunc(O.WindowAggConfig(width=S, key_names=["key"], aggs=[O.Agg("sum", "value", "sum"), O.Agg("count", None, "n")], final_projection=False))
+    owner = O.SlidingAggregatingWindowFunc(O.WindowAggConfig(width=3 * S, slide=S, key_names=["key"], aggs=[O.Agg("sum", "sum", "sum"), O.Agg("sum", "n", "n")], window_index=1))
+    lctx, octx = O.OperatorContext(1), O.OperatorContext(1)
+    lout, out = O.Collector(), O.Collector()
+    n_rounds = torch.tensor([len(batches)])
+    dist.all_reduce(n_rounds, op=dist.ReduceOp.MAX)
+    multi_round_seen = 0
+    for i in range(int(n_rounds) + 1):
+        wm = None
+        if i < len(batches):
+            local.process_batch(batches[i], lctx, lout)
+            wm = gen.process_batch(batches[i][O.TIMESTAMP])
+        elif i == int(n_rounds):
+            wm = O.FINAL_WATERMARK
+        eff = ex.exchange_watermark(wm)
+        if eff is None:
+            continue
+        lctx.watermarks.set(0, eff)
+        local.handle_watermark(eff, lctx, lout)
+        chunks, lout.batches = list(lout.batches), []
+        multi_round_seen += len(chunks) > 1
+        j = 0
+        while True:
+            if j < len(chunks):
+                packed, counts = np_pack(chunks[j], names)
+                m = chunks[j].num_rows
+            else:
+                packed, counts, m = None, None, 0
+            j += 1
+            got, _, any_more = ex.round_packed(packed, counts, m, None, more=j < len(chunks))
+            for cols, r in got:
+                owner.process_batch(O.Batch({c: read_ptr(ptr, r) for c, ptr in zip(names, cols)}), octx, out)
+            if not any_more:
+                break
+        octx.watermarks.set(0, eff)
+        owner.handle_watermark(eff, octx, out)
+    rows = []
+    for b in out.batches:
+        rows += b.rows()
+    with open(os.path.join(outdir, f"rank{rank}.json"), "w") as f:
+        json.dump({"rows": rows, "multi": int(multi_round_seen)}, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_combiner_plan_world2_gloo_matches_direct_topology():
+    want = expected()
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(combiner_worker, args=(30533 + os.getpid() % 1000, d), nprocs=WORLD, join=True)
+        got, multi = [], 0
+        for r in range(WORLD):
+            o = json.load(open(os.path.join(d, f"rank{r}.json")))
+            got += o["rows"]
+            multi += o["multi"]
+    assert multiset(got) == multiset(want)
+    assert multi > 0  # the final watermark closes several panes at once: the multi-round path ran
+
+
 def test_shuffle_exchange_world2_gloo_matches_topology_simulation():
     want = expected()
     assert len(want) > 1000
