@@ -60,8 +60,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(f"--- nvcc {s} ---\n{out}\n")
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart"]
+    tmp = LIB + ".tmp"  # link beside the target, then rename: a reader never sees a half-written library
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp, *objs, "-lcudart"]
     subprocess.check_call(cmd)
+    os.replace(tmp, LIB)
     return LIB
 
 
