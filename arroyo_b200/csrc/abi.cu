@@ -189,6 +189,44 @@ int32_t arroyo_b200_op_handle_watermark(ArroyoB200Op* op, int64_t watermark_ns, 
   });
 }
 
+int32_t arroyo_b200_op_handle_watermark_begin(ArroyoB200Op* op, int64_t watermark_ns) {
+  if (!op) return ARROYO_B200_INVALID_ARGUMENT;
+  WallTimer wt(op->host_watermark_ms);
+  return guarded(op, [&](OpBase* o) {
+    AB_REQUIRE(o->pending_out == nullptr, ARROYO_B200_INVALID_ARGUMENT,
+               "the previous emission has not been collected (handle_watermark_poll)");
+    o->pending_out = new BatchesPriv();
+    try {
+      o->begin_watermark(watermark_ns);
+    } catch (...) {
+      o->poll_watermark(true);
+      ArroyoB200Batches tmp{};
+      batches_finish(o->pending_out, &tmp);
+      batches_release(&tmp);
+      o->pending_out = nullptr;
+      throw;
+    }
+  });
+}
+
+int32_t arroyo_b200_op_handle_watermark_poll(ArroyoB200Op* op, int32_t block, ArroyoB200Batches* out, int32_t* ready) {
+  if (out) memset(out, 0, sizeof *out);
+  if (ready) *ready = 0;
+  if (!op) return ARROYO_B200_INVALID_ARGUMENT;
+  WallTimer wt(op->host_watermark_ms);
+  return guarded(op, [&](OpBase* o) {
+    AB_REQUIRE(out != nullptr && ready != nullptr, ARROYO_B200_INVALID_ARGUMENT, "null out");
+    if (!o->pending_out) {
+      *ready = 1;  // nothing outstanding: an empty list
+      return;
+    }
+    if (!o->poll_watermark(block != 0)) return;
+    batches_finish(o->pending_out, out);
+    o->pending_out = nullptr;
+    *ready = 1;
+  });
+}
+
 int32_t arroyo_b200_op_handle_watermark_device(ArroyoB200Op* op, int64_t watermark_ns, ArroyoB200DeviceBatch* out,
                                                int64_t max_out, int64_t* n_out) {
   if (n_out) *n_out = 0;

@@ -28,6 +28,12 @@ class OpBase {
   virtual void flush() = 0;
   // enqueue whatever input is still being batched on the host side; does not wait
   virtual void submit() {}
+  // handle_watermark split in two, the way the reference's operators hand long-running work to
+  // ArrowOperator::future_to_poll / handle_future_result (operator.rs:1190-1204): `begin` enqueues the emission and
+  // the device->host copies of its windows into `pending_out`, `poll` says whether those copies have completed.
+  BatchesPriv* pending_out = nullptr;
+  virtual void begin_watermark(int64_t watermark) { handle_watermark(watermark, pending_out, nullptr); }
+  virtual bool poll_watermark(bool /*block*/) { return true; }
   virtual void stats(ArroyoB200Stats* out) = 0;
 };
 

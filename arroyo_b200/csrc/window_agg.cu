@@ -827,6 +827,8 @@ class WindowAggOp final : public OpBase {
   void on_close(int, BatchesPriv*) override { flush(); }
   void flush() override;
   void submit() override;
+  void begin_watermark(int64_t wm) override;
+  bool poll_watermark(bool block) override;
   void stats(ArroyoB200Stats* out) override;
 
  private:
@@ -868,6 +870,12 @@ class WindowAggOp final : public OpBase {
   DevBuf slots_, id_keys_, counters_, slot_rows_;
   uint32_t n_keys_host_ = 1;
   // direct-mapped key range (dict.cuh): decided once, from the first rows, before any id exists
+  // asynchronous emission (begin_watermark / poll_watermark): windows are copied back on a second stream so the
+  // device->host traffic overlaps the host->device traffic of the batches that follow
+  cudaStream_t out_stream_ = nullptr;
+  cudaEvent_t emit_done_ = nullptr, out_done_ = nullptr;
+  bool async_out_ = false, out_inflight_ = false;
+  void wait_outputs();
   bool direct_decided_ = false;
   long long direct_base_ = 0;
   uint32_t direct_n_ = 0;
@@ -1151,6 +1159,12 @@ WindowAggOp::~WindowAggOp() {
   for (auto& e : emit_events_) {
     cudaEventDestroy(e.first);
     cudaEventDestroy(e.second);
+  }
+  if (out_stream_) {
+    cudaStreamSynchronize(out_stream_);
+    cudaStreamDestroy(out_stream_);
+    cudaEventDestroy(emit_done_);
+    cudaEventDestroy(out_done_);
   }
   if (own_stream_ && stream_) cudaStreamDestroy(stream_);
 }
@@ -1895,6 +1909,44 @@ void WindowAggOp::submit() {
   launch_pending();
 }
 
+// The output buffers of the previous emission may still be in flight to the host.
+void WindowAggOp::wait_outputs() {
+  if (!out_inflight_) return;
+  AB_CUDA(cudaEventSynchronize(out_done_));
+  out_inflight_ = false;
+}
+
+void WindowAggOp::begin_watermark(int64_t wm) {
+  set_device();
+  if (!out_stream_) {
+    AB_CUDA(cudaStreamCreateWithFlags(&out_stream_, cudaStreamNonBlocking));
+    AB_CUDA(cudaEventCreateWithFlags(&emit_done_, cudaEventDisableTiming));
+    AB_CUDA(cudaEventCreateWithFlags(&out_done_, cudaEventDisableTiming));
+  }
+  struct Flag {
+    bool& f;
+    explicit Flag(bool& x) : f(x) { f = true; }
+    ~Flag() { f = false; }
+  } flag(async_out_);
+  handle_watermark(wm, pending_out, nullptr);
+  AB_CUDA(cudaEventRecord(out_done_, out_stream_));
+  out_inflight_ = true;
+}
+
+bool WindowAggOp::poll_watermark(bool block) {
+  if (!out_inflight_) return true;
+  set_device();
+  if (block) {
+    wait_outputs();
+    return true;
+  }
+  cudaError_t e = cudaEventQuery(out_done_);
+  if (e == cudaErrorNotReady) return false;
+  AB_CUDA(e);
+  out_inflight_ = false;
+  return true;
+}
+
 WindowAggOp::OutSet* WindowAggOp::out_set(size_t i, uint64_t cap) {
   while (out_sets_.size() <= i) out_sets_.emplace_back(new OutSet());
   OutSet* os = out_sets_[i].get();
@@ -2013,19 +2065,26 @@ static void* d2h_column(const void* dev, int64_t n, cudaStream_t s, uint64_t* by
 // Output batch in the operator's out_schema order: aggregate output columns [key?, aggs...] with the
 // window struct inserted at window_index, then _timestamp (planner extension/aggregate.rs:306-389).
 void WindowAggOp::export_window(OutSet* os, int64_t n, BatchesPriv* out_host) {
+  cudaStream_t cs = stream_;
+  if (async_out_) {
+    // the copies run behind everything the emission enqueued on the compute stream
+    AB_CUDA(cudaEventRecord(emit_done_, stream_));
+    AB_CUDA(cudaStreamWaitEvent(out_stream_, emit_done_, 0));
+    cs = out_stream_;
+  }
   std::vector<OutColumn> cols;
   if (keyed_) {
     OutColumn k;
     k.name = "key";
     k.format = key_format_;
-    k.data = d2h_column(os->key.p, n, stream_, &st_.d2h_bytes);
+    k.data = d2h_column(os->key.p, n, cs, &st_.d2h_bytes);
     cols.push_back(k);
   }
   for (int g = 0; g < n_aggs_; ++g) {
     OutColumn a;
     a.name = "agg" + std::to_string(g);
     a.format = agg_format_[g];
-    a.data = d2h_column(os->agg[g].p, n, stream_, &st_.d2h_bytes);
+    a.data = d2h_column(os->agg[g].p, n, cs, &st_.d2h_bytes);
     cols.push_back(a);
   }
   if (cfg.final_projection) {
@@ -2035,10 +2094,10 @@ void WindowAggOp::export_window(OutSet* os, int64_t n, BatchesPriv* out_host) {
     OutColumn ws, we;
     ws.name = "start";
     ws.format = "tsn:";
-    ws.data = d2h_column(os->wstart.p, n, stream_, &st_.d2h_bytes);
+    ws.data = d2h_column(os->wstart.p, n, cs, &st_.d2h_bytes);
     we.name = "end";
     we.format = "tsn:";
-    we.data = d2h_column(os->wend.p, n, stream_, &st_.d2h_bytes);
+    we.data = d2h_column(os->wend.p, n, cs, &st_.d2h_bytes);
     w.children = {ws, we};
     int wi = std::min<int>(std::max<int>(cfg.window_index, 0), (int)cols.size());
     cols.insert(cols.begin() + wi, w);
@@ -2046,9 +2105,9 @@ void WindowAggOp::export_window(OutSet* os, int64_t n, BatchesPriv* out_host) {
   OutColumn t;
   t.name = "_timestamp";
   t.format = "tsn:";
-  t.data = d2h_column(os->ts.p, n, stream_, &st_.d2h_bytes);
+  t.data = d2h_column(os->ts.p, n, cs, &st_.d2h_bytes);
   cols.push_back(t);
-  AB_CUDA(cudaStreamSynchronize(stream_));
+  if (!async_out_) AB_CUDA(cudaStreamSynchronize(stream_));
   out_host->arrays.emplace_back();
   out_host->schemas.emplace_back();
   export_batch(cols, n, &out_host->arrays.back(), &out_host->schemas.back());
@@ -2188,6 +2247,7 @@ void WindowAggOp::emit_window(int64_t a, int64_t b, size_t out_index, BatchesPri
 
 void WindowAggOp::handle_watermark(int64_t wm, BatchesPriv* out_host, std::vector<ArroyoB200DeviceBatch>* out_dev) {
   set_device();
+  wait_outputs();
   launch_pending();
   sync_all();
   poll_releases(false);
@@ -2264,6 +2324,7 @@ void WindowAggOp::handle_watermark(int64_t wm, BatchesPriv* out_host, std::vecto
 
 void WindowAggOp::handle_checkpoint(int64_t wm, BatchesPriv* out) {
   set_device();
+  wait_outputs();
   launch_pending();
   sync_all();
   std::vector<PlanStep> steps;

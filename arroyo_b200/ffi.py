@@ -106,6 +106,8 @@ SYMBOLS = [
     ("arroyo_b200_op_process_device_batches", C.c_int32, [_VP, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64),
                                                           C.c_int32, C.POINTER(C.c_int64), C.c_int64]),
     ("arroyo_b200_op_handle_watermark", C.c_int32, [_VP, C.c_int64, C.POINTER(Batches)]),
+    ("arroyo_b200_op_handle_watermark_begin", C.c_int32, [_VP, C.c_int64]),
+    ("arroyo_b200_op_handle_watermark_poll", C.c_int32, [_VP, C.c_int32, C.POINTER(Batches), C.POINTER(C.c_int32)]),
     ("arroyo_b200_op_handle_watermark_device", C.c_int32, [_VP, C.c_int64, C.POINTER(DeviceBatch), C.c_int64,
                                                            C.POINTER(C.c_int64)]),
     ("arroyo_b200_op_handle_checkpoint", C.c_int32, [_VP, C.c_int64, C.POINTER(Batches)]),

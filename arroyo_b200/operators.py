@@ -222,6 +222,29 @@ class _WindowAggregate(_NativeOperator):
             collector.collect(pa.RecordBatch.from_arrays(b.columns, names=names))
         return watermark
 
+    def handle_watermark_begin(self, watermark, ctx: OperatorContext) -> bool:
+        """First half of handle_watermark (arroyo_b200_op_handle_watermark_begin): the emitted windows start their
+        way to the host on a second stream.  Returns False when there was nothing to do (no watermark yet)."""
+        wm = ctx.last_present_watermark()
+        if wm is None or not self.created:
+            return False
+        _check(self._lib, self._h, self._lib.arroyo_b200_op_handle_watermark_begin(self._h, clamp_watermark(wm)))
+        return True
+
+    def handle_watermark_poll(self, collector: Collector, block: bool = True) -> bool:
+        """Second half: collects the windows once their copies have completed (the future_to_poll /
+        handle_future_result pair of the reference's operators).  Returns False while they are still in flight."""
+        out = ffi.Batches()
+        ready = C.c_int32(0)
+        st = self._lib.arroyo_b200_op_handle_watermark_poll(self._h, 1 if block else 0, C.byref(out), C.byref(ready))
+        _check(self._lib, self._h, st)
+        if not ready.value:
+            return False
+        names = self.output_names()
+        for b in import_batches(self._lib, out):
+            collector.collect(pa.RecordBatch.from_arrays(b.columns, names=names))
+        return True
+
     def handle_watermark_device(self, wm: int, max_out: int = 64):
         """Emission left on the device: list of (n_rows, [device pointers])."""
         out = (ffi.DeviceBatch * max_out)()

@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--keyspace", default="scattered", choices=["scattered", "dense"],
                     help="scattered: key ids multiplied by an odd 64-bit constant (every key is hashed); "
                          "dense: Nexmark-shaped ids 1000 + n (the operator maps the range straight onto dense ids)")
+    ap.add_argument("--sync-emit", action="store_true",
+                    help="e2e: blocking arroyo_b200_op_handle_watermark instead of the begin / poll pair")
     ap.add_argument("--no-direct", action="store_true", help="measurement knob: hash dense keys as well")
     ap.add_argument("--shuffle", default="partials", choices=["partials", "rows"],
                     help="N>1: what crosses the all-to-all (per-pane partial aggregates, or raw rows)")
@@ -465,34 +467,56 @@ def run_e2e(args, torch, device, local, gen_pane):
     ctx = ab.OperatorContext(1)
     col = ab.Collector()
     d2h = 0
+    outstanding = False  # an emission whose windows are still on their way to the host
+
+    def collect(block):
+        """The shim's handle_future_result: take the windows of the outstanding emission (then it would forward the
+        watermark it held back)."""
+        nonlocal d2h, outstanding
+        if not outstanding or not op.handle_watermark_poll(col, block=block):
+            return
+        outstanding = False
+        for rb in col.batches:
+            d2h += rb.num_rows * 48
+        col.batches.clear()
 
     def step(p):
-        nonlocal d2h
+        nonlocal d2h, outstanding
         for b in range(nb):
             op.process_batch(batches[p][b], ctx, col)
             wm = wms[p * nb + b]
             if wm is not None:
                 ctx.watermarks.set(0, wm)
-                op.handle_watermark(wm, ctx, col)
-                for rb in col.batches:
-                    d2h += rb.num_rows * 48
-                col.batches.clear()
+                if args.sync_emit:
+                    op.handle_watermark(wm, ctx, col)
+                    for rb in col.batches:
+                        d2h += rb.num_rows * 48
+                    col.batches.clear()
+                else:
+                    collect(block=True)  # windows leave in order: the previous emission first
+                    outstanding = op.handle_watermark_begin(wm, ctx)
+            elif outstanding and b % 8 == 0:
+                collect(block=False)  # the run loop polls the future between batches
 
     for p in range(W):
         step(p)
+    collect(block=True)
     op.flush()
     torch.cuda.synchronize()
     d2h = 0
     t0 = time.perf_counter()
     for p in range(W, W + K):
         step(p)
+    collect(block=True)
     op.flush()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     op.close()
+    how = ("arroyo_b200_op_handle_watermark" if args.sync_emit else
+           "arroyo_b200_op_handle_watermark_begin / _poll (windows copied back while the next batches are copied in)")
     return {"value": K * rows / dt, "unit": "rows/s", "h2d_bytes_per_step": rows * 24,
             "d2h_bytes_per_step": d2h // max(K, 1), "steps": K, "ms_per_step": 1e3 * dt / K,
-            "path": "pinned host Arrow batches -> arroyo_b200_op_process_batch -> host Arrow windows"}
+            "path": f"pinned host Arrow batches -> arroyo_b200_op_process_batch -> {how} -> host Arrow windows"}
 
 
 def run_reference(args):

@@ -282,6 +282,18 @@ int32_t arroyo_b200_op_process_device_batches(ArroyoB200Op* op, uint32_t input_i
  * (context.rs:490-494) before it forwards the watermark. */
 int32_t arroyo_b200_op_handle_watermark(ArroyoB200Op* op, int64_t watermark_ns, ArroyoB200Batches* out);
 
+/* handle_watermark in two halves, for shims that keep the run loop going while windows travel to the host -- the
+ * mechanism the reference's own operators use for long-running work: ArrowOperator::future_to_poll /
+ * handle_future_result (operator.rs:1190-1204; tumbling_aggregating_window.rs:394-428).
+ *   begin: everything handle_watermark does, except that the device->host copies of the emitted windows are
+ *          enqueued on a second stream and not awaited; the call returns as soon as they are enqueued.
+ *   poll : `*ready` = 1 and `out` = the batches once those copies have completed (`block` != 0 waits for them),
+ *          else `*ready` = 0.  The shim forwards the watermark after it has collected the batches
+ *          (operator.rs:777-786).  `begin` with an uncollected emission outstanding is an error; the other
+ *          entry points may be called in between (the copies overlap the next batches' host->device copies). */
+int32_t arroyo_b200_op_handle_watermark_begin(ArroyoB200Op* op, int64_t watermark_ns);
+int32_t arroyo_b200_op_handle_watermark_poll(ArroyoB200Op* op, int32_t block, ArroyoB200Batches* out, int32_t* ready);
+
 /* Same, leaving the emitted windows on the device.  `out` must have room for `max_out`
  * entries; `*n_out` receives the number written (excess windows are an error). */
 int32_t arroyo_b200_op_handle_watermark_device(ArroyoB200Op* op, int64_t watermark_ns,

@@ -457,6 +457,51 @@ def test_pinned_host_batches_are_read_in_place(G):
     assert op.stats()["h2d_bytes"] == 150_000 * 24
 
 
+def test_begin_poll_emission_matches_blocking_handle_watermark(G):
+    """handle_watermark_begin / _poll (windows copied back on a second stream while the next batches arrive):
+    the same batches, in the same order, as the blocking call; a second `begin` before the first emission was
+    collected is refused; checkpoints and the blocking call may be mixed in."""
+    import arroyo_b200 as ab
+    from arroyo_b200 import ffi, operators as native
+    from tests.gpu_ops import from_arrow, to_arrow
+    rng = np.random.default_rng(21)
+    batches = gen_stream(rng, 200_000, 6_000, rate_per_s=25_000, batch=5_000)
+    cfg = O.WindowAggConfig(width=3 * S, slide=S, key_names=["key"], aggs=SUM_AVG, window_index=1)
+    want = O.run_single_input(O.SlidingAggregatingWindowFunc(cfg), batches, S).batches
+    op = native.SlidingAggregatingWindowFunc(cfg)
+    ctx, out, gen = ab.OperatorContext(1), ab.Collector(), ab.WatermarkGenerator(S)
+    outstanding, polls, refused = False, 0, 0
+    for i, b in enumerate(batches):
+        op.process_batch(to_arrow(b), ctx, out)
+        if outstanding and op.handle_watermark_poll(out, block=False):
+            outstanding = False
+        polls += 1
+        wm = gen.on_batch(int(b[O.TIMESTAMP].min()), int(b[O.TIMESTAMP].max()))
+        if wm is None:
+            continue
+        ctx.watermarks.set(0, wm)
+        if outstanding and refused == 0:
+            with pytest.raises(ffi.ArroyoB200Error):
+                op.handle_watermark_begin(wm, ctx)
+            refused += 1
+        if outstanding:
+            assert op.handle_watermark_poll(out, block=True)
+            outstanding = False
+        if i % 7 == 3:
+            op.handle_watermark(wm, ctx, out)  # the blocking form in between
+        else:
+            outstanding = op.handle_watermark_begin(wm, ctx)
+    if outstanding:
+        assert op.handle_watermark_poll(out, block=True)
+    assert op.handle_watermark_poll(out, block=False)  # nothing outstanding: ready, empty
+    ctx.watermarks.set(0, ab.FINAL_WATERMARK)
+    assert op.handle_watermark_begin(ab.FINAL_WATERMARK, ctx)
+    assert op.handle_watermark_poll(out, block=True)
+    got = [from_arrow(b) for b in out.batches]
+    assert_same(want, got, float_cols=("avg",))
+    assert [int(b["window_start"][0]) for b in got] == [int(b["window_start"][0]) for b in want]
+
+
 def test_partial_then_final_equals_direct(G):
     """partial -> (shuffle) -> final: a per-pane tumbling stage emits (key, sum, count) partial rows; a
     sliding operator declared with `partial_count_col` merges them.  The windows must equal the direct
