@@ -227,6 +227,50 @@ int32_t arroyo_b200_op_handle_watermark_poll(ArroyoB200Op* op, int32_t block, Ar
   });
 }
 
+int32_t arroyo_b200_op_run_batches(ArroyoB200Op* op, struct ArrowArray* batches, const struct ArrowSchema* schema,
+                                    int64_t n_batches, const int64_t* watermarks, int32_t async_emit,
+                                    ArroyoB200Batches* out, int64_t* n_consumed) {
+  if (out) memset(out, 0, sizeof *out);
+  if (n_consumed) *n_consumed = 0;
+  if (!op) return ARROYO_B200_INVALID_ARGUMENT;
+  auto* acc = new BatchesPriv();
+  int32_t st = guarded(op, [&](OpBase* o) {
+    AB_REQUIRE(out != nullptr && n_consumed != nullptr && (n_batches == 0 || (batches != nullptr && schema != nullptr)),
+               ARROYO_B200_INVALID_ARGUMENT, "null argument");
+    // the windows of an emission that has been begun: hand them on once their copies have completed
+    auto collect = [&](bool block) {
+      if (!o->pending_out || !o->poll_watermark(block)) return;
+      for (auto& a : o->pending_out->arrays) acc->arrays.push_back(a);
+      for (auto& s : o->pending_out->schemas) acc->schemas.push_back(s);
+      delete o->pending_out;
+      o->pending_out = nullptr;
+    };
+    for (int64_t i = 0; i < n_batches; ++i) {
+      {
+        WallTimer wt(op->host_process_ms);
+        o->process_batch(0, 1, &batches[i], schema);
+      }
+      ++*n_consumed;
+      const int64_t wm = watermarks ? watermarks[i] : INT64_MIN;
+      WallTimer wt(op->host_watermark_ms);
+      if (wm == INT64_MIN) {
+        if (async_emit && (i & 7) == 0) collect(false);
+        continue;
+      }
+      if (async_emit) {
+        collect(true);  // windows leave in order: the previous emission first
+        o->pending_out = new BatchesPriv();
+        o->begin_watermark(wm);
+      } else {
+        o->handle_watermark(wm, acc, nullptr);
+      }
+    }
+    if (async_emit) collect(false);
+  });
+  batches_finish(acc, out);
+  return st;
+}
+
 int32_t arroyo_b200_op_handle_watermark_device(ArroyoB200Op* op, int64_t watermark_ns, ArroyoB200DeviceBatch* out,
                                                int64_t max_out, int64_t* n_out) {
   if (n_out) *n_out = 0;

@@ -809,6 +809,7 @@ struct LaunchRec {
   int chunk = -1;  // staging chunk read by this launch (-1: none)
 };
 
+constexpr size_t RELEASE_GROUP = 8;
 struct PendingRelease {
   cudaEvent_t ev;
   std::vector<ArrowArray> arrs;  // moved-in copies; released when ev completes
@@ -876,6 +877,9 @@ class WindowAggOp final : public OpBase {
   cudaEvent_t emit_done_ = nullptr, out_done_ = nullptr;
   bool async_out_ = false, out_inflight_ = false;
   void wait_outputs();
+  std::vector<ArrowArray> open_release_;  // staged inputs whose copies have no release event yet
+  std::vector<cudaEvent_t> ev_pool_;
+  void seal_release();
   bool direct_decided_ = false;
   long long direct_base_ = 0;
   uint32_t direct_n_ = 0;
@@ -1149,6 +1153,9 @@ WindowAggOp::~WindowAggOp() {
   }
   for (auto& a : zero_copy_inputs_)
     if (a.release) a.release(&a);
+  for (auto& a : open_release_)
+    if (a.release) a.release(&a);
+  for (auto e : ev_pool_) cudaEventDestroy(e);
   for (int i = 0; i < NCHUNK; ++i)
     if (chunk_free_[i]) cudaEventDestroy(chunk_free_[i]);
   for (int i = 0; i < NLAUNCH; ++i) {
@@ -1430,7 +1437,24 @@ void WindowAggOp::upload_ring() {
   ring_dirty_ = false;
 }
 
+// Input batches are handed back in groups: one CUDA event per RELEASE_GROUP batches (or per launch / flush)
+// instead of one per batch, and the events are recycled.
+void WindowAggOp::seal_release() {
+  if (open_release_.empty()) return;
+  PendingRelease r;
+  if (!ev_pool_.empty()) {
+    r.ev = ev_pool_.back();
+    ev_pool_.pop_back();
+  } else {
+    AB_CUDA(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
+  }
+  AB_CUDA(cudaEventRecord(r.ev, stream_));
+  r.arrs.swap(open_release_);
+  releases_.push_back(std::move(r));
+}
+
 void WindowAggOp::poll_releases(bool wait) {
+  if (wait) seal_release();
   while (!releases_.empty()) {
     PendingRelease& r = releases_.front();
     if (wait) {
@@ -1442,7 +1466,7 @@ void WindowAggOp::poll_releases(bool wait) {
     }
     for (auto& a : r.arrs)
       if (a.release) a.release(&a);
-    cudaEventDestroy(r.ev);
+    ev_pool_.push_back(r.ev);
     releases_.pop_front();
   }
 }
@@ -1567,13 +1591,10 @@ void WindowAggOp::process_batch(uint32_t, uint32_t, ArrowArray* batch, const Arr
     cur_rows_ += take;
     done += take;
   }
-  // ownership of the input moves to the library; release once the copies have completed
-  PendingRelease r;
-  AB_CUDA(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
-  AB_CUDA(cudaEventRecord(r.ev, stream_));
-  r.arrs.push_back(*batch);
+  // ownership of the input moves to the library; released once the copies have completed
+  open_release_.push_back(*batch);
   batch->release = nullptr;
-  releases_.push_back(std::move(r));
+  if (open_release_.size() >= RELEASE_GROUP) seal_release();
   if (cur_rows_ == chunk_rows_) {
     launch_pending();
     rotate_chunk();
@@ -1774,6 +1795,7 @@ void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk
 }
 
 void WindowAggOp::launch_pending() {
+  seal_release();
   if (segs_.empty()) return;
   std::vector<Segment> segs;
   segs.swap(segs_);
@@ -1784,7 +1806,12 @@ void WindowAggOp::launch_pending() {
   if (!zero_copy_inputs_.empty()) {
     // the pinned input batches these segments point into may be released once this kernel has run
     PendingRelease r;
-    AB_CUDA(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
+    if (!ev_pool_.empty()) {
+      r.ev = ev_pool_.back();
+      ev_pool_.pop_back();
+    } else {
+      AB_CUDA(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
+    }
     AB_CUDA(cudaEventRecord(r.ev, stream_));
     r.arrs.swap(zero_copy_inputs_);
     releases_.push_back(std::move(r));

@@ -17,6 +17,7 @@ AGG_COUNT_STAR, AGG_SUM_I64, AGG_AVG_I64, AGG_MIN_I64, AGG_MAX_I64 = 1, 2, 3, 4,
 JOIN_INNER, JOIN_LEFT, JOIN_RIGHT, JOIN_FULL = 0, 1, 2, 3
 FLAG_PROFILE, FLAG_REMERGE_ONLY, FLAG_COMBINE, FLAG_AVG_F64, FLAG_NO_COMBINE, FLAG_ZERO_COPY = 1, 2, 4, 8, 16, 32
 FLAG_NO_DIRECT = 64
+NO_WATERMARK = -(1 << 63)
 INT64_MIN = -(1 << 63)
 INT64_MAX = (1 << 63) - 1
 
@@ -108,6 +109,8 @@ SYMBOLS = [
     ("arroyo_b200_op_handle_watermark", C.c_int32, [_VP, C.c_int64, C.POINTER(Batches)]),
     ("arroyo_b200_op_handle_watermark_begin", C.c_int32, [_VP, C.c_int64]),
     ("arroyo_b200_op_handle_watermark_poll", C.c_int32, [_VP, C.c_int32, C.POINTER(Batches), C.POINTER(C.c_int32)]),
+    ("arroyo_b200_op_run_batches", C.c_int32, [_VP, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_int32,
+                                               C.POINTER(Batches), C.POINTER(C.c_int64)]),
     ("arroyo_b200_op_handle_watermark_device", C.c_int32, [_VP, C.c_int64, C.POINTER(DeviceBatch), C.c_int64,
                                                            C.POINTER(C.c_int64)]),
     ("arroyo_b200_op_handle_checkpoint", C.c_int32, [_VP, C.c_int64, C.POINTER(Batches)]),

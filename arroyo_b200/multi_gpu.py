@@ -372,6 +372,9 @@ def bench(args, torch, dist, rank, world, local):
     from . import operators as native
 
     device = torch.device("cuda", local)
+    # torch, NCCL's ordering, the partitioner and the owner stage share the explicit stream bench.py installed
+    # (passing the legacy default stream's handle, 0, would make every native handle create a private stream)
+    assert torch.cuda.current_stream().cuda_stream != 0
     W, K = max(args.warmup, 3), args.steps
     rows = args.rows_per_pane
     nb = rows // B.BATCH_ROWS

@@ -34,6 +34,38 @@ def export_batch(batch: pa.RecordBatch):
     return arr, sch
 
 
+class ExportedBatches:
+    """A run of record batches (same schema) exported once to Arrow C Data structs laid out as one C array -- the
+    input of arroyo_b200_op_run_batches.  Export only builds descriptors: the buffers stay where they are."""
+
+    def __init__(self, batches: List[pa.RecordBatch]):
+        self.n = len(batches)
+        self.names = list(batches[0].schema.names) if batches else []
+        self.arrays = (ffi.ArrowArray * max(self.n, 1))()
+        self.schema = ffi.ArrowSchema()
+        step = C.sizeof(ffi.ArrowArray)
+        base = C.addressof(self.arrays)
+        for i, b in enumerate(batches):
+            if i == 0:
+                b._export_to_c(base, C.addressof(self.schema))
+            else:
+                b._export_to_c(base + i * step)
+
+    def release_unconsumed(self, first: int):
+        """Releases the batches the library did not take (after an error)."""
+        for i in range(first, self.n):
+            a = self.arrays[i]
+            if a.release:
+                C.CFUNCTYPE(None, C.c_void_p)(a.release)(C.addressof(a))
+
+    def __del__(self):
+        try:
+            if self.schema.release:
+                C.CFUNCTYPE(None, C.c_void_p)(self.schema.release)(C.addressof(self.schema))
+        except Exception:
+            pass
+
+
 def import_batches(lib, out: ffi.Batches) -> List[pa.RecordBatch]:
     res = []
     try:
@@ -244,6 +276,26 @@ class _WindowAggregate(_NativeOperator):
         for b in import_batches(self._lib, out):
             collector.collect(pa.RecordBatch.from_arrays(b.columns, names=names))
         return True
+
+    def run_batches(self, exported: "ExportedBatches", watermarks, collector: Collector, first: int = 0,
+                    count: Optional[int] = None, async_emit: bool = True):
+        """arroyo_b200_op_run_batches over exported[first : first + count]: the subtask run loop inside the library.
+        `watermarks` is a (c_int64 * exported.n) array: the effective watermark that follows each batch, or
+        ffi.NO_WATERMARK.  Windows collected during the call go to `collector`; with `async_emit` the last
+        emission may still be outstanding (handle_watermark_poll, or the next call, delivers it)."""
+        if not self.created:
+            self._build(exported.names)
+        count = exported.n - first if count is None else count
+        out, taken = ffi.Batches(), C.c_int64(0)
+        step = C.sizeof(ffi.ArrowArray)
+        st = self._lib.arroyo_b200_op_run_batches(
+            self._h, C.addressof(exported.arrays) + first * step, C.addressof(exported.schema), count,
+            C.cast(C.addressof(watermarks) + 8 * first, C.POINTER(C.c_int64)), 1 if async_emit else 0, C.byref(out),
+            C.byref(taken))
+        names = self.output_names()
+        for b in import_batches(self._lib, out):
+            collector.collect(pa.RecordBatch.from_arrays(b.columns, names=names))
+        _check(self._lib, self._h, st)
 
     def handle_watermark_device(self, wm: int, max_out: int = 64):
         """Emission left on the device: list of (n_rows, [device pointers])."""

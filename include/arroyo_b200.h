@@ -294,6 +294,19 @@ int32_t arroyo_b200_op_handle_watermark(ArroyoB200Op* op, int64_t watermark_ns, 
 int32_t arroyo_b200_op_handle_watermark_begin(ArroyoB200Op* op, int64_t watermark_ns);
 int32_t arroyo_b200_op_handle_watermark_poll(ArroyoB200Op* op, int32_t block, ArroyoB200Batches* out, int32_t* ready);
 
+/* The run loop of a single-input operator task for a run of queued batches, inside the library -- what the
+ * subtask's loop does between two control messages (arroyo-operator/src/operator.rs:982-1062): for every batch
+ * `process_batch`; when `watermarks[i]` != INT64_MIN the (already min-merged) watermark that follows batch i is
+ * handled, with the begin / poll pair when `async_emit` != 0 (outstanding windows are collected before the next
+ * emission begins and polled every few batches), else with the blocking call.  `out` receives the windows
+ * collected during the call in emission order; with `async_emit` the last emission may still be outstanding on
+ * return -- the next call, or handle_watermark_poll, delivers it.  Ownership of batches [0, *n_consumed) has moved
+ * to the library (all of them on success).  For hosts whose per-call FFI cost is not negligible against a
+ * 64 Ki-row batch's 28 us of PCIe time (Python ctypes; a Rust shim can as well loop itself). */
+int32_t arroyo_b200_op_run_batches(ArroyoB200Op* op, struct ArrowArray* batches, const struct ArrowSchema* schema,
+                                    int64_t n_batches, const int64_t* watermarks, int32_t async_emit,
+                                    ArroyoB200Batches* out, int64_t* n_consumed);
+
 /* Same, leaving the emitted windows on the device.  `out` must have room for `max_out`
  * entries; `*n_out` receives the number written (excess windows are an error). */
 int32_t arroyo_b200_op_handle_watermark_device(ArroyoB200Op* op, int64_t watermark_ns,

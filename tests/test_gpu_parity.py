@@ -502,6 +502,38 @@ def test_begin_poll_emission_matches_blocking_handle_watermark(G):
     assert [int(b["window_start"][0]) for b in got] == [int(b["window_start"][0]) for b in want]
 
 
+@pytest.mark.parametrize("async_emit", [True, False])
+def test_run_batches_loop_matches_per_batch_calls(G, async_emit):
+    """arroyo_b200_op_run_batches (the subtask run loop inside the library) over runs of queued batches with the
+    watermark that follows each: the same windows, in the same order, as one call per batch."""
+    import ctypes as C
+    import arroyo_b200 as ab
+    from arroyo_b200 import ffi, operators as native
+    from tests.gpu_ops import from_arrow, to_arrow
+    rng = np.random.default_rng(33)
+    batches = gen_stream(rng, 150_000, 2_000, rate_per_s=15_000, batch=3_000)
+    cfg = O.WindowAggConfig(width=4 * S, slide=S, key_names=["key"], aggs=SUM_AVG, window_index=1)
+    want = O.run_single_input(O.SlidingAggregatingWindowFunc(cfg), batches, S).batches
+    gen = ab.WatermarkGenerator(S)
+    wms = [gen.on_batch(int(b[O.TIMESTAMP].min()), int(b[O.TIMESTAMP].max())) for b in batches]
+    op = native.SlidingAggregatingWindowFunc(cfg)
+    out = ab.Collector()
+    run = 13  # batches per call: emissions fall in the middle and at the end of runs
+    for s in range(0, len(batches), run):
+        chunk = batches[s:s + run]
+        ex = native.ExportedBatches([to_arrow(b) for b in chunk])
+        w = (C.c_int64 * len(chunk))(*[ffi.NO_WATERMARK if x is None else x for x in wms[s:s + run]])
+        op.run_batches(ex, w, out, async_emit=async_emit)
+        assert not any(ex.arrays[i].release for i in range(ex.n))  # every batch was taken
+    ctx = ab.OperatorContext(1)
+    ctx.watermarks.set(0, ab.FINAL_WATERMARK)
+    op.handle_watermark_poll(out, block=True)
+    op.handle_watermark(ab.FINAL_WATERMARK, ctx, out)
+    got = [from_arrow(b) for b in out.batches]
+    assert_same(want, got, float_cols=("avg",))
+    assert [int(b["window_start"][0]) for b in got] == [int(b["window_start"][0]) for b in want]
+
+
 def test_partial_then_final_equals_direct(G):
     """partial -> (shuffle) -> final: a per-pane tumbling stage emits (key, sum, count) partial rows; a
     sliding operator declared with `partial_count_col` merges them.  The windows must equal the direct

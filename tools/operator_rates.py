@@ -40,7 +40,11 @@ def main():
 
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
+    # one explicit stream for torch, the operators and the partitioner (a stream argument of 0 would make each
+    # handle create its own stream, invisible to the events below)
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     stream = torch.cuda.current_stream().cuda_stream
+    assert stream != 0
     peak, _ = B.measured_peak()
     out = []
     g = torch.Generator(device=dev)
@@ -150,7 +154,8 @@ def main():
     scfg = ab.SessionConfig(gap=5 * S, key_names=["key"], aggs=[ab.Agg("sum", "value", "sum"), ab.Agg("count", None, "n")],
                             window_index=1)
     sop = native.SessionAggregatingWindowFunc(scfg, input_schema=raw_schema, device=0, stream=stream, expected_keys=n_keys)
-    sk = [torch.randint(0, n_keys, (srows,), device=dev, generator=g, dtype=torch.int64) * 7919 for _ in range(4)]
+    n_steps = 26
+    sk = [torch.randint(0, n_keys, (srows,), device=dev, generator=g, dtype=torch.int64) * 7919 for _ in range(n_steps)]
     sv = torch.randint(0, 10**6, (srows,), device=dev, generator=g, dtype=torch.int64)
     offs = torch.sort(torch.randint(0, S, (srows,), device=dev, generator=g, dtype=torch.int64)).values
     sess_out = 0
@@ -158,14 +163,14 @@ def main():
     def sstep(p):
         nonlocal sess_out
         ts = offs + (T0 + p * S)
-        sop.process_device_batch([sk[p % 4].data_ptr(), sv.data_ptr(), ts.data_ptr()], srows)
+        sop.process_device_batch([sk[p].data_ptr(), sv.data_ptr(), ts.data_ptr()], srows)
         for n, _ in sop.handle_watermark_device(T0 + p * S - S):
             sess_out += n
 
-    for p in range(12):
+    for p in range(14):
         sstep(p)
     sess_out = 0
-    ms = timed(torch, lambda r: sstep(12 + r), 12)
+    ms = timed(torch, lambda r: sstep(14 + r), 12)
     rec("SessionAggregatingWindowFunc", f"configs[4] shape: gap 5 s, {n_keys} keys, 4 Mi rows per second of event time, "
         f"{sess_out // 12} sessions closed per step", srows, ms, 24,
         "one thread per key replays the reference's per-key state machine; inputs read once")
