@@ -2239,7 +2239,9 @@ void WindowAggOp::emit_window(int64_t a, int64_t b, size_t out_index, BatchesPri
     }
     if (blocks.empty()) return;  // aggregate over an empty input has no groups
   }
-  OutSet* os = out_set(out_dev ? out_index : 0, std::max<uint64_t>(n_keys_host_, 1));
+  // device output and asynchronous host output keep every window of the emission alive until the caller (or the
+  // copy stream) is done with it: one output set per window; blocking host output reuses set 0
+  OutSet* os = out_set(out_dev || async_out_ ? out_index : 0, std::max<uint64_t>(n_keys_host_, 1));
   const int64_t ts = cfg.final_projection ? b - 1 : a;
   int64_t n = run_emit(blocks, n_add, use_running, false, a, b, ts, os);
   // blocks of panes that had already left the store have now been subtracted from W

@@ -38,6 +38,11 @@ def main():
     from arroyo_b200 import ffi, operators as native
     from arroyo_b200.multi_gpu import DevicePartitioner
 
+    only = set(sys.argv[1:])  # e.g. `join session`; empty = everything
+
+    def want(section):
+        return not only or section in only
+
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     # one explicit stream for torch, the operators and the partitioner (a stream argument of 0 would make each
@@ -61,7 +66,7 @@ def main():
     rows = 1 << 24
 
     # ---- configs[1]: tumbling 1 s COUNT(*) GROUP BY key, 10 K keys --------------------------------------
-    for keyspace in ("scattered", "dense"):
+    for keyspace in (("scattered", "dense") if want("tumbling") else ()):
         gen = B.make_generator(torch, dev, rows, 10_000, "uniform", 42, keyspace)
         W, K = 6, 20
         panes = [gen(p) for p in range(W + K)]
@@ -85,7 +90,7 @@ def main():
     # ---- shuffle: hash partition of raw rows into 8 destinations ----------------------------------------
     gen = B.make_generator(torch, dev, rows, 1 << 20, "uniform", 42)
     k, v, t = gen(0)
-    for packed in (False, True):
+    for packed in ((False, True) if want("shuffle") else ()):
         part = DevicePartitioner(torch, 8, 3, 0, rows, 0, stream)
         fn = (lambda r: part.pack([k.data_ptr(), v.data_ptr(), t.data_ptr()], rows)) if packed else (lambda r: part([k, v, t], rows))
         for _ in range(3):
@@ -95,86 +100,94 @@ def main():
             rows, ms, 48 + 8, "24 B read + 24 B written per row, key read once more by the histogram pass")
         part.close()
 
-    # ---- WatermarkGenerator reductions --------------------------------------------------------------------
-    lib = ffi.load()
-    mn, mx = C.c_int64(), C.c_int64()
-    fn = lambda r: lib.arroyo_b200_ts_minmax(0, stream, t.data_ptr(), rows, C.byref(mn), C.byref(mx))
-    fn(0)
-    ms = timed(torch, fn, 20)
-    rec("WatermarkGenerator min/max", "one 16 Mi-row batch (synchronous call: includes the result's D2H)", rows, ms, 8)
-    nb = 1 << 16
-    fn = lambda r: lib.arroyo_b200_ts_minmax(0, stream, t.data_ptr(), nb, C.byref(mn), C.byref(mx))
-    ms = timed(torch, fn, 200)
-    rec("WatermarkGenerator min/max", "one 64 Ki-row batch (latency-bound: launch + D2H + sync)", nb, ms, 8)
-    del k, v, t, gen
-    torch.cuda.empty_cache()
+    def wm_section():
+        # ---- WatermarkGenerator reductions --------------------------------------------------------------------
+        lib = ffi.load()
+        mn, mx = C.c_int64(), C.c_int64()
+        fn = lambda r: lib.arroyo_b200_ts_minmax(0, stream, t.data_ptr(), rows, C.byref(mn), C.byref(mx))
+        fn(0)
+        ms = timed(torch, fn, 20)
+        rec("WatermarkGenerator min/max", "one 16 Mi-row batch (synchronous call: includes the result's D2H)", rows, ms, 8)
+        nb = 1 << 16
+        fn = lambda r: lib.arroyo_b200_ts_minmax(0, stream, t.data_ptr(), nb, C.byref(mn), C.byref(mx))
+        ms = timed(torch, fn, 200)
+        rec("WatermarkGenerator min/max", "one 64 Ki-row batch (latency-bound: launch + D2H + sync)", nb, ms, 8)
 
-    # ---- configs[3]: q8-shaped windowed join, person x auction per 30 s tumbling window ----------------
-    n_p, n_a = 1 << 21, 1 << 23
-    W30 = 30 * S
-    jcfg = ab.JoinConfig(left_on=["id"], right_on=["seller"], join_type="inner")
-    l_schema = pa.schema([("id", pa.int64()), ("name_code", pa.int64()), ("_timestamp", pa.timestamp("ns"))])
-    r_schema = pa.schema([("seller", pa.int64()), ("auction", pa.int64()), ("reserve", pa.int64()), ("_timestamp", pa.timestamp("ns"))])
-    jop = native.InstantJoin(jcfg, left_schema=l_schema, right_schema=r_schema, device=0, stream=stream)
-    pid = torch.randperm(n_p, device=dev, generator=g).to(torch.int64) + 1000
-    name = torch.randint(0, 10**6, (n_p,), device=dev, generator=g, dtype=torch.int64)
-    seller = torch.randint(0, n_p, (n_a,), device=dev, generator=g, dtype=torch.int64) + 1000
-    auction = torch.arange(n_a, device=dev, dtype=torch.int64)
-    reserve = torch.randint(1, 10**5, (n_a,), device=dev, generator=g, dtype=torch.int64)
-    rows_out = 0
+    def join_section():
+        # ---- configs[3]: q8-shaped windowed join, person x auction per 30 s tumbling window ----------------
+        n_p, n_a = 1 << 21, 1 << 23
+        W30 = 30 * S
+        jcfg = ab.JoinConfig(left_on=["id"], right_on=["seller"], join_type="inner")
+        l_schema = pa.schema([("id", pa.int64()), ("name_code", pa.int64()), ("_timestamp", pa.timestamp("ns"))])
+        r_schema = pa.schema([("seller", pa.int64()), ("auction", pa.int64()), ("reserve", pa.int64()), ("_timestamp", pa.timestamp("ns"))])
+        jop = native.InstantJoin(jcfg, left_schema=l_schema, right_schema=r_schema, device=0, stream=stream)
+        pid = torch.randperm(n_p, device=dev, generator=g).to(torch.int64) + 1000
+        name = torch.randint(0, 10**6, (n_p,), device=dev, generator=g, dtype=torch.int64)
+        seller = torch.randint(0, n_p, (n_a,), device=dev, generator=g, dtype=torch.int64) + 1000
+        auction = torch.arange(n_a, device=dev, dtype=torch.int64)
+        reserve = torch.randint(1, 10**5, (n_a,), device=dev, generator=g, dtype=torch.int64)
+        rows_out = 0
 
-    def jstep(w):
-        nonlocal rows_out
-        ts = T0 + (w + 1) * W30 - 1
-        tl = torch.full((n_p,), ts, device=dev, dtype=torch.int64)
-        tr = torch.full((n_a,), ts, device=dev, dtype=torch.int64)
-        la = (C.c_uint64 * 3)(pid.data_ptr(), name.data_ptr(), tl.data_ptr())
-        ra = (C.c_uint64 * 4)(seller.data_ptr(), auction.data_ptr(), reserve.data_ptr(), tr.data_ptr())
-        native._check(jop._lib, jop._h, jop._lib.arroyo_b200_op_process_device_batch(jop._h, 0, 2, la, 3, n_p))
-        native._check(jop._lib, jop._h, jop._lib.arroyo_b200_op_process_device_batch(jop._h, 1, 2, ra, 4, n_a))
-        outb = (ffi.DeviceBatch * 8)()
-        n = C.c_int64(0)
-        native._check(jop._lib, jop._h, jop._lib.arroyo_b200_op_handle_watermark_device(jop._h, ts + 1, outb, 8, C.byref(n)))
-        rows_out += sum(outb[i].n_rows for i in range(n.value))
+        def jstep(w):
+            nonlocal rows_out
+            ts = T0 + (w + 1) * W30 - 1
+            tl = torch.full((n_p,), ts, device=dev, dtype=torch.int64)
+            tr = torch.full((n_a,), ts, device=dev, dtype=torch.int64)
+            la = (C.c_uint64 * 3)(pid.data_ptr(), name.data_ptr(), tl.data_ptr())
+            ra = (C.c_uint64 * 4)(seller.data_ptr(), auction.data_ptr(), reserve.data_ptr(), tr.data_ptr())
+            native._check(jop._lib, jop._h, jop._lib.arroyo_b200_op_process_device_batch(jop._h, 0, 2, la, 3, n_p))
+            native._check(jop._lib, jop._h, jop._lib.arroyo_b200_op_process_device_batch(jop._h, 1, 2, ra, 4, n_a))
+            outb = (ffi.DeviceBatch * 8)()
+            n = C.c_int64(0)
+            native._check(jop._lib, jop._h, jop._lib.arroyo_b200_op_handle_watermark_device(jop._h, ts + 1, outb, 8, C.byref(n)))
+            rows_out += sum(outb[i].n_rows for i in range(n.value))
 
-    for w in range(3):
-        jstep(w)
-    rows_out = 0
-    ms = timed(torch, lambda r: jstep(3 + r), 10)
-    rec("InstantJoin (inner)", f"configs[3] shape: per 30 s window {n_p} persons x {n_a} auctions on person id = seller, "
-        f"{rows_out // 10} joined rows out", n_p + n_a, ms, (24 * n_p + 32 * n_a + 48 * (rows_out // 10)) / (n_p + n_a),
-        "inputs read once + joined rows (6 columns) written once; includes the arena append and the compaction")
-    jop.close()
-    del pid, name, seller, auction, reserve
-    torch.cuda.empty_cache()
+        for w in range(3):
+            jstep(w)
+        rows_out = 0
+        ms = timed(torch, lambda r: jstep(3 + r), 10)
+        rec("InstantJoin (inner)", f"configs[3] shape: per 30 s window {n_p} persons x {n_a} auctions on person id = seller, "
+            f"{rows_out // 10} joined rows out", n_p + n_a, ms, (24 * n_p + 32 * n_a + 48 * (rows_out // 10)) / (n_p + n_a),
+            "inputs read once + joined rows (6 columns) written once; includes the arena append and the compaction")
+        jop.close()
+        del pid, name, seller, auction, reserve
+        torch.cuda.empty_cache()
 
-    # ---- configs[4]: session windows, 5 s gap, many keys -------------------------------------------------
-    n_keys = int(os.environ.get("SESSION_KEYS", 10_000_000))
-    srows = 1 << 22
-    scfg = ab.SessionConfig(gap=5 * S, key_names=["key"], aggs=[ab.Agg("sum", "value", "sum"), ab.Agg("count", None, "n")],
-                            window_index=1)
-    sop = native.SessionAggregatingWindowFunc(scfg, input_schema=raw_schema, device=0, stream=stream, expected_keys=n_keys)
-    n_steps = 26
-    sk = [torch.randint(0, n_keys, (srows,), device=dev, generator=g, dtype=torch.int64) * 7919 for _ in range(n_steps)]
-    sv = torch.randint(0, 10**6, (srows,), device=dev, generator=g, dtype=torch.int64)
-    offs = torch.sort(torch.randint(0, S, (srows,), device=dev, generator=g, dtype=torch.int64)).values
-    sess_out = 0
+    def session_section():
+        # ---- configs[4]: session windows, 5 s gap, many keys -------------------------------------------------
+        n_keys = int(os.environ.get("SESSION_KEYS", 10_000_000))
+        srows = 1 << 22
+        scfg = ab.SessionConfig(gap=5 * S, key_names=["key"], aggs=[ab.Agg("sum", "value", "sum"), ab.Agg("count", None, "n")],
+                                window_index=1)
+        sop = native.SessionAggregatingWindowFunc(scfg, input_schema=raw_schema, device=0, stream=stream, expected_keys=n_keys)
+        n_steps = 26
+        sk = [torch.randint(0, n_keys, (srows,), device=dev, generator=g, dtype=torch.int64) * 7919 for _ in range(n_steps)]
+        sv = torch.randint(0, 10**6, (srows,), device=dev, generator=g, dtype=torch.int64)
+        offs = torch.sort(torch.randint(0, S, (srows,), device=dev, generator=g, dtype=torch.int64)).values
+        sess_out = 0
 
-    def sstep(p):
-        nonlocal sess_out
-        ts = offs + (T0 + p * S)
-        sop.process_device_batch([sk[p].data_ptr(), sv.data_ptr(), ts.data_ptr()], srows)
-        for n, _ in sop.handle_watermark_device(T0 + p * S - S):
-            sess_out += n
+        def sstep(p):
+            nonlocal sess_out
+            ts = offs + (T0 + p * S)
+            sop.process_device_batch([sk[p].data_ptr(), sv.data_ptr(), ts.data_ptr()], srows)
+            for n, _ in sop.handle_watermark_device(T0 + p * S - S):
+                sess_out += n
 
-    for p in range(14):
-        sstep(p)
-    sess_out = 0
-    ms = timed(torch, lambda r: sstep(14 + r), 12)
-    rec("SessionAggregatingWindowFunc", f"configs[4] shape: gap 5 s, {n_keys} keys, 4 Mi rows per second of event time, "
-        f"{sess_out // 12} sessions closed per step", srows, ms, 24,
-        "one thread per key replays the reference's per-key state machine; inputs read once")
-    sop.close()
+        for p in range(14):
+            sstep(p)
+        sess_out = 0
+        ms = timed(torch, lambda r: sstep(14 + r), 12)
+        rec("SessionAggregatingWindowFunc", f"configs[4] shape: gap 5 s, {n_keys} keys, 4 Mi rows per second of event time, "
+            f"{sess_out // 12} sessions closed per step", srows, ms, 24,
+            "one thread per key replays the reference's per-key state machine; inputs read once")
+        sop.close()
+
+    if want("wm"):
+        wm_section()
+    if want("join"):
+        join_section()
+    if want("session"):
+        session_section()
 
     print(json.dumps({"peak_GBps": peak, "cases": out}, indent=1))
 
