@@ -58,55 +58,72 @@ __global__ void mark_kernel(const long long* __restrict__ ts, long long n, long 
   }
 }
 
+// Build-side table: 16-byte slots {key, row + 1, low 32 bits of the timestamp}: one sector per probe step, the
+// key compared exactly and the timestamp pre-filtered in the slot; the full timestamp of a candidate is read
+// from the build column only when both agree.  row + 1 == 0 marks an empty slot.
+struct alignas(16) JSlot {
+  long long key;
+  unsigned int row1;
+  unsigned int ts_lo;
+};
+
 __global__ void build_kernel(const long long* __restrict__ key, const long long* __restrict__ ts,
-                             const unsigned char* __restrict__ elig, long long n, unsigned int* __restrict__ tab,
-                             uint32_t mask) {
+                             const unsigned char* __restrict__ elig, long long n, JSlot* __restrict__ tab, uint32_t mask) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     if (!elig[i]) continue;
-    uint32_t pos = (uint32_t)pair_hash(key[i], ts[i]) & mask;
-    while (atomicCAS(&tab[pos], 0u, (unsigned int)i + 1u) != 0u) pos = (pos + 1) & mask;
+    const long long k = key[i], t = ts[i];
+    uint32_t pos = (uint32_t)pair_hash(k, t) & mask;
+    while (atomicCAS(&tab[pos].row1, 0u, (unsigned int)i + 1u) != 0u) pos = (pos + 1) & mask;
+    // the probe runs in a later kernel: plain stores are enough for the rest of the slot
+    tab[pos].key = k;
+    tab[pos].ts_lo = (unsigned int)(unsigned long long)t;
   }
 }
 
-// pass 0: cnt[i] = number of output rows of left row i; pass 1: write the pairs at off[i]
+// pass 0: cnt[i] = number of output rows of probe row i; pass 1: write the pairs at off[i].
+// out_p / out_b receive the probe-side / build-side row of each pair (-1 = none).
 template <int PASS>
-__global__ void probe_kernel(const long long* __restrict__ lkey, const long long* __restrict__ lts,
-                             const unsigned char* __restrict__ lelig, long long n_left,
-                             const long long* __restrict__ rkey, const long long* __restrict__ rts,
-                             const unsigned int* __restrict__ tab, uint32_t mask, int keep_unmatched_left,
-                             unsigned int* __restrict__ cnt, const unsigned long long* __restrict__ off,
-                             int* __restrict__ out_l, int* __restrict__ out_r, unsigned char* __restrict__ r_matched) {
+__global__ void probe_kernel(const long long* __restrict__ pkey, const long long* __restrict__ pts,
+                             const unsigned char* __restrict__ pelig, long long n_probe,
+                             const long long* __restrict__ bts, const JSlot* __restrict__ tab, uint32_t mask,
+                             int keep_unmatched_probe, unsigned int* __restrict__ cnt,
+                             const unsigned long long* __restrict__ off, int* __restrict__ out_p, int* __restrict__ out_b,
+                             unsigned char* __restrict__ b_matched) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < n_left; i += stride) {
-    if (!lelig[i]) {
+  for (; i < n_probe; i += stride) {
+    if (!pelig[i]) {
       if (PASS == 0) cnt[i] = 0;
       continue;
     }
-    const long long k = lkey[i], t = lts[i];
+    const long long k = pkey[i], t = pts[i];
+    const unsigned int tlo = (unsigned int)(unsigned long long)t;
     uint32_t pos = (uint32_t)pair_hash(k, t) & mask;
     unsigned int c = 0;
     unsigned long long o = PASS == 1 ? off[i] : 0;
     while (true) {
-      unsigned int e = tab[pos];
-      if (e == 0) break;
-      unsigned int j = e - 1;
-      if (rkey[j] == k && rts[j] == t) {
-        if (PASS == 1) {
-          out_l[o + c] = (int)i;
-          out_r[o + c] = (int)j;
-          r_matched[j] = 1;
+      const ulonglong2 raw = __ldg(reinterpret_cast<const ulonglong2*>(tab + pos));
+      const unsigned int row1 = (unsigned int)raw.y;
+      if (row1 == 0) break;
+      if ((long long)raw.x == k && (unsigned int)(raw.y >> 32) == tlo) {
+        const unsigned int j = row1 - 1;
+        if (__ldg(bts + j) == t) {
+          if (PASS == 1) {
+            out_p[o + c] = (int)i;
+            out_b[o + c] = (int)j;
+            b_matched[j] = 1;
+          }
+          ++c;
         }
-        ++c;
       }
       pos = (pos + 1) & mask;
     }
-    if (c == 0 && keep_unmatched_left) {
+    if (c == 0 && keep_unmatched_probe) {
       if (PASS == 1) {
-        out_l[o] = (int)i;
-        out_r[o] = -1;
+        out_p[o] = (int)i;
+        out_b[o] = -1;
       }
       c = 1;
     }
@@ -114,10 +131,10 @@ __global__ void probe_kernel(const long long* __restrict__ lkey, const long long
   }
 }
 
-// right / full joins: eligible right rows nobody matched, appended after the probe output
+// outer joins: eligible build-side rows nobody matched, appended after the probe output
 __global__ void append_unmatched_kernel(const unsigned char* __restrict__ elig, const unsigned char* __restrict__ matched,
-                                        long long n, unsigned long long* __restrict__ cursor, int* __restrict__ out_l,
-                                        int* __restrict__ out_r) {
+                                        long long n, unsigned long long* __restrict__ cursor, int* __restrict__ out_p,
+                                        int* __restrict__ out_b) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -130,8 +147,8 @@ __global__ void append_unmatched_kernel(const unsigned char* __restrict__ elig, 
     if (lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(b));
     base = __shfl_sync(b, base, leader);
     unsigned long long o = base + __popc(b & ((1u << lane) - 1u));
-    out_l[o] = -1;
-    out_r[o] = (int)i;
+    out_p[o] = -1;
+    out_b[o] = (int)i;
   }
 }
 
@@ -433,34 +450,40 @@ void InstantJoinOp::handle_watermark(int64_t wm, BatchesPriv* out_host, std::vec
 
   const bool keep_l = join_type_ == ARROYO_B200_JOIN_LEFT || join_type_ == ARROYO_B200_JOIN_FULL;
   const bool keep_r = join_type_ == ARROYO_B200_JOIN_RIGHT || join_type_ == ARROYO_B200_JOIN_FULL;
-  // build on the right side
+  // Build on the side with fewer eligible rows (persons under auctions in q8), probe with the other.  The pair
+  // arrays are filled through (probe side, build side) views, so everything downstream is side-agnostic.
+  const int bsd = nl < nr ? 0 : 1;
+  Side& Bs = side_[bsd];
+  Side& Ps = side_[1 - bsd];
+  const int64_t nb = bsd == 0 ? nl : nr;
+  const bool keep_b = bsd == 0 ? keep_l : keep_r, keep_p = bsd == 0 ? keep_r : keep_l;
   uint64_t cap = 1024;
-  while (cap < (uint64_t)nr * 2 + 2) cap <<= 1;
+  while (cap < (uint64_t)nb * 2 + 2) cap <<= 1;
   AB_REQUIRE(cap <= (1ull << 31), ARROYO_B200_RUNTIME, "join build side too large");
-  if (tab_.bytes < cap * 4) tab_.alloc(cap * 4);
-  AB_CUDA(cudaMemsetAsync(tab_.p, 0, cap * 4, stream_));
-  if (r_matched_.bytes < (size_t)std::max<int64_t>(R.n, 1)) r_matched_.alloc((size_t)std::max<int64_t>(R.cap, 1));
-  if (R.n) AB_CUDA(cudaMemsetAsync(r_matched_.p, 0, (size_t)R.n, stream_));
-  if (nr) {
-    build_kernel<<<grid_for(R.n), JT, 0, stream_>>>(R.cols[R.key_col].as<long long>(), R.cols[R.ts_col].as<long long>(),
-                                                   R.elig.as<unsigned char>(), R.n, tab_.as<unsigned int>(), (uint32_t)(cap - 1));
+  if (tab_.bytes < cap * sizeof(JSlot)) tab_.alloc(cap * sizeof(JSlot));
+  AB_CUDA(cudaMemsetAsync(tab_.p, 0, cap * sizeof(JSlot), stream_));
+  if (r_matched_.bytes < (size_t)std::max<int64_t>(Bs.n, 1)) r_matched_.alloc((size_t)std::max<int64_t>(Bs.cap, 1));
+  if (Bs.n) AB_CUDA(cudaMemsetAsync(r_matched_.p, 0, (size_t)Bs.n, stream_));
+  if (nb) {
+    build_kernel<<<grid_for(Bs.n), JT, 0, stream_>>>(Bs.cols[Bs.key_col].as<long long>(), Bs.cols[Bs.ts_col].as<long long>(),
+                                                    Bs.elig.as<unsigned char>(), Bs.n, tab_.as<JSlot>(), (uint32_t)(cap - 1));
     AB_CUDA(cudaGetLastError());
     ++st_.kernel_launches;
   }
   int64_t n_probe_out = 0;
-  if (L.n) {
-    probe_kernel<0><<<grid_for(L.n), JT, 0, stream_>>>(
-        L.cols[L.key_col].as<long long>(), L.cols[L.ts_col].as<long long>(), L.elig.as<unsigned char>(), L.n,
-        R.cols[R.key_col].as<long long>(), R.cols[R.ts_col].as<long long>(), tab_.as<unsigned int>(), (uint32_t)(cap - 1),
-        keep_l ? 1 : 0, L.cnt.as<unsigned int>(), nullptr, nullptr, nullptr, nullptr);
+  if (Ps.n) {
+    probe_kernel<0><<<grid_for(Ps.n), JT, 0, stream_>>>(
+        Ps.cols[Ps.key_col].as<long long>(), Ps.cols[Ps.ts_col].as<long long>(), Ps.elig.as<unsigned char>(), Ps.n,
+        Bs.cols[Bs.ts_col].as<long long>(), tab_.as<JSlot>(), (uint32_t)(cap - 1), keep_p ? 1 : 0,
+        Ps.cnt.as<unsigned int>(), nullptr, nullptr, nullptr, nullptr);
     AB_CUDA(cudaGetLastError());
-    exclusive_scan(L.cnt.as<unsigned int>(), L.n, L.off.as<unsigned long long>(), sc + 4);
+    exclusive_scan(Ps.cnt.as<unsigned int>(), Ps.n, Ps.off.as<unsigned long long>(), sc + 4);
     AB_CUDA(cudaMemcpyAsync(h_scalars_.as<unsigned long long>() + 4, sc + 4, 8, cudaMemcpyDeviceToHost, stream_));
     AB_CUDA(cudaStreamSynchronize(stream_));
     n_probe_out = (int64_t)h_scalars_.as<unsigned long long>()[4];
     ++st_.kernel_launches;
   }
-  const int64_t max_out = n_probe_out + (keep_r ? nr : 0);
+  const int64_t max_out = n_probe_out + (keep_b ? nb : 0);
   AB_REQUIRE(max_out < (int64_t)INT_MAX, ARROYO_B200_RUNTIME, "join output too large for one watermark");
   int64_t n_out = n_probe_out;
   if (max_out > 0) {
@@ -469,20 +492,21 @@ void InstantJoinOp::handle_watermark(int64_t wm, BatchesPriv* out_host, std::vec
       pair_r_.alloc((size_t)max_out * 4);
       pair_cap_ = max_out;
     }
+    int* pair_p = bsd == 0 ? pair_r_.as<int>() : pair_l_.as<int>();
+    int* pair_b = bsd == 0 ? pair_l_.as<int>() : pair_r_.as<int>();
     if (n_probe_out) {
-      probe_kernel<1><<<grid_for(L.n), JT, 0, stream_>>>(
-          L.cols[L.key_col].as<long long>(), L.cols[L.ts_col].as<long long>(), L.elig.as<unsigned char>(), L.n,
-          R.cols[R.key_col].as<long long>(), R.cols[R.ts_col].as<long long>(), tab_.as<unsigned int>(), (uint32_t)(cap - 1),
-          keep_l ? 1 : 0, nullptr, L.off.as<unsigned long long>(), pair_l_.as<int>(), pair_r_.as<int>(),
-          r_matched_.as<unsigned char>());
+      probe_kernel<1><<<grid_for(Ps.n), JT, 0, stream_>>>(
+          Ps.cols[Ps.key_col].as<long long>(), Ps.cols[Ps.ts_col].as<long long>(), Ps.elig.as<unsigned char>(), Ps.n,
+          Bs.cols[Bs.ts_col].as<long long>(), tab_.as<JSlot>(), (uint32_t)(cap - 1), keep_p ? 1 : 0, nullptr,
+          Ps.off.as<unsigned long long>(), pair_p, pair_b, r_matched_.as<unsigned char>());
       AB_CUDA(cudaGetLastError());
       ++st_.kernel_launches;
     }
-    if (keep_r && nr) {
+    if (keep_b && nb) {
       unsigned long long cur = (unsigned long long)n_probe_out;
       AB_CUDA(cudaMemcpyAsync(sc + 5, &cur, 8, cudaMemcpyHostToDevice, stream_));
-      append_unmatched_kernel<<<grid_for(R.n), JT, 0, stream_>>>(R.elig.as<unsigned char>(), r_matched_.as<unsigned char>(),
-                                                                R.n, sc + 5, pair_l_.as<int>(), pair_r_.as<int>());
+      append_unmatched_kernel<<<grid_for(Bs.n), JT, 0, stream_>>>(Bs.elig.as<unsigned char>(), r_matched_.as<unsigned char>(),
+                                                                 Bs.n, sc + 5, pair_p, pair_b);
       AB_CUDA(cudaGetLastError());
       AB_CUDA(cudaMemcpyAsync(h_scalars_.as<unsigned long long>() + 5, sc + 5, 8, cudaMemcpyDeviceToHost, stream_));
       AB_CUDA(cudaStreamSynchronize(stream_));

@@ -5,7 +5,7 @@
 
 namespace ab {
 
-// Exclusive scan of 32-bit counts into 64-bit offsets: block sums, serial scan of the (few) block sums,
+// Exclusive scan of 32-bit counts into 64-bit offsets: block sums, one-block scan of the block sums,
 // then per-block scan.  n is at most a few hundred million: 1024-element blocks.
 constexpr int SCAN_BLOCK = 1024;
 static __global__ void scan_block_sums(const unsigned int* __restrict__ in, long long n, unsigned long long* __restrict__ sums) {
@@ -21,14 +21,42 @@ static __global__ void scan_block_sums(const unsigned int* __restrict__ in, long
     if (threadIdx.x == 0) sums[blockIdx.x] = t;
   }
 }
-static __global__ void scan_sums_serial(unsigned long long* sums, long long n_blocks, unsigned long long* total) {
-  unsigned long long acc = 0;
-  for (long long b = 0; b < n_blocks; ++b) {
-    unsigned long long v = sums[b];
-    sums[b] = acc;
-    acc += v;
+// Exclusive scan of the block sums by one block: 1024 sums per round (warp scans + a scan of the warp totals),
+// a running carry between rounds.  (A single thread walking 10 K sums took 0.25 - 0.55 ms per call.)
+static __global__ void __launch_bounds__(SCAN_BLOCK) scan_sums_block(unsigned long long* sums, long long n_blocks,
+                                                                     unsigned long long* total) {
+  __shared__ unsigned long long s_warp[32];
+  __shared__ unsigned long long s_carry;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (long long base = 0; base < n_blocks; base += SCAN_BLOCK) {
+    const long long i = base + threadIdx.x;
+    const unsigned long long v = i < n_blocks ? sums[i] : 0;
+    unsigned long long x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      const unsigned long long t = s_warp[lane];
+      unsigned long long u = t;
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long y = __shfl_up_sync(0xffffffffu, u, o);
+        if (lane >= o) u += y;
+      }
+      s_warp[lane] = u - t;
+    }
+    __syncthreads();
+    const unsigned long long carry = s_carry;
+    if (i < n_blocks) sums[i] = carry + s_warp[w] + x - v;
+    __syncthreads();
+    if (threadIdx.x == SCAN_BLOCK - 1) s_carry = carry + s_warp[w] + x;
+    __syncthreads();
   }
-  *total = acc;
+  if (threadIdx.x == 0) *total = s_carry;
 }
 static __global__ void scan_apply(const unsigned int* __restrict__ in, long long n, const unsigned long long* __restrict__ sums,
                            unsigned long long* __restrict__ out) {
@@ -67,7 +95,7 @@ inline void device_exclusive_scan(const unsigned int* cnt, int64_t n, unsigned l
     scan_block_sums<<<(unsigned)nb, SCAN_BLOCK, 0, stream>>>(cnt, n, sums.as<unsigned long long>());
     AB_CUDA(cudaGetLastError());
   }
-  scan_sums_serial<<<1, 1, 0, stream>>>(sums.as<unsigned long long>(), nb, total_dev);
+  scan_sums_block<<<1, SCAN_BLOCK, 0, stream>>>(sums.as<unsigned long long>(), nb, total_dev);
   AB_CUDA(cudaGetLastError());
   if (nb > 0) {
     scan_apply<<<(unsigned)nb, SCAN_BLOCK, 0, stream>>>(cnt, n, sums.as<unsigned long long>(), off);
