@@ -89,6 +89,29 @@ struct RowsRef {
 
 __device__ __forceinline__ void set_err(const SessCtx& c, unsigned long long e) { atomicOr(c.ctr + 5, e); }
 
+// Bookkeeping a thread accumulates while it runs its keys' state machines; published once per warp at the end of
+// the kernel.  (One global atomic per event on four shared counters serialised the whole kernel: tens of millions
+// of same-address atomics per launch.)
+struct Tally {
+  unsigned long long dead_nodes = 0, dead_rows = 0;
+  long long open = 0;
+};
+__device__ __forceinline__ void publish_tally(const SessCtx& c, const Tally& t) {
+  unsigned long long dn = t.dead_nodes, dr = t.dead_rows;
+  long long op = t.open;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dn += __shfl_xor_sync(0xffffffffu, dn, o);
+    dr += __shfl_xor_sync(0xffffffffu, dr, o);
+    op += __shfl_xor_sync(0xffffffffu, op, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (dn) atomicAdd(c.ctr + 2, dn);
+    if (dr) atomicAdd(c.ctr + 3, dr);
+    if (op) atomicAdd(c.ctr + 7, (unsigned long long)op);
+  }
+}
+
 __device__ void acc_reset(const SessCtx& c, uint32_t id) {
   for (int a = 0; a < c.n_acc; ++a) {
     unsigned long long v = 0;
@@ -175,6 +198,19 @@ __device__ int alloc_node(const SessCtx& c, long long start, long long off, int 
   return (int)i;
 }
 
+// node `i` was reserved for the caller (apply_kernel hands every run the slot of its first row)
+__device__ int init_node(const SessCtx& c, unsigned long long i, long long start, long long off, int len) {
+  if (i >= c.node_cap) {
+    set_err(c, ERR_POOL);
+    return -1;
+  }
+  c.n_next[i] = -1;
+  c.n_start[i] = start;
+  c.n_off[i] = off;
+  c.n_len[i] = len;
+  return (int)i;
+}
+
 // by_start.entry(start).or_default().push(node): ordered by start, after the nodes with the same start
 __device__ void pending_insert(const SessCtx& c, uint32_t id, int node) {
   if (node < 0) return;
@@ -204,7 +240,7 @@ __device__ RowsRef pool_rows(const SessCtx& c, int node) {
 }
 
 // KeyComputingHolder::fill_active_session (:610-643)
-__device__ void fill_active_session(const SessCtx& c, uint32_t id) {
+__device__ void fill_active_session(const SessCtx& c, uint32_t id, Tally& tally) {
   int guard = 0;
   while (true) {
     if (++guard > LOOP_GUARD) {
@@ -237,25 +273,25 @@ __device__ void fill_active_session(const SessCtx& c, uint32_t id) {
       if (active_add_batch(c, id, r, &rem_lo)) {
         const int nn = alloc_node(c, r.ts[r.off + rem_lo], r.off + rem_lo, r.n - rem_lo);
         pending_insert(c, id, nn);
-        atomicAdd(c.ctr + 3, (unsigned long long)rem_lo);
+        tally.dead_rows += (unsigned long long)rem_lo;
       } else {
-        atomicAdd(c.ctr + 3, (unsigned long long)r.n);
+        tally.dead_rows += (unsigned long long)r.n;
       }
-      atomicAdd(c.ctr + 2, 1ull);
+      tally.dead_nodes += 1;
       node = next;
     }
   }
 }
 
 // ActiveSession::finish (:494-523) + to_record_batch (:316-382): one output row
-__device__ void finish_session(const SessCtx& c, uint32_t id) {
+__device__ void finish_session(const SessCtx& c, uint32_t id, Tally& tally) {
   const unsigned long long o = atomicAdd(c.ctr + 4, 1ull);
   if (o >= c.out_cap) {
     // cannot happen (the host sizes the output for one session per live row): still close the session so the
     // caller's loop makes progress, and report
     set_err(c, ERR_OUT);
     c.active[id] = 0;
-    atomicAdd(c.ctr + 7, (unsigned long long)-1ll);
+    tally.open -= 1;
     return;
   }
   const long long start = c.data_start[id], end = c.data_end[id] + c.gap;
@@ -277,11 +313,11 @@ __device__ void finish_session(const SessCtx& c, uint32_t id) {
     c.o_agg[g][o] = v;
   }
   c.active[id] = 0;
-  atomicAdd(c.ctr + 7, (unsigned long long)-1ll);
+  tally.open -= 1;
 }
 
 // KeyComputingHolder::watermark_update (:557-603)
-__device__ void watermark_update(const SessCtx& c, uint32_t id, long long wm, bool in_add) {
+__device__ void watermark_update(const SessCtx& c, uint32_t id, long long wm, bool in_add, Tally& tally) {
   int guard = 0;
   while (true) {
     if (++guard > LOOP_GUARD) {
@@ -291,7 +327,7 @@ __device__ void watermark_update(const SessCtx& c, uint32_t id, long long wm, bo
     if (c.active[id]) {
       if (c.data_end[id] + c.gap < wm) {
         if (in_add) set_err(c, ERR_ADD_FLUSHED);  // "should not have flushed batches when adding a batch" (:672-675)
-        finish_session(c, id);
+        finish_session(c, id, tally);
       } else {
         break;
       }
@@ -304,28 +340,20 @@ __device__ void watermark_update(const SessCtx& c, uint32_t id, long long wm, bo
       c.data_start[id] = initial;
       c.data_end[id] = initial;
       acc_reset(c, id);
-      atomicAdd(c.ctr + 7, 1ull);
-      fill_active_session(c, id);
+      tally.open += 1;
+      fill_active_session(c, id, tally);
     }
   }
 }
 
-// KeyComputingHolder::add_batch (:645-677) for one run of `id`
-__device__ void add_run(const SessCtx& c, uint32_t id, const RowsRef& run, int has_wm, long long wm) {
-  // the run is stored under its start time: its rows move to the row pool
-  const unsigned long long off = atomicAdd(c.ctr + 1, (unsigned long long)run.n);
-  if (off + (unsigned long long)run.n > c.row_cap) {
-    set_err(c, ERR_POOL);
-    return;
-  }
-  for (int i = 0; i < run.n; ++i) {
-    c.r_ts[off + i] = run.ts[run.off + i];
-    for (int v = 0; v < c.n_vals; ++v) c.r_val[v][off + i] = run.val[v][run.off + i];
-  }
-  pending_insert(c, id, alloc_node(c, run.ts[run.off], (long long)off, run.n));
+// KeyComputingHolder::add_batch (:645-677) for one run of `id`.  The run's rows already sit in the row pool at
+// `pool_off` (the grouping pass scatters straight into it) and `node` is the slot reserved for it.
+__device__ void add_run(const SessCtx& c, uint32_t id, unsigned long long node, long long pool_off, int n, int has_wm,
+                        long long wm, Tally& tally) {
+  pending_insert(c, id, init_node(c, node, c.r_ts[pool_off], pool_off, n));
   if (!has_wm) return;
-  if (c.active[id]) fill_active_session(c, id);
-  watermark_update(c, id, wm, true);
+  if (c.active[id]) fill_active_session(c, id, tally);
+  watermark_update(c, id, wm, true, tally);
 }
 
 // ---- kernels --------------------------------------------------------------------------------------------
@@ -354,22 +382,35 @@ __global__ void __launch_bounds__(ST) prep_kernel(const __grid_constant__ PrepPa
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   unsigned long long late = 0;
-  for (; i < p.n; i += stride) {
-    const long long ts = __ldcs(p.ts + i);
-    if (p.has_wm && ts < p.wm) {  // K7: gt_eq(timestamp, watermark) filter (:858-868)
-      ++late;
-      continue;
-    }
+  const int lane = threadIdx.x & 31;
+  // uniform trip count: the arena slots of a warp's rows come from one atomic per warp iteration
+  const long long n_round = (p.n + stride - 1) / stride * stride;
+  for (; i < n_round; i += stride) {
+    bool keep = i < p.n;
+    long long ts = 0;
     uint32_t id = 0;
-    if (p.keyed) {
+    if (keep) {
+      ts = __ldcs(p.ts + i);
+      if (p.has_wm && ts < p.wm) {  // K7: gt_eq(timestamp, watermark) filter (:858-868)
+        ++late;
+        keep = false;
+      }
+    }
+    if (keep && p.keyed) {
       const long long key = __ldcs(p.key + i);
       id = key == EMPTY_KEY ? 0u : dict_insert(p.dict, key, dict_home((uint64_t)key, p.dict.cap));
       if (id >= ID_OVERFLOW) {
         atomicOr(p.ctr + 5, (unsigned long long)ERR_POOL);
-        continue;
+        keep = false;
       }
     }
-    const unsigned long long o = atomicAdd(p.ctr + 6, 1ull);
+    const unsigned int kept = __ballot_sync(0xffffffffu, keep);
+    if (!kept) continue;
+    unsigned long long base = 0;
+    if (lane == __ffs(kept) - 1) base = atomicAdd(p.ctr + 6, (unsigned long long)__popc(kept));
+    base = __shfl_sync(0xffffffffu, base, __ffs(kept) - 1);
+    if (!keep) continue;
+    const unsigned long long o = base + __popc(kept & ((1u << lane) - 1u));
     if (o >= p.arena_cap) {
       atomicOr(p.ctr + 5, (unsigned long long)ERR_POOL);
       continue;
@@ -416,8 +457,9 @@ struct ApplyParams {
   unsigned int* cursor;
   const unsigned long long* offset;
   unsigned int* g_seq;
-  long long* g_ts;
+  long long* g_ts;       // row pool + row_base: the grouping pass wrote this launch's rows straight into the pool
   long long* g_val[SV];
+  unsigned long long row_base, node_base;  // pool positions of grouped row 0 / of the node slot of grouped row 0
   int has_wm;
   long long wm;
 };
@@ -425,6 +467,7 @@ struct ApplyParams {
 __global__ void __launch_bounds__(128) apply_kernel(const __grid_constant__ ApplyParams p) {
   unsigned int id = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned int stride = gridDim.x * blockDim.x;
+  Tally tally;
   for (; id < p.n_ids; id += stride) {
     const unsigned int cnt = p.count[id];
     if (!cnt) continue;
@@ -448,20 +491,18 @@ __global__ void __launch_bounds__(128) apply_kernel(const __grid_constant__ Appl
       p.g_ts[off + j + 1] = t;
       for (int v = 0; v < p.c.n_vals; ++v) p.g_val[v][off + j + 1] = vv[v];
     }
-    // one run per input batch, in arrival order
-    unsigned int lo = 0;
+    // one run per input batch, in arrival order; a run's node is the slot of its first row
+    unsigned int lo = 0, runs = 0;
     while (lo < cnt) {
       unsigned int hi = lo + 1;
       while (hi < cnt && p.g_seq[off + hi] == p.g_seq[off + lo]) ++hi;
-      RowsRef run;
-      run.ts = p.g_ts;
-      for (int v = 0; v < SV; ++v) run.val[v] = p.g_val[v];
-      run.off = (long long)(off + lo);
-      run.n = (int)(hi - lo);
-      add_run(p.c, id, run, p.has_wm, p.wm);
+      add_run(p.c, id, p.node_base + off + lo, (long long)(p.row_base + off + lo), (int)(hi - lo), p.has_wm, p.wm, tally);
+      ++runs;
       lo = hi;
     }
+    tally.dead_nodes += cnt - runs;  // reserved node slots that no run uses
   }
+  publish_tally(p.c, tally);
 }
 
 struct AdvanceParams {
@@ -473,6 +514,7 @@ struct AdvanceParams {
 __global__ void __launch_bounds__(128) advance_kernel(const __grid_constant__ AdvanceParams p) {
   unsigned int id = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned int stride = gridDim.x * blockDim.x;
+  Tally tally;
   for (; id < p.n_ids; id += stride) {
     const int h = p.c.head[id];
     const bool act = p.c.active[id] != 0;
@@ -480,8 +522,9 @@ __global__ void __launch_bounds__(128) advance_kernel(const __grid_constant__ Ad
     // next_watermark_action (:536-546); only keys whose action time is before the watermark advance (:62-74)
     const __int128 action = act ? (__int128)p.c.data_end[id] + p.c.gap : (__int128)p.c.n_start[h] - p.c.gap;
     if (!(action < (__int128)p.wm)) continue;
-    watermark_update(p.c, id, p.wm, false);
+    watermark_update(p.c, id, p.wm, false, tally);
   }
+  publish_tally(p.c, tally);
 }
 
 // pool compaction: live nodes / rows per key -> offsets -> copy
@@ -1035,11 +1078,19 @@ void SessionOp::apply_pending() {
   g.n_vals = n_vals_;
   g.offset = offset_.as<unsigned long long>();
   g.cursor = cursor_.as<unsigned int>();
+  // This launch's rows go straight into the row pool at [row_base, row_base + n) in grouped order, and grouped
+  // row i owns node slot node_base + i: no allocation atomics in the per-key state machines (remainder nodes, the
+  // only other allocation, come from the cursor behind the reserved range).
+  const SessCtx cx = ctx();
+  const unsigned long long row_base = h_ctr_.as<unsigned long long>()[1], node_base = h_ctr_.as<unsigned long long>()[0];
+  AB_REQUIRE(row_base + n <= cx.row_cap && node_base + n <= cx.node_cap, ARROYO_B200_RUNTIME, "session pools too small");
+  const unsigned long long cur2[2] = {node_base + n, row_base + n};
+  AB_CUDA(cudaMemcpyAsync(ctr_.as<unsigned long long>(), cur2, sizeof cur2, cudaMemcpyHostToDevice, stream_));
   g.g_seq = g_seq_.as<unsigned int>();
-  g.g_ts = g_ts_.as<long long>();
+  g.g_ts = cx.r_ts + row_base;
   for (int v = 0; v < n_vals_; ++v) {
     g.a_val[v] = a_val_[v].as<long long>();
-    g.g_val[v] = g_val_[v].as<long long>();
+    g.g_val[v] = cx.r_val[v] + row_base;
   }
   group_kernel<<<grid_for(n, ST), ST, 0, stream_>>>(g);
   AB_CUDA(cudaGetLastError());
@@ -1050,8 +1101,10 @@ void SessionOp::apply_pending() {
   a.cursor = cursor_.as<unsigned int>();
   a.offset = offset_.as<unsigned long long>();
   a.g_seq = g_seq_.as<unsigned int>();
-  a.g_ts = g_ts_.as<long long>();
-  for (int v = 0; v < n_vals_; ++v) a.g_val[v] = g_val_[v].as<long long>();
+  a.g_ts = cx.r_ts + row_base;
+  for (int v = 0; v < n_vals_; ++v) a.g_val[v] = cx.r_val[v] + row_base;
+  a.row_base = row_base;
+  a.node_base = node_base;
   a.has_wm = has_wm_ ? 1 : 0;
   a.wm = wm_;
   apply_kernel<<<grid_for(n_keys_, 128), 128, 0, stream_>>>(a);

@@ -918,6 +918,10 @@ class WindowAggOp final : public OpBase {
   int64_t chunk_rows_ = 1 << 23;
   DevBuf chunk_[NCHUNK];
   cudaEvent_t chunk_free_[NCHUNK] = {nullptr, nullptr, nullptr};
+  // host batches are staged by the copy engine on their own stream, so the link never waits for an ingest kernel:
+  // copy stream --copied_--> compute stream (kernel reads the chunk) --chunk_free_--> copy stream (chunk reused)
+  cudaStream_t copy_stream_ = nullptr;
+  cudaEvent_t copied_ = nullptr;
   int cur_chunk_ = 0;
   int64_t cur_rows_ = 0;
   std::vector<Segment> segs_;
@@ -1126,6 +1130,10 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
   const int n_used = 2 + n_vals_;
   for (int i = 0; i < NCHUNK; ++i) {
     AB_CUDA(cudaEventCreateWithFlags(&chunk_free_[i], cudaEventDisableTiming));
+    if (i == 0) {
+      AB_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+      AB_CUDA(cudaEventCreateWithFlags(&copied_, cudaEventDisableTiming));
+    }
   }
   (void)n_used;
   for (int i = 0; i < NLAUNCH; ++i) {
@@ -1164,6 +1172,11 @@ WindowAggOp::~WindowAggOp() {
   for (auto e : ev_pool_) cudaEventDestroy(e);
   for (int i = 0; i < NCHUNK; ++i)
     if (chunk_free_[i]) cudaEventDestroy(chunk_free_[i]);
+  if (copy_stream_) {
+    cudaStreamSynchronize(copy_stream_);
+    cudaStreamDestroy(copy_stream_);
+    cudaEventDestroy(copied_);
+  }
   for (int i = 0; i < NLAUNCH; ++i) {
     if (launches_[i].done) cudaEventDestroy(launches_[i].done);
     if (launches_[i].t0) cudaEventDestroy(launches_[i].t0);
@@ -1465,7 +1478,7 @@ void WindowAggOp::flush_copies() {
     at.flags = cudaMemcpyFlagPreferOverlapWithCompute;
     size_t idx = 0, fail = 0;
     cudaError_t e = cudaMemcpyBatchAsync(copy_dst_.data(), copy_src_.data(), copy_size_.data(), n, &at, &idx, 1, &fail,
-                                         stream_);
+                                         copy_stream_);
     if (e == cudaSuccess) {
       done = true;
     } else if (e == cudaErrorNotSupported || e == cudaErrorInvalidValue) {
@@ -1478,7 +1491,7 @@ void WindowAggOp::flush_copies() {
 #endif
   if (!done)
     for (size_t i = 0; i < n; ++i)
-      AB_CUDA(cudaMemcpyAsync(copy_dst_[i], copy_src_[i], copy_size_[i], cudaMemcpyHostToDevice, stream_));
+      AB_CUDA(cudaMemcpyAsync(copy_dst_[i], copy_src_[i], copy_size_[i], cudaMemcpyHostToDevice, copy_stream_));
   copy_dst_.clear();
   copy_src_.clear();
   copy_size_.clear();
@@ -1496,7 +1509,7 @@ void WindowAggOp::seal_release() {
   } else {
     AB_CUDA(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
   }
-  AB_CUDA(cudaEventRecord(r.ev, stream_));
+  AB_CUDA(cudaEventRecord(r.ev, copy_stream_));
   r.arrs.swap(open_release_);
   releases_.push_back(std::move(r));
 }
@@ -1544,8 +1557,9 @@ void WindowAggOp::add_segment(const long long* key, const long long* ts, const l
 void WindowAggOp::rotate_chunk() {
   cur_chunk_ = (cur_chunk_ + 1) % NCHUNK;
   cur_rows_ = 0;
-  // the launch that last read this chunk must have finished
-  AB_CUDA(cudaEventSynchronize(chunk_free_[cur_chunk_]));
+  // the launch that last read this chunk must have finished before the copy engine writes it again (a wait on
+  // the copy stream, not on the host)
+  AB_CUDA(cudaStreamWaitEvent(copy_stream_, chunk_free_[cur_chunk_], 0));
 }
 
 void WindowAggOp::process_batch(uint32_t, uint32_t, ArrowArray* batch, const ArrowSchema* schema) {
@@ -1849,6 +1863,11 @@ void WindowAggOp::launch_pending() {
   pending_rows_ = 0;
   int chunk = pending_uses_chunk_ ? cur_chunk_ : -1;
   pending_uses_chunk_ = false;
+  if (chunk >= 0) {
+    // the kernel reads staged rows: it runs behind the copies that were queued up to here
+    AB_CUDA(cudaEventRecord(copied_, copy_stream_));
+    AB_CUDA(cudaStreamWaitEvent(stream_, copied_, 0));
+  }
   launch_segments(segs, chunk);
   if (!zero_copy_inputs_.empty()) {
     // the pinned input batches these segments point into may be released once this kernel has run
