@@ -503,7 +503,8 @@ def bench(args, torch, dist, rank, world, local):
                           "keys": args.keys, "rows_per_step_per_gpu": rows, "batch_rows": B.BATCH_ROWS,
                           "shuffle": ("partial aggregates per pane (partial -> shuffle -> final)" if mode == "partials"
                                       else "raw rows (reference plan shape)"),
-                          "l2": "inputs larger than L2, never re-read", "parallelism": f"key-partitioned x{world}"},
+                          "l2": "inputs larger than L2, never re-read", "parallelism": f"key-partitioned x{world}",
+                          "numa": getattr(args, "numa", None)},
                "rows_out_per_step": int(tot[1].item()) / max(K, 1), "gpu_launches": int(tot[0].item()),
                "roofline": {"bound": "hbm", "kernel": "ingest_kernel<1>",
                             "achieved": round(ingest_gbs, 1) if ingest_gbs else None, "peak": peak,

@@ -64,6 +64,8 @@ def parse():
     ap.add_argument("--e2e-host", default="library", choices=["library", "python"],
                     help="e2e run loop: arroyo_b200_op_run_batches (the loop a compiled shim would run, inside the "
                          "library) or one ctypes call per batch from Python")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="do not bind the process to the CPUs local to its GPU (NVML affinity)")
     ap.add_argument("--sync-emit", action="store_true",
                     help="e2e: blocking arroyo_b200_op_handle_watermark instead of the begin / poll pair")
     ap.add_argument("--no-direct", action="store_true", help="measurement knob: hash dense keys as well")
@@ -294,6 +296,26 @@ def build_batch_lists(torch, panes, rows_per_pane):
     return plans
 
 
+def bind_to_gpu_numa_node(local):
+    """Pins this process to the CPUs NVML reports as local to GPU `local`, before any pinned host memory is
+    allocated (first touch then places it on the GPU's NUMA node).  On this pool's two-socket hosts a process that
+    lands on the other socket moves host<->device data at about 20 GB/s instead of 55.  Returns a description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return "unchanged (no overlap with the allowed CPUs)"
+        os.sched_setaffinity(0, cpus)
+        return f"process bound to the {len(cpus)} CPUs local to GPU {local}"
+    except Exception as e:  # noqa: BLE001
+        return f"unchanged ({type(e).__name__}: {e})"
+
+
 def device_resident(args, torch, native, ffi, local, gen_pane, W, K, rows):
     """W warm-up + K timed steps with the input already in HBM; CUDA events on the operator's stream.
     Returns (ms, stats delta, rows emitted, clocks)."""
@@ -350,6 +372,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    args.numa = "not bound" if args.no_numa_bind else bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if ffi.load().arroyo_b200_device_count() < 1:
@@ -396,7 +419,8 @@ def run_ours(args):
                       "emission": "remerge" if args.remerge else "running add/evict",
                       "avg": "f64 accumulator" if args.avg_f64 else "exact integer sum (guarded)",
                       "combine": not args.no_combine,
-                      "l2": "inputs larger than L2 (402 MB per step, never re-read)", "parallelism": "1 gpu"},
+                      "l2": "inputs larger than L2 (402 MB per step, never re-read)", "parallelism": "1 gpu",
+                      "numa": args.numa},
            "rows_out_per_step": rows_out / max(K, 1), "gpu_launches": int(d["kernel_launches"]),
            "roofline": roof, "clocks": clocks}
 
