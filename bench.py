@@ -372,6 +372,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    all_cpus = os.sched_getaffinity(0)
     args.numa = "not bound" if args.no_numa_bind else bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -440,6 +441,7 @@ def run_ours(args):
     if not args.skip_e2e:
         out["e2e"] = run_e2e(args, torch, device, local, gen_pane)
     if not args.skip_cpu:
+        os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core again
         cpu = run_cpu(torch, args, device, budget_s=25.0, warm_panes=11, timed_panes=3)
         out["cpu_baseline"] = {"value": cpu["rows_per_s"], "unit": "rows/s", "cores": cpu["threads"], "kind": "port",
                                "sample": cpu["sample"]}
