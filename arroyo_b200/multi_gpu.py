@@ -56,17 +56,20 @@ class DevicePartitioner:
             raise ffi.ArroyoB200Error(st, "partition failed")
         return [o[:n_rows] for o in self.out], self.counts
 
-    def pack(self, col_ptrs: Sequence[int], n_rows: int):
+    def pack(self, col_ptrs: Sequence[int], n_rows: int, counts_out=None):
         """arroyo_b200_partition_packed: `col_ptrs` are raw device pointers; returns (packed buffer,
-        counts[world] device tensor).  Destination d's block holds its n_cols columns back to back."""
+        counts[world] device tensor).  Destination d's block holds its n_cols columns back to back.
+        `counts_out`: device tensor whose first `world` int64 receive the counts (e.g. the exchange's control
+        record) instead of the partitioner's own."""
         if self._packed is None:
             self._packed = self.torch.empty(self.max_rows * self.n_cols, dtype=self.torch.int64, device=self._dev)
         inp = (C.c_uint64 * self.n_cols)(*col_ptrs)
-        st = self.lib.arroyo_b200_partition_packed(self.h, inp, n_rows, self._packed.data_ptr(), self.counts.data_ptr(),
+        counts = self.counts if counts_out is None else counts_out
+        st = self.lib.arroyo_b200_partition_packed(self.h, inp, n_rows, self._packed.data_ptr(), counts.data_ptr(),
                                                    self.offsets.data_ptr())
         if st != ffi.OK:
             raise ffi.ArroyoB200Error(st, "partition_packed failed")
-        return self._packed[:n_rows * self.n_cols], self.counts
+        return self._packed[:n_rows * self.n_cols], counts
 
     def close(self):
         if self.h:
@@ -93,6 +96,11 @@ class ShuffleExchange:
         # and whether the sender has more rounds queued behind this one
         self.ctrl = torch.zeros(world + 2, dtype=torch.int64, device=device)
         self.ctrl_all = torch.zeros(world * (world + 2), dtype=torch.int64, device=device)
+        # the two host-written words of a control record (watermark, more-rounds flag) go through one pinned
+        # staging tensor: one small async copy per round instead of one tensor op per word
+        self._ctl_host = torch.zeros(2, dtype=torch.int64)
+        if device.type == "cuda":
+            self._ctl_host = self._ctl_host.pin_memory()
         self._recv = None
         self._recv_packed = None
         self._flip = 0
@@ -105,8 +113,9 @@ class ShuffleExchange:
         """Broadcasts this sender's watermark (or none) and returns the min-merged effective watermark if it
         advanced (signals go to every downstream queue, context.rs:663-677; merge = WatermarkHolder)."""
         torch, dist, W = self.torch, self.dist, self.world
-        self.ctrl.zero_()
-        self.ctrl[W] = NO_WM if watermark is None else int(min(watermark, (1 << 63) - 1))
+        self._ctl_host[0] = NO_WM if watermark is None else int(min(watermark, (1 << 63) - 1))
+        self._ctl_host[1] = 0
+        self.ctrl[W:].copy_(self._ctl_host, non_blocking=True)  # the count words are not read by this exchange
         dist.all_gather_into_tensor(self.ctrl_all, self.ctrl)
         m = self.ctrl_all.view(W, W + 2)[:, W].cpu().tolist()
         before = self.holder.last_present_watermark
@@ -159,11 +168,13 @@ class ShuffleExchange:
         buffer alternates between two allocations, so a batch stays valid until the round after next."""
         torch, dist, W, nc = self.torch, self.dist, self.world, self.n_cols
         if n_rows > 0:
-            self.ctrl[:W] = counts
+            if counts.data_ptr() != self.ctrl.data_ptr():  # DevicePartitioner.pack(counts_out=ctrl) writes in place
+                self.ctrl[:W] = counts
         else:
             self.ctrl[:W] = 0
-        self.ctrl[W] = NO_WM if watermark is None else int(min(watermark, (1 << 63) - 1))
-        self.ctrl[W + 1] = 1 if more else 0
+        self._ctl_host[0] = NO_WM if watermark is None else int(min(watermark, (1 << 63) - 1))
+        self._ctl_host[1] = 1 if more else 0
+        self.ctrl[W:].copy_(self._ctl_host, non_blocking=True)
         dist.all_gather_into_tensor(self.ctrl_all, self.ctrl)
         m = self.ctrl_all.view(W, W + 2).cpu()
         send_rows = m[self.rank, :W].tolist()
@@ -265,7 +276,7 @@ class PartialsPlan:
         while True:
             if i < len(chunks):
                 cols, m = chunks[i]
-                packed, counts = self.part.pack(cols, m)
+                packed, counts = self.part.pack(cols, m, counts_out=self.ex.ctrl)
             else:
                 packed, counts, m = None, None, 0
             i += 1
