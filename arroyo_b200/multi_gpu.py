@@ -244,7 +244,8 @@ class PartialsPlan:
         # stream=0: the operator creates its own non-blocking stream
         self.local_op = native.TumblingAggregatingWindowFunc(local_cfg, input_schema=raw_schema, device=local, stream=0,
                                                              flags=local_flags, expected_keys=args.keys,
-                                                             task_index=rank, parallelism=world)
+                                                             task_index=rank, parallelism=world,
+                                                             chunk_log2=getattr(args, "local_chunk_log2", 21))
         owner_cfg = ab.WindowAggConfig(width=B.WIDTH, slide=B.SLIDE, key_names=["key"],
                                        aggs=[ab.Agg("sum", "sum", "sum"), ab.Agg("avg", "sum", "avg"),
                                              ab.Agg("count", None, "count")], window_index=1, partial_count_col="count")

@@ -69,6 +69,9 @@ def parse():
     ap.add_argument("--sync-emit", action="store_true",
                     help="e2e: blocking arroyo_b200_op_handle_watermark instead of the begin / poll pair")
     ap.add_argument("--no-direct", action="store_true", help="measurement knob: hash dense keys as well")
+    ap.add_argument("--local-chunk-log2", type=int, default=21,
+                    help="N>1, partials: rows per ingest launch of the local stage = 2^n; short launches let the owner "
+                         "stage's kernels in between")
     ap.add_argument("--shuffle", default="partials", choices=["partials", "rows"],
                     help="N>1: what crosses the all-to-all (per-pane partial aggregates, or raw rows)")
     return ap.parse_args()
@@ -382,7 +385,9 @@ def run_ours(args):
     device = torch.device("cuda", local)
     # one explicit CUDA stream for torch and the operator: the CUDA events below are recorded on the stream the
     # kernels are launched on (a stream handle of 0 would make the operator create a private stream)
-    torch.cuda.set_stream(torch.cuda.Stream(device=device))
+    # (high priority: at N > 1 the exchange and the owner stage run on it while the local stage's ingest kernels
+    # fill the GPU from another stream)
+    torch.cuda.set_stream(torch.cuda.Stream(device=device, priority=-1))
     if world > 1:
         from arroyo_b200 import multi_gpu
         return multi_gpu.bench(args, torch, dist, rank, world, local)
