@@ -291,10 +291,155 @@ class PartialsPlan:
             self.owner_op.flush()  # more rounds follow: the receive buffers come round again
         sink(self.owner_op, eff)
 
+    def pipeline(self, sink, lag: int = 2):
+        """LaggedCombiner over this plan's operators; `sink(owner_op, eff)` emits."""
+        torch = self.torch
+        dev = torch.cuda.current_device()
+        stream = torch.cuda.current_stream()
+
+        def thread_init():
+            torch.cuda.set_device(dev)
+            torch.cuda.set_stream(stream)  # the current stream is per thread
+
+        def local_close(eff):
+            chunks = []
+            for n, cols in self.local_op.handle_watermark_device(eff):
+                for o in range(0, n, self.part_rows):
+                    chunks.append(([c + 8 * o for c in cols], min(self.part_rows, n - o)))
+            return chunks
+
+        def pack(chunk):
+            cols, m = chunk
+            packed, counts = self.part.pack(cols, m, counts_out=self.ex.ctrl)
+            return packed, counts, m
+
+        def owner_ingest(batches, consume_now):
+            flat = (C.c_uint64 * (self.N_COLS * len(batches)))(*[p for cols, _ in batches for p in cols])
+            nr = (C.c_int64 * len(batches))(*[r for _, r in batches])
+            self.owner_op.process_device_batches(flat, nr, self.N_COLS)
+            if consume_now:
+                self.owner_op.flush()
+
+        return LaggedCombiner(self.ex, local_close, pack, owner_ingest, lambda eff: sink(self.owner_op, eff), lag=lag,
+                              thread_init=thread_init)
+
     def close(self):
         self.owner_op.close()
         self.local_op.close()
         self.part.close()
+
+
+class LaggedCombiner:
+    """The combiner plan as a two-stage software pipeline on one rank.
+
+    The local stage (caller's thread) and the shuffle edge + owner stage (a second host thread) are different
+    operators of the dataflow, connected by a queue -- exactly as in the reference, where every operator is its own
+    task.  Watermarks ride on the data rounds (they are in-band signals of the edge): round p carries this rank's
+    watermark after step p and the partial rows of the panes the local stage closed in step p.  The local stage closes
+    panes with the effective watermark that came out of round p - lag, so it never waits for the round in flight;
+    every rank uses the same (deterministic) lag, hence the same effective watermark for the same step.
+
+    Callbacks (all on device pointers or host arrays -- the class only sequences them):
+      local_close(eff) -> [chunk]            panes the local stage closes at `eff` (its output buffers must stay valid
+                                             until the chunk was packed; `local_step` waits for that)
+      pack(chunk) -> (packed, counts, rows)  arroyo_b200_partition_packed (or its CPU restatement)
+      owner_ingest([(cols, rows)], consume_now)  partial rows received in a round (`consume_now`: the buffers are
+                                             about to be reused and no owner_watermark call follows)
+      owner_watermark(eff)                   the owner stage's handle_watermark"""
+
+    def __init__(self, ex, local_close, pack, owner_ingest, owner_watermark, lag: int = 2, thread_init=None):
+        import queue
+        import threading
+        self.ex, self.lag = ex, lag
+        self.local_close, self.pack = local_close, pack
+        self.owner_ingest, self.owner_watermark = owner_ingest, owner_watermark
+        self.thread_init = thread_init
+        self.q = queue.Queue()
+        self.cv = threading.Condition()
+        self.eff_after = {}      # step -> effective watermark after that step's rounds
+        self.packed_upto = -1    # last step whose chunks have left the local stage's buffers
+        self.step = 0
+        self.last_closed = None
+        self.error = None
+        self.th = threading.Thread(target=self._owner_loop, daemon=True)
+        self.th.start()
+
+    # ---- local stage (caller's thread) ----
+    def local_step(self, feed_first, feed_rest, watermark):
+        p = self.step
+        self.step += 1
+        feed_first()
+        eff = None
+        with self.cv:
+            if p - self.lag >= 0:
+                self.cv.wait_for(lambda: (p - self.lag) in self.eff_after or self.error is not None)
+                self._raise()
+                eff = self.eff_after.pop(p - self.lag)
+            # the previous step's partial rows must have been packed before the local stage overwrites them
+            self.cv.wait_for(lambda: self.packed_upto >= p - 1 or self.error is not None)
+            self._raise()
+        chunks, closing = [], None
+        if eff is not None and eff != self.last_closed:
+            chunks = self.local_close(eff)
+            closing = self.last_closed = eff
+        feed_rest()
+        self.q.put((p, closing, chunks, watermark))
+
+    def drain(self):
+        """Waits until the owner stage has consumed everything queued so far."""
+        with self.cv:
+            self.cv.wait_for(lambda: self.packed_upto >= self.step - 1 and self.q.unfinished_tasks == 0
+                             or self.error is not None)
+            self._raise()
+
+    def close(self):
+        self.q.put(None)
+        self.th.join()
+        self._raise()
+
+    def _raise(self):
+        if self.error is not None:
+            raise RuntimeError(f"owner stage failed: {self.error!r}")
+
+    # ---- shuffle edge + owner stage (second thread) ----
+    def _owner_loop(self):
+        try:
+            if self.thread_init:
+                self.thread_init()
+            while True:
+                item = self.q.get()
+                if item is None:
+                    self.q.task_done()
+                    return
+                p, closing, chunks, wm = item
+                i = 0
+                while True:
+                    if i < len(chunks):
+                        packed, counts, m = self.pack(chunks[i])
+                    else:
+                        packed, counts, m = None, None, 0
+                    i += 1
+                    batches, _, any_more = self.ex.round_packed(packed, counts, m, wm if i == 1 else None,
+                                                                more=i < len(chunks))
+                    if batches:
+                        # the receive buffers come round again two rounds later: rows that no watermark is about to
+                        # push through the owner must be consumed now
+                        self.owner_ingest(batches, consume_now=any_more or closing is None)
+                    if not any_more:
+                        break
+                with self.cv:
+                    self.packed_upto = p
+                    self.eff_after[p] = self.ex.holder.last_present_watermark
+                    self.cv.notify_all()
+                if closing is not None:
+                    self.owner_watermark(closing)
+                self.q.task_done()
+                with self.cv:
+                    self.cv.notify_all()
+        except BaseException as e:  # noqa: BLE001
+            with self.cv:
+                self.error = e
+                self.cv.notify_all()
 
 
 def _wm_point(wms, p, nb):
@@ -427,17 +572,29 @@ def bench(args, torch, dist, rank, world, local):
         for n, _ in owner_op.handle_watermark_device(eff):
             rows_out += n
 
+    pipe = plan.pipeline(lambda op, w: emit(w)) if (plan is not None and not args.sync_plan) else None
+
     def step_partials(p):
         k, v, t = panes[p]
         b0, wm = _wm_point(wms, p, nb)
         e = (b0 + 1) * B.BATCH_ROWS
-        local_op.process_device_batch([k.data_ptr(), v.data_ptr(), t.data_ptr()], e)
+
+        def feed_first():
+            local_op.process_device_batch([k.data_ptr(), v.data_ptr(), t.data_ptr()], e)
+
+        def feed_rest():
+            if e < rows:
+                local_op.process_device_batch([k.data_ptr() + 8 * e, v.data_ptr() + 8 * e, t.data_ptr() + 8 * e], rows - e)
+                local_op.submit()
+
+        if pipe is not None:
+            # two-stage pipeline: the shuffle edge and the owner stage run on a second host thread, one or two
+            # rounds behind the local stage (LaggedCombiner)
+            pipe.local_step(feed_first, feed_rest, wm)
+            return
+        feed_first()
         eff, chunks = plan.close_panes(wm)
-        if e < rows:
-            # the rest of this pane's input is enqueued on the local stage's stream before the owner stage runs,
-            # so the exchange and the owner's kernels overlap it
-            local_op.process_device_batch([k.data_ptr() + 8 * e, v.data_ptr() + 8 * e, t.data_ptr() + 8 * e], rows - e)
-            local_op.submit()
+        feed_rest()  # enqueued before the owner stage runs, so the exchange and the owner's kernels overlap it
         if eff is not None:
             plan.owner_stage(eff, chunks, lambda op, w: emit(w))
 
@@ -463,6 +620,8 @@ def bench(args, torch, dist, rank, world, local):
     timed_op = local_op if mode == "partials" else owner_op
     for p in range(W):
         step(p)
+    if pipe is not None:
+        pipe.drain()
     owner_op.flush()
     torch.cuda.synchronize()
     dist.barrier()
@@ -477,6 +636,8 @@ def bench(args, torch, dist, rank, world, local):
     e0.record()
     for p in range(W, W + K):
         step(p)
+    if pipe is not None:
+        pipe.drain()
     owner_op.flush()
     if local_op is not None:
         local_op.flush()
@@ -494,6 +655,8 @@ def bench(args, torch, dist, rank, world, local):
     tot = torch.tensor([launches, rows_out, d["rows_in"]], dtype=torch.int64, device=device)
     dist.all_reduce(tot)
     sent = ex.bytes_sent - sent0
+    if pipe is not None:
+        pipe.close()
     if plan is not None:
         plan.close()
     else:
@@ -517,6 +680,10 @@ def bench(args, torch, dist, rank, world, local):
                                       else "raw rows (reference plan shape)"),
                           "l2": "inputs larger than L2, never re-read", "parallelism": f"key-partitioned x{world}",
                           "numa": getattr(args, "numa", None)},
+               "plan": (None if mode != "partials" else
+                        "local stage and shuffle+owner stage on two host threads, watermarks ride on the data rounds, "
+                        "local stage closes panes 2 rounds behind (LaggedCombiner)" if pipe is not None else
+                        "synchronous: watermark exchange, local close, shuffle, owner stage in sequence"),
                "rows_out_per_step": int(tot[1].item()) / max(K, 1), "gpu_launches": int(tot[0].item()),
                "roofline": {"bound": "hbm", "kernel": "ingest_kernel<1>",
                             "achieved": round(ingest_gbs, 1) if ingest_gbs else None, "peak": peak,

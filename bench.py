@@ -69,9 +69,12 @@ def parse():
     ap.add_argument("--sync-emit", action="store_true",
                     help="e2e: blocking arroyo_b200_op_handle_watermark instead of the begin / poll pair")
     ap.add_argument("--no-direct", action="store_true", help="measurement knob: hash dense keys as well")
-    ap.add_argument("--local-chunk-log2", type=int, default=21,
+    ap.add_argument("--local-chunk-log2", type=int, default=23,
                     help="N>1, partials: rows per ingest launch of the local stage = 2^n; short launches let the owner "
                          "stage's kernels in between")
+    ap.add_argument("--sync-plan", action="store_true",
+                    help="N>1, partials: run the local stage, the shuffle and the owner stage in sequence on one host "
+                         "thread instead of as a two-stage pipeline")
     ap.add_argument("--shuffle", default="partials", choices=["partials", "rows"],
                     help="N>1: what crosses the all-to-all (per-pane partial aggregates, or raw rows)")
     return ap.parse_args()

@@ -198,6 +198,73 @@ def combiner_worker(rank, port, outdir):
     dist.destroy_process_group()
 
 
+def lagged_worker(rank, port, outdir):
+    """The same plan through LaggedCombiner: local stage on the caller's thread, shuffle edge + owner stage on a second
+    thread, watermarks riding on the data rounds, panes closed two rounds behind."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(WORLD))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    from arroyo_b200.multi_gpu import LaggedCombiner, ShuffleExchange
+    names = ("key", "sum", "n", O.TIMESTAMP)
+    ex = ShuffleExchange(torch, dist, rank, WORLD, None, torch.device("cpu"), max_recv_rows=1 << 16, n_cols=4)
+    batches = shard(rank)
+    gen = O.WatermarkGenerator()
+    local = O.TumblingAggregatingWindowFunc(O.WindowAggConfig(width=S, key_names=["key"], aggs=[O.Agg("sum", "value", "sum"), O.Agg("count", None, "n")], final_projection=False))
+    owner = O.SlidingAggregatingWindowFunc(O.WindowAggConfig(width=3 * S, slide=S, key_names=["key"], aggs=[O.Agg("sum", "sum", "sum"), O.Agg("sum", "n", "n")], window_index=1))
+    lctx, octx = O.OperatorContext(1), O.OperatorContext(1)
+    lout, out = O.Collector(), O.Collector()
+
+    def local_close(eff):
+        lctx.watermarks.set(0, eff)
+        local.handle_watermark(eff, lctx, lout)
+        chunks, lout.batches = list(lout.batches), []
+        return chunks
+
+    def pack(chunk):
+        packed, counts = np_pack(chunk, names)
+        return packed, counts, chunk.num_rows
+
+    def owner_ingest(got, consume_now):
+        for cols, r in got:
+            owner.process_batch(O.Batch({c: read_ptr(ptr, r) for c, ptr in zip(names, cols)}), octx, out)
+
+    def owner_watermark(eff):
+        octx.watermarks.set(0, eff)
+        owner.handle_watermark(eff, octx, out)
+
+    pipe = LaggedCombiner(ex, local_close, pack, owner_ingest, owner_watermark, lag=2)
+    n_rounds = torch.tensor([len(batches)])
+    dist.all_reduce(n_rounds, op=dist.ReduceOp.MAX)
+    n_rounds = int(n_rounds)
+    # the final watermark needs `lag` more steps to come back to the local stage, and one more to reach the owner
+    for i in range(n_rounds + 4):
+        wm = None
+        b = batches[i] if i < len(batches) else None
+        if b is not None:
+            wm = gen.process_batch(b[O.TIMESTAMP])
+        elif i == n_rounds:
+            wm = O.FINAL_WATERMARK
+        pipe.local_step((lambda: local.process_batch(b, lctx, lout)) if b is not None else (lambda: None), lambda: None, wm)
+    pipe.drain()
+    pipe.close()
+    rows = []
+    for b in out.batches:
+        rows += b.rows()
+    with open(os.path.join(outdir, f"rank{rank}.json"), "w") as f:
+        json.dump({"rows": rows, "multi": 0}, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_lagged_combiner_pipeline_world2_gloo_matches_direct_topology():
+    want = expected()
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(lagged_worker, args=(31533 + os.getpid() % 1000, d), nprocs=WORLD, join=True)
+        got = []
+        for r in range(WORLD):
+            got += json.load(open(os.path.join(d, f"rank{r}.json")))["rows"]
+    assert multiset(got) == multiset(want)
+
+
 def test_combiner_plan_world2_gloo_matches_direct_topology():
     want = expected()
     with tempfile.TemporaryDirectory() as d:
