@@ -365,10 +365,13 @@ class LaggedCombiner:
         self.th.start()
 
     # ---- local stage (caller's thread) ----
-    def local_step(self, feed_first, feed_rest, watermark):
+    def local_step(self, feed, watermark):
+        """One step of the local stage: `feed()` enqueues the step's input on the local operator (asynchronously);
+        then the panes that the effective watermark of round p - lag closes leave as partial rows.  Feeding first
+        keeps the device busy with the ingest while this thread waits for the round and for the emission."""
         p = self.step
         self.step += 1
-        feed_first()
+        feed()
         eff = None
         with self.cv:
             if p - self.lag >= 0:
@@ -382,7 +385,6 @@ class LaggedCombiner:
         if eff is not None and eff != self.last_closed:
             chunks = self.local_close(eff)
             closing = self.last_closed = eff
-        feed_rest()
         self.q.put((p, closing, chunks, watermark))
 
     def drain(self):
@@ -590,7 +592,7 @@ def bench(args, torch, dist, rank, world, local):
         if pipe is not None:
             # two-stage pipeline: the shuffle edge and the owner stage run on a second host thread, one or two
             # rounds behind the local stage (LaggedCombiner)
-            pipe.local_step(feed_first, feed_rest, wm)
+            pipe.local_step(lambda: (feed_first(), feed_rest()), wm)
             return
         feed_first()
         eff, chunks = plan.close_panes(wm)

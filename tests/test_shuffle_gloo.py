@@ -243,7 +243,7 @@ def lagged_worker(rank, port, outdir):
             wm = gen.process_batch(b[O.TIMESTAMP])
         elif i == n_rounds:
             wm = O.FINAL_WATERMARK
-        pipe.local_step((lambda: local.process_batch(b, lctx, lout)) if b is not None else (lambda: None), lambda: None, wm)
+        pipe.local_step((lambda: local.process_batch(b, lctx, lout)) if b is not None else (lambda: None), wm)
     pipe.drain()
     pipe.close()
     rows = []
