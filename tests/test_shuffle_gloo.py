@@ -20,7 +20,7 @@ from tests.golden_cases import multiset  # noqa: E402
 
 S = 1_000_000_000
 T0 = 1_700_000_000 * S
-WORLD = 2
+WORLD = int(os.environ.get("SHUFFLE_TEST_WORLD", "2"))  # CI runs 2; 4 and 8 were run by hand
 BATCH = 500
 
 
