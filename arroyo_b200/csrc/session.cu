@@ -629,7 +629,7 @@ class SessionOp final : public OpBase {
   PinnedBuf h_ctr_;
   // launch arena
   uint64_t arena_cap_ = 0;
-  DevBuf a_id_, a_seq_, a_ts_, a_val_[SV], g_seq_, g_ts_, g_val_[SV];
+  DevBuf a_id_, a_seq_, a_ts_, a_val_[SV], g_seq_;
   uint64_t arena_rows_bound_ = 0;  // rows prepped since the last apply (upper bound incl. late rows)
   uint32_t seq_ = 0;
   bool has_wm_ = false;
@@ -878,12 +878,8 @@ void SessionOp::ensure_arena(uint64_t rows) {
   a_id_.alloc(nc * 4);
   a_seq_.alloc(nc * 4);
   a_ts_.alloc(nc * 8);
-  g_seq_.alloc(nc * 4);
-  g_ts_.alloc(nc * 8);
-  for (int v = 0; v < n_vals_; ++v) {
-    a_val_[v].alloc(nc * 8);
-    g_val_[v].alloc(nc * 8);
-  }
+  g_seq_.alloc(nc * 4);  // grouped timestamps / values go straight into the row pool (apply_pending)
+  for (int v = 0; v < n_vals_; ++v) a_val_[v].alloc(nc * 8);
   arena_cap_ = nc;
 }
 
