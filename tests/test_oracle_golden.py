@@ -51,3 +51,48 @@ def test_c_oracle_parallel_driver_matches_numpy_oracle():
         assert r.sum_of_rows == int(out["n"].sum())
         assert r.sum_of_sums == int(out["sum"].astype(np.uint64).sum())
         assert abs(r.sum_of_avgs - float(out["avg"].sum())) <= 1e-9 * abs(float(out["avg"].sum()))
+
+
+@pytest.mark.parametrize("kind", ["tumbling", "sliding"])
+def test_windowed_sum_avg_min_max_against_an_independent_engine(kind):
+    """No reference golden vector uses SUM or AVG inside a *windowed* aggregate; this pins the
+    oracle's accumulators for them against an independent columnar engine: Arrow C++ / Acero group-by
+    (hash_sum, hash_mean, hash_min, hash_max, hash_count) over (key, window) computed from first principles
+    (every row belongs to the windows [b - width + slide .. b] of its bin b)."""
+    import numpy as np
+    import pyarrow as pa
+    S = 1_000_000_000
+    T0 = 1_700_000_000 * S
+    rng = np.random.default_rng(12)
+    n = 60_000
+    ts = T0 + np.sort(rng.integers(0, 20 * S, n)).astype(np.int64)
+    key = rng.integers(0, 500, n, dtype=np.int64) * 7919 - 3
+    val = rng.integers(-10**8, 10**8, n, dtype=np.int64)
+    width, slide = (2 * S, 0) if kind == "tumbling" else (5 * S, S)
+    aggs = [O.Agg("sum", "value", "sum"), O.Agg("avg", "value", "avg"), O.Agg("min", "value", "mn"),
+            O.Agg("max", "value", "mx"), O.Agg("count", None, "n")]
+    cfg = O.WindowAggConfig(width=width, slide=slide, key_names=["key"], aggs=aggs, window_index=1)
+    op = O.TumblingAggregatingWindowFunc(cfg) if kind == "tumbling" else O.SlidingAggregatingWindowFunc(cfg)
+    # in-order stream, watermark far behind: nothing is late, every window is emitted by the final watermark
+    got = O.run_single_input(op, O.source_batches({"key": key, "value": val, O.TIMESTAMP: ts}, 4096), 30 * S).all()
+
+    step = width if kind == "tumbling" else slide
+    bins = ts - ts % step
+    ks, ws, vs = [], [], []
+    for j in range(width // step):  # the window starting at bin - j * step contains the row
+        ks.append(key)
+        ws.append(bins - j * step)
+        vs.append(val)
+    t = pa.table({"key": np.concatenate(ks), "window_start": np.concatenate(ws), "value": np.concatenate(vs)})
+    ref = t.group_by(["key", "window_start"]).aggregate([("value", "sum"), ("value", "mean"), ("value", "min"),
+                                                         ("value", "max"), ("value", "count")])
+    want = {(k, w): (s, m, lo, hi, c) for k, w, s, m, lo, hi, c in zip(
+        ref["key"].to_pylist(), ref["window_start"].to_pylist(), ref["value_sum"].to_pylist(),
+        ref["value_mean"].to_pylist(), ref["value_min"].to_pylist(), ref["value_max"].to_pylist(),
+        ref["value_count"].to_pylist())}
+    assert got.num_rows == len(want)
+    for i in range(got.num_rows):
+        s, m, lo, hi, c = want[(int(got["key"][i]), int(got["window_start"][i]))]
+        assert int(got["window_end"][i]) == int(got["window_start"][i]) + width
+        assert (int(got["sum"][i]), int(got["mn"][i]), int(got["mx"][i]), int(got["n"][i])) == (s, lo, hi, c)
+        assert abs(float(got["avg"][i]) - m) <= 1e-9 * max(1.0, abs(m))
