@@ -453,7 +453,7 @@ def _wm_point(wms, p, nb):
     return found[0][0], found[-1][1]
 
 
-def _e2e_partials(args, torch, dist, B, ab, native, rank, world, local, device, gen_pane):
+def _e2e_partials(args, torch, dist, B, ab, native, rank, world, local, device, gen_pane, feed=None):
     """End to end at N GPUs: every rank feeds its shard as pinned host Arrow batches through
     arroyo_b200_op_process_batch (host -> device copies inside the timed region), partial aggregates cross the
     all-to-all, and each rank reads the windows of its keys back as host Arrow batches."""
@@ -463,7 +463,7 @@ def _e2e_partials(args, torch, dist, B, ab, native, rank, world, local, device, 
     nb = rows // B.BATCH_ROWS
     K = args.e2e_steps or min(args.steps, 6)
     W = 13
-    batches, wms, _keep = B.host_feed(torch, gen_pane, range(W + K), rows)
+    batches, wms, _keep = feed if feed is not None else B.host_feed(torch, gen_pane, range(W + K), rows)
     plan = PartialsPlan(torch, dist, B, ab, native, args, rank, world, local, device, B.op_flags(args), B.op_flags(args))
     lctx, octx, col = ab.OperatorContext(1), ab.OperatorContext(1), ab.Collector()
     d2h = 0
@@ -666,7 +666,15 @@ def bench(args, torch, dist, rank, world, local):
         part.close()
     e2e = None
     if mode == "partials" and not args.skip_e2e:
-        e2e = _e2e_partials(args, torch, dist, B, ab, native, rank, world, local, device, gen_pane)
+        # repeated like the single-GPU pass (the host links are shared with the box's other tenants): median reported
+        Ke = args.e2e_steps or min(args.steps, 6)
+        feed = B.host_feed(torch, gen_pane, range(13 + Ke), rows)
+        trials = [_e2e_partials(args, torch, dist, B, ab, native, rank, world, local, device, gen_pane, feed=feed)
+                  for _ in range(max(1, args.e2e_trials))]
+        trials.sort(key=lambda r: r["value"])
+        e2e = dict(trials[len(trials) // 2])
+        e2e["trials"] = [round(r["value"]) for r in trials]
+        del feed
     if rank == 0:
         peak, peak_kind = B.measured_peak()
         ingest_gbs = 24.0 * d["ingest_rows_timed"] / (d["ingest_ms"] * 1e-3) / 1e9 if d["ingest_ms"] else None

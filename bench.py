@@ -66,6 +66,7 @@ def parse():
                          "library) or one ctypes call per batch from Python")
     ap.add_argument("--no-numa-bind", action="store_true",
                     help="do not bind the process to the CPUs local to its GPU (NVML affinity)")
+    ap.add_argument("--e2e-trials", type=int, default=3, help="e2e passes (median reported, all listed)")
     ap.add_argument("--sync-emit", action="store_true",
                     help="e2e: blocking arroyo_b200_op_handle_watermark instead of the begin / poll pair")
     ap.add_argument("--no-direct", action="store_true", help="measurement knob: hash dense keys as well")
@@ -502,91 +503,104 @@ def run_e2e(args, torch, device, local, gen_pane):
     rows = args.rows_per_pane
     nb = rows // BATCH_ROWS
     batches, wms, _keep = host_feed(torch, gen_pane, range(W + K), rows)
-    op = native.SlidingAggregatingWindowFunc(window_config(), device=local, expected_keys=args.keys,
-                                             flags=op_flags(args))
-    ctx = ab.OperatorContext(1)
-    col = ab.Collector()
-    d2h = 0
-    outstanding = False  # an emission whose windows are still on their way to the host
 
-    def collect(block):
-        """The shim's handle_future_result: take the windows of the outstanding emission (then it would forward the
-        watermark it held back)."""
-        nonlocal d2h, outstanding
-        if not outstanding or not op.handle_watermark_poll(col, block=block):
-            return
-        outstanding = False
-        for rb in col.batches:
-            d2h += rb.num_rows * 48
-        col.batches.clear()
+    def trial():
+        """One fresh operator over the same pinned host batches: W warm-up panes, K timed panes."""
+        op = native.SlidingAggregatingWindowFunc(window_config(), device=local, expected_keys=args.keys,
+                                                 flags=op_flags(args))
+        ctx = ab.OperatorContext(1)
+        col = ab.Collector()
+        d2h = 0
+        outstanding = False  # an emission whose windows are still on their way to the host
 
-    def step(p):
-        nonlocal d2h, outstanding
-        for b in range(nb):
-            op.process_batch(batches[p][b], ctx, col)
-            wm = wms[p * nb + b]
-            if wm is not None:
-                ctx.watermarks.set(0, wm)
-                if args.sync_emit:
-                    op.handle_watermark(wm, ctx, col)
-                    for rb in col.batches:
-                        d2h += rb.num_rows * 48
-                    col.batches.clear()
-                else:
-                    collect(block=True)  # windows leave in order: the previous emission first
-                    outstanding = op.handle_watermark_begin(wm, ctx)
-            elif outstanding and b % 8 == 0:
-                collect(block=False)  # the run loop polls the future between batches
-
-    if args.e2e_host == "library":
-        # the subtask run loop in compiled code: one arroyo_b200_op_run_batches call per pane's worth of queued
-        # batches.  Exporting a batch builds Arrow C descriptors only (no buffer is touched), so it is done ahead.
-        import ctypes as C
-        exported = [native.ExportedBatches(batches[p]) for p in range(W + K)]
-        wm_arr = []
-        for p in range(W + K):
-            a = (C.c_int64 * nb)(*[ffi.NO_WATERMARK if wms[p * nb + b] is None else wms[p * nb + b] for b in range(nb)])
-            wm_arr.append(a)
-
-        def step(p):  # noqa: F811
-            nonlocal d2h
-            op.run_batches(exported[p], wm_arr[p], col, async_emit=not args.sync_emit)
+        def collect(block):
+            """The shim's handle_future_result: take the windows of the outstanding emission (then it would forward the
+            watermark it held back)."""
+            nonlocal d2h, outstanding
+            if not outstanding or not op.handle_watermark_poll(col, block=block):
+                return
+            outstanding = False
             for rb in col.batches:
                 d2h += rb.num_rows * 48
             col.batches.clear()
 
-        def collect(block):  # noqa: F811
-            nonlocal d2h
-            op.handle_watermark_poll(col, block=block)
-            for rb in col.batches:
-                d2h += rb.num_rows * 48
-            col.batches.clear()
+        def step(p):
+            nonlocal d2h, outstanding
+            for b in range(nb):
+                op.process_batch(batches[p][b], ctx, col)
+                wm = wms[p * nb + b]
+                if wm is not None:
+                    ctx.watermarks.set(0, wm)
+                    if args.sync_emit:
+                        op.handle_watermark(wm, ctx, col)
+                        for rb in col.batches:
+                            d2h += rb.num_rows * 48
+                        col.batches.clear()
+                    else:
+                        collect(block=True)  # windows leave in order: the previous emission first
+                        outstanding = op.handle_watermark_begin(wm, ctx)
+                elif outstanding and b % 8 == 0:
+                    collect(block=False)  # the run loop polls the future between batches
 
-    for p in range(W):
-        step(p)
-    collect(block=True)
-    op.flush()
-    torch.cuda.synchronize()
-    d2h = 0
-    st0 = op.stats()
-    t0 = time.perf_counter()
-    for p in range(W, W + K):
-        step(p)
-    collect(block=True)
-    op.flush()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    st1 = op.stats()
-    op.close()
-    how = ("arroyo_b200_op_handle_watermark" if args.sync_emit else
-           "arroyo_b200_op_handle_watermark_begin / _poll (windows copied back while the next batches are copied in)")
-    loop = ("arroyo_b200_op_run_batches (run loop inside the library)" if args.e2e_host == "library" else
-            "arroyo_b200_op_process_batch per batch from Python")
-    return {"value": K * rows / dt, "unit": "rows/s", "h2d_bytes_per_step": rows * 24,
-            "d2h_bytes_per_step": d2h // max(K, 1), "steps": K, "ms_per_step": 1e3 * dt / K,
-            "host_process_ms_per_step": round((st1["host_process_ms"] - st0["host_process_ms"]) / K, 3),
-            "host_watermark_ms_per_step": round((st1["host_watermark_ms"] - st0["host_watermark_ms"]) / K, 3),
-            "path": f"pinned host Arrow batches -> {loop} -> {how} -> host Arrow windows"}
+        if args.e2e_host == "library":
+            # the subtask run loop in compiled code: one arroyo_b200_op_run_batches call per pane's worth of queued
+            # batches.  Exporting a batch builds Arrow C descriptors only (no buffer is touched), so it is done ahead.
+            import ctypes as C
+            exported = [native.ExportedBatches(batches[p]) for p in range(W + K)]
+            wm_arr = []
+            for p in range(W + K):
+                a = (C.c_int64 * nb)(*[ffi.NO_WATERMARK if wms[p * nb + b] is None else wms[p * nb + b] for b in range(nb)])
+                wm_arr.append(a)
+
+            def step(p):  # noqa: F811
+                nonlocal d2h
+                op.run_batches(exported[p], wm_arr[p], col, async_emit=not args.sync_emit)
+                for rb in col.batches:
+                    d2h += rb.num_rows * 48
+                col.batches.clear()
+
+            def collect(block):  # noqa: F811
+                nonlocal d2h
+                op.handle_watermark_poll(col, block=block)
+                for rb in col.batches:
+                    d2h += rb.num_rows * 48
+                col.batches.clear()
+
+        for p in range(W):
+            step(p)
+        collect(block=True)
+        op.flush()
+        torch.cuda.synchronize()
+        d2h = 0
+        st0 = op.stats()
+        t0 = time.perf_counter()
+        for p in range(W, W + K):
+            step(p)
+        collect(block=True)
+        op.flush()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        st1 = op.stats()
+        op.close()
+        how = ("arroyo_b200_op_handle_watermark" if args.sync_emit else
+               "arroyo_b200_op_handle_watermark_begin / _poll (windows copied back while the next batches are copied in)")
+        loop = ("arroyo_b200_op_run_batches (run loop inside the library)" if args.e2e_host == "library" else
+                "arroyo_b200_op_process_batch per batch from Python")
+        return {"value": K * rows / dt, "unit": "rows/s", "h2d_bytes_per_step": rows * 24,
+                "d2h_bytes_per_step": d2h // max(K, 1), "steps": K, "ms_per_step": 1e3 * dt / K,
+                "host_process_ms_per_step": round((st1["host_process_ms"] - st0["host_process_ms"]) / K, 3),
+                "host_watermark_ms_per_step": round((st1["host_watermark_ms"] - st0["host_watermark_ms"]) / K, 3),
+                "path": f"pinned host Arrow batches -> {loop} -> {how} -> host Arrow windows"}
+
+    # The host link is shared with the box's other tenants (a neighbour's copies can halve a 100 ms measurement),
+    # so the pass is repeated: the median trial is reported, every trial is listed.
+    n_trials = max(1, args.e2e_trials)
+    results = [trial() for _ in range(n_trials)]
+    results.sort(key=lambda r: r["value"])
+    out = dict(results[len(results) // 2])
+    out["trials"] = [round(r["value"]) for r in results]
+    out["trials_note"] = f"median of {n_trials} passes (fresh operator each, same pinned host batches)"
+    return out
 
 
 def run_reference(args):

@@ -23,3 +23,11 @@ def golden():
     with open(os.path.join(d, "expected.json")) as f:
         expected = json.load(f)
     return inputs, expected
+
+
+@pytest.fixture(scope="session")
+def accumulator_golden():
+    """Merged final rows of the reference's updating-aggregate goldens (tests/golden/make_golden.py)."""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "accumulators.json")) as f:
+        return json.load(f)

@@ -9,6 +9,7 @@ Run in the build container only (the reference tree is not present on the GPU bo
 Source of the vectors (read-only, never copied verbatim):
   crates/arroyo-sql-testing/inputs/{cars,impulse,nexmark_bids}.json     -> inputs.npz
   crates/arroyo-sql-testing/golden_outputs/<query>.json                  -> expected.json
+  crates/arroyo-sql-testing/golden_outputs/{grouped_aggregates,aggregates}.json -> accumulators.json
 The JSON lines are re-encoded: timestamps become int64 nanoseconds since the Unix
 epoch, the `event_type` strings become the int64 codes in EVENT_TYPE_CODES, and the
 columns the hot path never reads (location, url, extra, ...) are dropped.
@@ -83,6 +84,23 @@ def main():
     with open(os.path.join(OUT, "expected.json"), "w") as f:
         json.dump(expected, f, separators=(",", ":"), sort_keys=True)
     print({q: len(v) for q, v in expected.items()})
+
+    # Updating (non-windowed) aggregates: the sink is a Debezium change stream that the reference's test merges per
+    # primary key before comparing (smoke_tests.rs:519-562).  Their merged final rows pin the SUM / AVG / MIN / MAX /
+    # COUNT accumulators -- the same DataFusion accumulators the windowed operators use.
+    acc = {}
+    for q, pk in (("grouped_aggregates", "counter_mod"), ("aggregates", None)):
+        state = {}
+        for r in lines(os.path.join(BASE, "golden_outputs", q + ".json")):
+            op, before, after = r["op"], r.get("before"), r.get("after")
+            if op in ("u", "d") and before is not None:
+                state.pop(before.get(pk) if pk else 0, None)
+            if op in ("c", "u") and after is not None:
+                state[after.get(pk) if pk else 0] = after
+        acc[q] = [state[k] for k in sorted(state)]
+    with open(os.path.join(OUT, "accumulators.json"), "w") as f:
+        json.dump(acc, f, separators=(",", ":"), sort_keys=True)
+    print({q: len(v) for q, v in acc.items()})
 
 
 if __name__ == "__main__":

@@ -216,6 +216,42 @@ def nexmark_q5(ops, inputs):
     return [{"auction": r["auction"], "count": r["num"]} for r in out.rows() if r["num"] >= r["maxn"]]
 
 
+def _accumulators(ops, inputs, keyed, window):
+    """min / max / sum / count / avg over the whole impulse input, per `counter % 5` or globally: the final state the
+    reference's updating aggregate reaches (queries grouped_aggregates.sql / aggregates.sql), computed here by the
+    windowed operators over one window that contains every row -- same accumulators, pinned by the same vectors."""
+    counter = inputs["impulse_counter"]
+    cols = {"counter": counter, O.TIMESTAMP: inputs["impulse_ts"]}
+    keys = []
+    if keyed:
+        cols = {"counter_mod": counter % 5, **cols}
+        keys = ["counter_mod"]
+    aggs = [O.Agg("min", "counter", "min"), O.Agg("max", "counter", "max"), O.Agg("sum", "counter", "sum"),
+            O.Agg("count", None, "count"), O.Agg("avg", "counter", "avg")]
+    if window == "tumbling":
+        op = ops.TumblingAggregatingWindowFunc(O.WindowAggConfig(width=HOUR, key_names=keys, aggs=aggs,
+                                                                 window_index=len(keys)))
+    else:  # one hop whose window [start, start + 1 h) holds all rows: only the fullest window is compared
+        op = ops.SlidingAggregatingWindowFunc(O.WindowAggConfig(width=HOUR, slide=HOUR // 2, key_names=keys, aggs=aggs,
+                                                                window_index=len(keys)))
+    out = ops.run_single_input(op, O.source_batches(cols, BATCH)).all()
+    rows = _rows(out, {**({"counter_mod": "counter_mod"} if keyed else {}), "min": "min", "max": "max", "sum": "sum",
+                       "count": "count", "avg": "avg", "_start": "window_start"})
+    if window == "sliding":  # rows sit in two overlapping hops; keep the hop that starts on the hour
+        rows = [r for r in rows if r["_start"] % HOUR == 0]
+    for r in rows:
+        del r["_start"]
+    return rows
+
+
+ACCUMULATOR_CASES = {
+    ("grouped_aggregates", "tumbling"): lambda ops, inputs: _accumulators(ops, inputs, True, "tumbling"),
+    ("grouped_aggregates", "sliding"): lambda ops, inputs: _accumulators(ops, inputs, True, "sliding"),
+    ("aggregates", "tumbling"): lambda ops, inputs: _accumulators(ops, inputs, False, "tumbling"),
+    ("aggregates", "sliding"): lambda ops, inputs: _accumulators(ops, inputs, False, "sliding"),
+}
+
+
 CASES = {
     "sliding_window_end": sliding_window_end,
     "hourly_by_event_type": hourly_by_event_type,

@@ -37,3 +37,12 @@ def test_remerge_mode_matches_reference_golden(golden, gpu_ops, name):
     finally:
         gpu_ops.DEFAULT_KW.clear()
     assert multiset(got) == multiset(expected[name]), name
+
+
+@pytest.mark.parametrize("case", sorted(__import__("tests.golden_cases", fromlist=["x"]).ACCUMULATOR_CASES))
+def test_cuda_accumulators_match_reference_updating_aggregate_goldens(golden, accumulator_golden, gpu_ops, case):
+    """SUM / AVG / MIN / MAX / COUNT on the GPU against the final rows of the reference's grouped_aggregates /
+    aggregates goldens."""
+    from tests.golden_cases import ACCUMULATOR_CASES
+    got = ACCUMULATOR_CASES[case](gpu_ops, golden[0])
+    assert multiset(got) == multiset(accumulator_golden[case[0]])

@@ -15,6 +15,20 @@ def test_oracle_matches_reference_golden(golden, name):
     assert multiset(got) == multiset(expected[name]), name
 
 
+@pytest.mark.parametrize("impl", ["numpy", "c"])
+@pytest.mark.parametrize("case", sorted(__import__("tests.golden_cases", fromlist=["x"]).ACCUMULATOR_CASES))
+def test_accumulators_match_reference_updating_aggregate_goldens(golden, accumulator_golden, case, impl):
+    """SUM / AVG / MIN / MAX / COUNT over Int64 are pinned by the reference's grouped_aggregates / aggregates
+    goldens (the updating aggregate reaches these final rows with the same DataFusion accumulators)."""
+    from tests.golden_cases import ACCUMULATOR_CASES
+    ops = O
+    if impl == "c":
+        from oracle import c_oracle
+        ops = c_oracle
+    got = ACCUMULATOR_CASES[case](ops, golden[0])
+    assert multiset(got) == multiset(accumulator_golden[case[0]])
+
+
 C_CASES = ["sliding_window_end", "hourly_by_event_type", "tight_watermark", "month_loose_watermark",
            "most_active_driver_last_hour", "offset_impulse_join", "nexmark_q5", "windowed_inner_join",
            "windowed_outer_join"]
