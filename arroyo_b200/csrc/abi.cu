@@ -121,6 +121,14 @@ int32_t arroyo_b200_op_create(const ArroyoB200OpConfig* config, ArroyoB200Op** o
 void arroyo_b200_op_destroy(ArroyoB200Op* op) {
   if (!op) return;
   try {
+    if (op->impl && op->impl->pending_out) {
+      // an emission that was begun and never collected: wait for its copies, give the buffers back
+      op->impl->poll_watermark(true);
+      ArroyoB200Batches tmp{};
+      batches_finish(op->impl->pending_out, &tmp);
+      batches_release(&tmp);
+      op->impl->pending_out = nullptr;
+    }
     delete op->impl;
   } catch (...) {
   }

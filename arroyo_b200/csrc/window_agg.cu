@@ -1159,6 +1159,9 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
 
 WindowAggOp::~WindowAggOp() {
   cudaSetDevice(device_);
+  // nothing may still be reading the input batches or writing output buffers when they are handed back
+  if (copy_stream_) cudaStreamSynchronize(copy_stream_);
+  if (out_stream_) cudaStreamSynchronize(out_stream_);
   cudaStreamSynchronize(stream_);
   for (auto& r : releases_) {
     for (auto& a : r.arrs)
