@@ -9,7 +9,8 @@ Run in the build container only (the reference tree is not present on the GPU bo
 Source of the vectors (read-only, never copied verbatim):
   crates/arroyo-sql-testing/inputs/{cars,impulse,nexmark_bids}.json     -> inputs.npz
   crates/arroyo-sql-testing/golden_outputs/<query>.json                  -> expected.json
-  crates/arroyo-sql-testing/golden_outputs/{grouped_aggregates,aggregates}.json -> accumulators.json
+  crates/arroyo-sql-testing/golden_outputs/{grouped_aggregates,aggregates,debezium_agg}.json -> accumulators.json
+  crates/arroyo-sql-testing/inputs/aggregate_updates.json                -> updating_inputs.npz
 The JSON lines are re-encoded: timestamps become int64 nanoseconds since the Unix
 epoch, the `event_type` strings become the int64 codes in EVENT_TYPE_CODES, and the
 columns the hot path never reads (location, url, extra, ...) are dropped.
@@ -98,6 +99,32 @@ def main():
             if op in ("c", "u") and after is not None:
                 state[after.get(pk) if pk else 0] = after
         acc[q] = [state[k] for k in sorted(state)]
+    # debezium_agg.sql: a Debezium change stream (c / u / d with both row images) into an updating aggregate
+    # GROUP BY product: count(*), count(distinct customer_name), sum(quantity + 5) + 10.  Strings become codes.
+    upd = lines(os.path.join(BASE, "inputs", "aggregate_updates.json"))
+    products, customers = {}, {}
+    rows = []  # (is_retract, product code, customer code, quantity) in stream order: u = retract(before), append(after)
+    for r in upd:
+        imgs = []
+        if r["op"] in ("u", "d"):
+            imgs.append((1, r["before"]))
+        if r["op"] in ("c", "u", "r"):
+            imgs.append((0, r["after"]))
+        for retract, img in imgs:
+            rows.append((retract, products.setdefault(img["product_name"], len(products)),
+                         customers.setdefault(img["customer_name"], len(customers)), img["quantity"]))
+    arr = np.array(rows, dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "updating_inputs.npz"), is_retract=arr[:, 0], product=arr[:, 1],
+                        customer=arr[:, 2], quantity=arr[:, 3])
+    state = {}
+    for r in lines(os.path.join(BASE, "golden_outputs", "debezium_agg.json")):
+        op, before, after = r["op"], r.get("before"), r.get("after")
+        if op in ("u", "d") and before is not None:
+            state.pop(before["id"], None)
+        if op in ("c", "u") and after is not None:
+            state[after["id"]] = after
+    acc["debezium_agg"] = [{"product": products[v["id"][2:]], "c": v["c"], "d": v["d"], "q": v["q"]}
+                           for _, v in sorted(state.items())]
     with open(os.path.join(OUT, "accumulators.json"), "w") as f:
         json.dump(acc, f, separators=(",", ":"), sort_keys=True)
     print({q: len(v) for q, v in acc.items()})
