@@ -148,8 +148,128 @@ class SlidingAggregatingWindowFunc(_WindowOp):
 
 
 SessionAggregatingWindowFunc = O.SessionAggregatingWindowFunc
-InstantJoin = O.InstantJoin
 run_single_input = O.run_single_input
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# instant join (join_oracle.c)
+# ---------------------------------------------------------------------------------------------------------------
+JOIN_LIB = os.path.join(HERE, "liboracle_join.so")
+_join_lib = None
+_JOIN_TYPES = {"inner": 0, "left": 1, "right": 2, "full": 3}
+
+
+class _JoinOut(C.Structure):
+    _fields_ = [("n", C.c_int64), ("cap", C.c_int64), ("n_cols", C.c_int), ("cols", C.POINTER(I64P)),
+                ("valid", C.POINTER(C.POINTER(C.c_uint8)))]
+
+
+def load_join():
+    global _join_lib
+    if _join_lib is not None:
+        return _join_lib
+    src = os.path.join(HERE, "join_oracle.c")
+    if not os.path.exists(JOIN_LIB) or os.path.getmtime(JOIN_LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", HERE, "liboracle_join.so"])
+    lib = C.CDLL(JOIN_LIB)
+    lib.oracle_join_create.restype = C.c_void_p
+    lib.oracle_join_create.argtypes = [C.c_int] * 7
+    lib.oracle_join_destroy.argtypes = [C.c_void_p]
+    lib.oracle_join_process.restype = C.c_int
+    lib.oracle_join_process.argtypes = [C.c_void_p, C.c_int, C.POINTER(I64P), C.c_int64, C.c_int, C.c_int64]
+    lib.oracle_join_out_create.restype = C.POINTER(_JoinOut)
+    lib.oracle_join_out_create.argtypes = [C.c_void_p]
+    lib.oracle_join_out_clear.argtypes = [C.POINTER(_JoinOut)]
+    lib.oracle_join_out_destroy.argtypes = [C.POINTER(_JoinOut)]
+    lib.oracle_join_handle_watermark.argtypes = [C.c_void_p, C.c_int64, C.POINTER(_JoinOut)]
+    lib.oracle_join_buffered.restype = C.c_int64
+    lib.oracle_join_buffered.argtypes = [C.c_void_p, C.c_int]
+    _join_lib = lib
+    return lib
+
+
+class InstantJoin:
+    """The oracle's InstantJoin interface over join_oracle.c (single-column Int64 equi-join, no routing-key copies).
+    Both inputs' layouts must be known before the first watermark (true of every pipeline in tests/golden_cases.py)."""
+
+    def __init__(self, cfg: O.JoinConfig):
+        assert len(cfg.left_on) == 1 and len(cfg.right_on) == 1 and not cfg.left_routing_keys and not cfg.right_routing_keys
+        self.cfg = cfg
+        self.lib = load_join()
+        self.names = [None, None]
+        self.pending = []  # batches that arrived before both layouts were known
+        self.h = None
+        self.out = None
+
+    def name(self):
+        return "InstantJoin"
+
+    def _create(self):
+        ln, rn = self.names
+        self.h = self.lib.oracle_join_create(_JOIN_TYPES[self.cfg.join_type], len(ln), ln.index(self.cfg.left_on[0]),
+                                             ln.index(O.TIMESTAMP), len(rn), rn.index(self.cfg.right_on[0]),
+                                             rn.index(O.TIMESTAMP))
+        self.out = self.lib.oracle_join_out_create(self.h)
+        out_names = [c for c in ln if c != O.TIMESTAMP]
+        for c in rn:
+            if c != O.TIMESTAMP:
+                out_names.append(c if c not in out_names else c + "_right")
+        self.out_names = out_names + [O.TIMESTAMP]
+        for side, batch, wm in self.pending:
+            self._send(side, batch, wm)
+        self.pending = []
+
+    def _send(self, side, batch, wm):
+        cols = [np.ascontiguousarray(batch[c], dtype=np.int64) for c in self.names[side]]
+        ptrs = (I64P * len(cols))(*[_p(c) for c in cols])
+        rc = self.lib.oracle_join_process(self.h, side, ptrs, batch.num_rows, 0 if wm is None else 1,
+                                          0 if wm is None else int(min(wm, (1 << 63) - 1)))
+        if rc != 0:
+            raise RuntimeError("shouldn't have a batch with timestamp before the watermark")  # instant_join.rs:129-139
+
+    def process_batch_index(self, index, total_inputs, batch, ctx, collector):
+        if batch.num_rows == 0:
+            raise RuntimeError("should have max timestamp")  # instant_join.rs:123
+        side = index // (total_inputs // 2)
+        if self.names[side] is None:
+            self.names[side] = batch.names()
+        wm = ctx.last_present_watermark()
+        if self.h is None:
+            if self.names[0] is not None and self.names[1] is not None:
+                self._create()
+            else:
+                self.pending.append((side, batch, wm))
+                return
+        self._send(side, batch, wm)
+
+    def handle_watermark(self, watermark, ctx, collector):
+        wm = ctx.last_present_watermark()
+        if wm is None:
+            return watermark
+        if self.h is None:
+            raise NotImplementedError("a watermark before both join inputs produced a batch")
+        self.lib.oracle_join_out_clear(self.out)
+        self.lib.oracle_join_handle_watermark(self.h, int(min(wm, (1 << 63) - 1)), self.out)
+        o = self.out.contents
+        n = int(o.n)
+        if n:
+            cols, valid = {}, {}
+            for c, name in enumerate(self.out_names):
+                cols[name] = np.ctypeslib.as_array(o.cols[c], shape=(n,)).copy()
+                v = np.ctypeslib.as_array(o.valid[c], shape=(n,)).astype(bool)
+                if not v.all():
+                    valid[name] = v
+            collector.collect(O.Batch(cols, valid))
+        return wm
+
+    def __del__(self):
+        try:
+            if self.out is not None:
+                self.lib.oracle_join_out_destroy(self.out)
+            if self.h is not None:
+                self.lib.oracle_join_destroy(self.h)
+        except Exception:
+            pass
 
 
 def run_windows(key, val, ts, batch_rows, width, slide, wm_delay, threads, flush_at_end=True) -> RunResult:

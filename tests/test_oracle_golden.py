@@ -110,3 +110,47 @@ def test_windowed_sum_avg_min_max_against_an_independent_engine(kind):
         assert int(got["window_end"][i]) == int(got["window_start"][i]) + width
         assert (int(got["sum"][i]), int(got["mn"][i]), int(got["mx"][i]), int(got["n"][i])) == (s, lo, hi, c)
         assert abs(float(got["avg"][i]) - m) <= 1e-9 * max(1.0, abs(m))
+
+
+@pytest.mark.parametrize("join_type", ["inner", "left", "right", "full"])
+def test_c_join_matches_numpy_oracle_on_random_streams(join_type):
+    """join_oracle.c against the numpy restatement: duplicates on both sides, unmatched rows on both sides, several
+    instants per watermark, rows that stay buffered across watermarks, and the "batch older than the watermark" panic."""
+    import numpy as np
+    from oracle import c_oracle
+    from tests.golden_cases import multiset as ms
+    S = 1_000_000_000
+    T0 = 1_700_000_000 * S
+    rng = np.random.default_rng(3)
+
+    def drive(join):
+        ctx, out = O.OperatorContext(2), O.Collector()
+        t = T0
+        for step in range(12):
+            for _ in range(int(rng.integers(1, 4))):  # several instants per step
+                t += int(rng.integers(1, 3)) * S
+                n_l, n_r = int(rng.integers(1, 40)), int(rng.integers(1, 60))
+                join.process_batch_index(0, 2, O.Batch({"id": rng.integers(0, 25, n_l), "a": rng.integers(0, 10**6, n_l),
+                                                        O.TIMESTAMP: np.full(n_l, t, dtype=np.int64)}), ctx, out)
+                join.process_batch_index(1, 2, O.Batch({"seller": rng.integers(10, 40, n_r), "id": rng.integers(0, 10**6, n_r),
+                                                        "b": rng.integers(0, 9, n_r), O.TIMESTAMP: np.full(n_r, t, dtype=np.int64)}),
+                                         ctx, out)
+            wm = t - int(rng.integers(0, 3)) * S  # sometimes leaves the newest instants buffered
+            for side in (0, 1):
+                ctx.watermarks.set(side, wm)
+            join.handle_watermark(wm, ctx, out)
+        with pytest.raises(RuntimeError):  # instant_join.rs:129-139
+            join.process_batch_index(0, 2, O.Batch({"id": np.array([1]), "a": np.array([1]),
+                                                    O.TIMESTAMP: np.array([T0], dtype=np.int64)}), ctx, out)
+        for side in (0, 1):
+            ctx.watermarks.set(side, O.FINAL_WATERMARK)
+        join.handle_watermark(O.FINAL_WATERMARK, ctx, out)
+        return [r for b in out.batches for r in b.rows()]
+
+    cfg = O.JoinConfig(left_on=["id"], right_on=["seller"], join_type=join_type)
+    rng = np.random.default_rng(3)
+    want = drive(O.InstantJoin(cfg))
+    rng = np.random.default_rng(3)
+    got = drive(c_oracle.InstantJoin(cfg))
+    assert ms(got) == ms(want)
+    assert len(want) > 100
