@@ -147,8 +147,111 @@ class SlidingAggregatingWindowFunc(_WindowOp):
     sliding = True
 
 
-SessionAggregatingWindowFunc = O.SessionAggregatingWindowFunc
 run_single_input = O.run_single_input
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# session windows (session_oracle.c)
+# ---------------------------------------------------------------------------------------------------------------
+SESSION_LIB = os.path.join(HERE, "liboracle_session.so")
+_session_lib = None
+
+
+class _SessionOut(C.Structure):
+    _fields_ = [(n, I64P) for n in ("key", "start", "end", "rows", "sum", "mn", "mx", "ts")] + [
+        ("avg", C.POINTER(C.c_double)), ("n", C.c_int64), ("cap", C.c_int64)]
+
+
+def load_session():
+    global _session_lib
+    if _session_lib is not None:
+        return _session_lib
+    src = os.path.join(HERE, "session_oracle.c")
+    if not os.path.exists(SESSION_LIB) or os.path.getmtime(SESSION_LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", HERE, "liboracle_session.so"])
+    lib = C.CDLL(SESSION_LIB)
+    lib.oracle_session_create.restype = C.c_void_p
+    lib.oracle_session_create.argtypes = [C.c_int64, C.c_int]
+    lib.oracle_session_destroy.argtypes = [C.c_void_p]
+    lib.oracle_session_error.restype = C.c_int
+    lib.oracle_session_error.argtypes = [C.c_void_p]
+    lib.oracle_session_late_rows.restype = C.c_uint64
+    lib.oracle_session_late_rows.argtypes = [C.c_void_p]
+    lib.oracle_session_process_batch.argtypes = [C.c_void_p, I64P, I64P, I64P, C.c_int64, C.c_int, C.c_int64]
+    lib.oracle_session_out_create.restype = C.POINTER(_SessionOut)
+    lib.oracle_session_out_clear.argtypes = [C.POINTER(_SessionOut)]
+    lib.oracle_session_out_destroy.argtypes = [C.POINTER(_SessionOut)]
+    lib.oracle_session_handle_watermark.argtypes = [C.c_void_p, C.c_int64, C.POINTER(_SessionOut)]
+    _session_lib = lib
+    return lib
+
+
+class SessionAggregatingWindowFunc:
+    """The oracle's session operator interface over session_oracle.c (at most one Int64 key column and one Int64
+    value column; COUNT(*) / SUM / AVG / MIN / MAX)."""
+
+    def __init__(self, cfg: O.SessionConfig):
+        self.cfg = cfg
+        self.lib = load_session()
+        cols = {a.col for a in cfg.aggs if a.col is not None}
+        assert len(cols) <= 1 and len(cfg.key_names) <= 1
+        self.val_col = next(iter(cols)) if cols else None
+        self.key_col = cfg.key_names[0] if cfg.key_names else None
+        self.h = self.lib.oracle_session_create(cfg.gap, 1 if self.key_col else 0)
+        self.out = self.lib.oracle_session_out_create()
+
+    def name(self):
+        return "session_window"
+
+    def __del__(self):
+        try:
+            self.lib.oracle_session_destroy(self.h)
+            self.lib.oracle_session_out_destroy(self.out)
+        except Exception:
+            pass
+
+    def _check(self):
+        e = self.lib.oracle_session_error(self.h)
+        if e & 1:
+            raise RuntimeError("should not have flushed batches when adding a batch")
+        if e & 2:
+            raise RuntimeError("received a batch that starts before the current data_start - gap")
+
+    def process_batch(self, batch: O.Batch, ctx, collector):
+        n = batch.num_rows
+        if n == 0:
+            return
+        k = np.ascontiguousarray(batch[self.key_col], dtype=np.int64) if self.key_col else None
+        v = np.ascontiguousarray(batch[self.val_col], dtype=np.int64) if self.val_col else None
+        t = np.ascontiguousarray(batch[O.TIMESTAMP], dtype=np.int64)
+        wm = ctx.last_present_watermark()
+        self.lib.oracle_session_process_batch(self.h, _p(k) if k is not None else None, _p(v) if v is not None else None,
+                                              _p(t), n, 0 if wm is None else 1,
+                                              0 if wm is None else min(wm, (1 << 63) - 1))
+        self._check()
+
+    def handle_watermark(self, watermark, ctx, collector):
+        wm = ctx.last_present_watermark()
+        if wm is None:
+            return watermark
+        self.lib.oracle_session_out_clear(self.out)
+        self.lib.oracle_session_handle_watermark(self.h, min(wm, (1 << 63) - 1), self.out)
+        self._check()
+        o = self.out.contents
+        n = int(o.n)
+        if n:
+            def arr(p):
+                return np.ctypeslib.as_array(p, shape=(n,)).copy()
+            full = {"rows": arr(o.rows), "sum": arr(o.sum), "avg": np.ctypeslib.as_array(o.avg, shape=(n,)).copy(),
+                    "mn": arr(o.mn), "mx": arr(o.mx)}
+            items = [(self.key_col, arr(o.key))] if self.key_col else []
+            items[self.cfg.window_index:self.cfg.window_index] = [("window_start", arr(o.start)), ("window_end", arr(o.end))]
+            for a in self.cfg.aggs:
+                items.append((a.name, full[{"count": "rows", "sum": "sum", "avg": "avg", "min": "mn", "max": "mx"}[a.kind]]))
+            cols = dict(items)
+            cols[O.TIMESTAMP] = arr(o.ts)
+            collector.collect(O.Batch(cols))
+        return watermark
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -31,7 +31,7 @@ def test_accumulators_match_reference_updating_aggregate_goldens(golden, accumul
 
 C_CASES = ["sliding_window_end", "hourly_by_event_type", "tight_watermark", "month_loose_watermark",
            "most_active_driver_last_hour", "offset_impulse_join", "nexmark_q5", "windowed_inner_join",
-           "windowed_outer_join"]
+           "windowed_outer_join", "session_window", "global_session_window"]
 
 
 @pytest.mark.parametrize("name", C_CASES)
@@ -154,3 +154,43 @@ def test_c_join_matches_numpy_oracle_on_random_streams(join_type):
     got = drive(c_oracle.InstantJoin(cfg))
     assert ms(got) == ms(want)
     assert len(want) > 100
+
+
+@pytest.mark.parametrize("shape", ["bursts", "multi_row_runs", "disorder", "unkeyed"])
+def test_c_session_matches_numpy_oracle_on_random_streams(shape):
+    """session_oracle.c against the numpy restatement on streams that exercise the state machine's corners: bursts
+    separated by more / exactly / less than the gap, several rows of a key inside one batch (the scan's off-by-one),
+    bounded disorder with late rows, and the single global key."""
+    import numpy as np
+    from oracle import c_oracle
+    from tests.golden_cases import multiset as ms
+    S = 1_000_000_000
+    T0 = 1_700_000_000 * S
+    rng = np.random.default_rng({"bursts": 1, "multi_row_runs": 2, "disorder": 3, "unkeyed": 4}[shape])
+    gap = 2 * S
+    n_keys = 1 if shape == "unkeyed" else (12 if shape == "multi_row_runs" else 150)
+    rows = []
+    for k in range(n_keys):
+        t = T0 + int(rng.integers(0, 3 * gap))
+        for _ in range(25 if shape in ("multi_row_runs", "unkeyed") else 6):
+            for _ in range(int(rng.integers(1, 7))):
+                rows.append((t, k * 31 + 5, int(rng.integers(-1000, 1000))))
+                t += int(rng.integers(1, gap)) if rng.random() > 0.05 else gap
+            t += gap + int(rng.integers(1, 4 * gap))
+    jitter = S if shape == "disorder" else 0
+    rows.sort(key=lambda r: r[0] + (int(rng.integers(-jitter, jitter + 1)) if jitter else 0))
+    a = np.array(rows, dtype=np.int64)
+    batch = 400 if shape in ("multi_row_runs", "unkeyed") else 300
+    cols = {"key": a[:, 1].copy(), "value": a[:, 2].copy(), O.TIMESTAMP: a[:, 0].copy()}
+    keys = [] if shape == "unkeyed" else ["key"]
+    if shape == "unkeyed":
+        del cols["key"]
+    batches = O.source_batches(cols, batch)
+    cfg = O.SessionConfig(gap=gap, key_names=keys, window_index=len(keys),
+                          aggs=[O.Agg("sum", "value", "sum"), O.Agg("avg", "value", "avg"), O.Agg("min", "value", "mn"),
+                                O.Agg("max", "value", "mx"), O.Agg("count", None, "n")])
+    delay = S // 2 if shape == "disorder" else S
+    want = O.run_single_input(O.SessionAggregatingWindowFunc(cfg), batches, delay).all()
+    got = O.run_single_input(c_oracle.SessionAggregatingWindowFunc(cfg), batches, delay).all()
+    assert ms(got.rows()) == ms(want.rows())
+    assert want.num_rows > 15
