@@ -29,7 +29,67 @@ def timed(torch, fn, reps):
     return e0.elapsed_time(e1) / reps
 
 
+def cpu_join_rate(n_p, n_a, windows=3):
+    """The C restatement of the reference's instant join (oracle/join_oracle.c) on the q8 shape, one thread -- the
+    reference runs one task per subtask.  Returns input rows/s."""
+    import time
+
+    import numpy as np
+    from oracle import arroyo_oracle as O, c_oracle
+    rng = np.random.default_rng(1)
+    pid = rng.permutation(n_p).astype(np.int64) + 1000
+    name = rng.integers(0, 10**6, n_p, dtype=np.int64)
+    seller = rng.integers(0, n_p, n_a, dtype=np.int64) + 1000
+    auction = np.arange(n_a, dtype=np.int64)
+    reserve = rng.integers(1, 10**5, n_a, dtype=np.int64)
+    join = c_oracle.InstantJoin(O.JoinConfig(left_on=["id"], right_on=["seller"], join_type="inner"))
+    ctx, out = O.OperatorContext(2), O.Collector()
+    t0 = None
+    for w in range(windows + 1):
+        if w == 1:
+            t0 = time.perf_counter()  # the first window warms the allocations up
+        ts = T0 + (w + 1) * 30 * S - 1
+        join.process_batch_index(0, 2, O.Batch({"id": pid, "name_code": name, O.TIMESTAMP: np.full(n_p, ts, dtype=np.int64)}), ctx, out)
+        join.process_batch_index(1, 2, O.Batch({"seller": seller, "auction": auction, "reserve": reserve,
+                                                O.TIMESTAMP: np.full(n_a, ts, dtype=np.int64)}), ctx, out)
+        for side in (0, 1):
+            ctx.watermarks.set(side, ts + 1)
+        join.handle_watermark(ts + 1, ctx, out)
+        out.batches.clear()
+    return windows * (n_p + n_a) / (time.perf_counter() - t0)
+
+
+def cpu_session_rate(n_keys, srows, steps=6, warm=8):
+    """The C restatement of the reference's session operator (oracle/session_oracle.c), one thread."""
+    import time
+
+    import numpy as np
+    from oracle import arroyo_oracle as O, c_oracle
+    rng = np.random.default_rng(1)
+    op = c_oracle.SessionAggregatingWindowFunc(O.SessionConfig(
+        gap=5 * S, key_names=["key"], aggs=[O.Agg("sum", "value", "sum"), O.Agg("count", None, "n")], window_index=1))
+    ctx, out = O.OperatorContext(1), O.Collector()
+    sv = rng.integers(0, 10**6, srows, dtype=np.int64)
+    offs = np.sort(rng.integers(0, S, srows, dtype=np.int64))
+    t0 = None
+    for p in range(warm + steps):
+        if p == warm:
+            t0 = time.perf_counter()
+        key = rng.integers(0, n_keys, srows, dtype=np.int64) * 7919
+        op.process_batch(O.Batch({"key": key, "value": sv, O.TIMESTAMP: offs + (T0 + p * S)}), ctx, out)
+        ctx.watermarks.set(0, T0 + p * S - S)
+        op.handle_watermark(T0 + p * S - S, ctx, out)
+        out.batches.clear()
+    return steps * srows / (time.perf_counter() - t0)
+
+
 def main():
+    if "--cpu-only" in sys.argv:
+        # the CPU restatements alone (no GPU needed): same shapes as the GPU cases below
+        print(json.dumps({"join_cpu_rows_per_s_1_thread": cpu_join_rate(1 << 21, 1 << 23),
+                          "session_cpu_rows_per_s_1_thread": cpu_session_rate(int(os.environ.get("SESSION_KEYS", 10_000_000)), 1 << 22)},
+                         indent=1))
+        return
     import pyarrow as pa
     import torch
 
@@ -38,7 +98,7 @@ def main():
     from arroyo_b200 import ffi, operators as native
     from arroyo_b200.multi_gpu import DevicePartitioner
 
-    only = set(sys.argv[1:])  # e.g. `join session`; empty = everything
+    only = {a for a in sys.argv[1:] if not a.startswith("--")}  # e.g. `join session`; empty = everything
 
     def want(section):
         return not only or section in only
@@ -55,11 +115,14 @@ def main():
     g = torch.Generator(device=dev)
     g.manual_seed(1)
 
-    def rec(name, config, rows, ms, bytes_per_row, note=""):
+    def rec(name, config, rows, ms, bytes_per_row, note="", cpu=None):
         gbs = rows * bytes_per_row / (ms * 1e-3) / 1e9
         out.append({"operator": name, "config": config, "rows_per_step": rows, "ms_per_step": round(ms, 4),
                     "rows_per_s": rows / (ms * 1e-3), "algorithmic_bytes_per_row": bytes_per_row,
                     "achieved_GBps": round(gbs, 1), "frac_of_measured_hbm_peak": round(gbs / peak, 4), "note": note})
+        if cpu is not None:  # the C restatement of the reference algorithm on one host thread, same shape
+            out[-1]["cpu_port_rows_per_s"] = cpu
+            out[-1]["cpu_port_threads"] = 1
         print(f"# {name}: {rows / (ms * 1e-3) / 1e9:.2f} G rows/s, {gbs:.0f} GB/s", file=sys.stderr, flush=True)
 
     raw_schema = pa.schema([("key", pa.int64()), ("value", pa.int64()), ("_timestamp", pa.timestamp("ns"))])
@@ -148,7 +211,8 @@ def main():
         ms = timed(torch, lambda r: jstep(3 + r), 10)
         rec("InstantJoin (inner)", f"configs[3] shape: per 30 s window {n_p} persons x {n_a} auctions on person id = seller, "
             f"{rows_out // 10} joined rows out", n_p + n_a, ms, (24 * n_p + 32 * n_a + 48 * (rows_out // 10)) / (n_p + n_a),
-            "inputs read once + joined rows (6 columns) written once; includes the arena append and the compaction")
+            "inputs read once + joined rows (6 columns) written once; includes the arena append and the compaction",
+            cpu=cpu_join_rate(n_p, n_a))
         jop.close()
         del pid, name, seller, auction, reserve
         torch.cuda.empty_cache()
@@ -179,7 +243,8 @@ def main():
         ms = timed(torch, lambda r: sstep(14 + r), 12)
         rec("SessionAggregatingWindowFunc", f"configs[4] shape: gap 5 s, {n_keys} keys, 4 Mi rows per second of event time, "
             f"{sess_out // 12} sessions closed per step", srows, ms, 24,
-            "one thread per key replays the reference's per-key state machine; inputs read once")
+            "one thread per key replays the reference's per-key state machine; inputs read once",
+            cpu=cpu_session_rate(n_keys, srows))
         sop.close()
 
     if want("wm"):
