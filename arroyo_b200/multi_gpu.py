@@ -291,8 +291,9 @@ class PartialsPlan:
             self.owner_op.flush()  # more rounds follow: the receive buffers come round again
         sink(self.owner_op, eff)
 
-    def pipeline(self, sink, lag: int = 2):
-        """LaggedCombiner over this plan's operators; `sink(owner_op, eff)` emits."""
+    def pipeline(self, sink, lag: int = 2, exchange=None):
+        """LaggedCombiner over this plan's operators; `sink(owner_op, eff)` emits.  `exchange`: an object with
+        ShuffleExchange's round_packed contract that partitions by itself (native_exchange.NativeExchange)."""
         torch = self.torch
         dev = torch.cuda.current_device()
         stream = torch.cuda.current_stream()
@@ -310,6 +311,8 @@ class PartialsPlan:
 
         def pack(chunk):
             cols, m = chunk
+            if exchange is not None:
+                return cols, None, m  # the native exchange partitions inside its round
             packed, counts = self.part.pack(cols, m, counts_out=self.ex.ctrl)
             return packed, counts, m
 
@@ -320,8 +323,8 @@ class PartialsPlan:
             if consume_now:
                 self.owner_op.flush()
 
-        return LaggedCombiner(self.ex, local_close, pack, owner_ingest, lambda eff: sink(self.owner_op, eff), lag=lag,
-                              thread_init=thread_init)
+        return LaggedCombiner(exchange if exchange is not None else self.ex, local_close, pack, owner_ingest,
+                              lambda eff: sink(self.owner_op, eff), lag=lag, thread_init=thread_init)
 
     def close(self):
         self.owner_op.close()
@@ -574,7 +577,13 @@ def bench(args, torch, dist, rank, world, local):
         for n, _ in owner_op.handle_watermark_device(eff):
             rows_out += n
 
-    pipe = plan.pipeline(lambda op, w: emit(w)) if (plan is not None and not args.sync_plan) else None
+    native_ex = None
+    if plan is not None and not args.sync_plan and getattr(args, "native_exchange", False):
+        # opt-in: the shuffle round as one C call (csrc/exchange.cu); not the measured default
+        from .native_exchange import NativeExchange
+        native_ex = NativeExchange(torch, dist, rank, world, local, stream, plan.N_COLS, 0, plan.part_rows,
+                                   2 * plan.part_rows)
+    pipe = plan.pipeline(lambda op, w: emit(w), exchange=native_ex) if (plan is not None and not args.sync_plan) else None
 
     def step_partials(p):
         k, v, t = panes[p]
@@ -659,6 +668,8 @@ def bench(args, torch, dist, rank, world, local):
     sent = ex.bytes_sent - sent0
     if pipe is not None:
         pipe.close()
+    if native_ex is not None:
+        native_ex.close()
     if plan is not None:
         plan.close()
     else:

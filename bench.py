@@ -73,6 +73,9 @@ def parse():
     ap.add_argument("--local-chunk-log2", type=int, default=23,
                     help="N>1, partials: rows per ingest launch of the local stage = 2^n; short launches let the owner "
                          "stage's kernels in between")
+    ap.add_argument("--native-exchange", action="store_true",
+                    help="N>1, partials: the shuffle round as one C call with NCCL from C++ (csrc/exchange.cu); "
+                         "experimental, not the measured default")
     ap.add_argument("--sync-plan", action="store_true",
                     help="N>1, partials: run the local stage, the shuffle and the owner stage in sequence on one host "
                          "thread instead of as a two-stage pipeline")
