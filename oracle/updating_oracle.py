@@ -170,3 +170,46 @@ def merge_change_stream(batches: Sequence[Optional[Batch]], key_names: Sequence[
             else:
                 state[k] = {c: v for c, v in r.items() if c not in (IS_RETRACT, TIMESTAMP)}
     return [state[k] for k in sorted(state)]
+
+
+class JoinWithExpiration:
+    """SURVEY.md 8(f) rank 3, inner joins of append-only inputs only: arroyo-worker/src/arrow/join_with_expiration.rs.
+
+    process_left / process_right (:42-108): the arriving batch is inserted into its side's key-time table
+    (KeyTimeView::insert, arroyo-state/src/tables/expiring_time_key_map.rs:997-1046: rows grouped per key), the other
+    side's stored rows of the batch's keys are fetched (get_batch :970-985) and the pair goes through the join plan
+    (compute_pair :110-130) -- so every matching pair is emitted exactly once, when its later row arrives.  Rows leave
+    the tables only through the state backend's retention (`ttl`, applied at restore / compaction), never inside a
+    run: not restated.  Outer joins rely on the planner's updating-join rewrite and are out of this restatement.
+    Output = [left payload..., right payload (clashing names get `_right`)..., _timestamp = max(l.ts, r.ts)]."""
+
+    def __init__(self, left_on: str, right_on: str):
+        self.on = (left_on, right_on)
+        self.rows: List[Dict[int, List[dict]]] = [{}, {}]  # side -> key -> stored rows
+        self.names: List[Optional[List[str]]] = [None, None]
+
+    def name(self):
+        return "JoinWithExpiration"
+
+    def _pair(self, l: dict, r: dict) -> dict:
+        out = {k: v for k, v in l.items() if k != TIMESTAMP}
+        for k, v in r.items():
+            if k != TIMESTAMP:
+                out[k if k not in out else k + "_right"] = v
+        out[TIMESTAMP] = max(l[TIMESTAMP], r[TIMESTAMP])
+        return out
+
+    def process_batch_index(self, index: int, total_inputs: int, batch: Batch, ctx=None, collector=None):
+        side = index // (total_inputs // 2)
+        other = 1 - side
+        new_rows = batch.rows()
+        for r in new_rows:                                   # insert first (:52, :83) ...
+            self.rows[side].setdefault(r[self.on[side]], []).append(r)
+        out = []
+        for r in new_rows:                                   # ... then join the batch with the other side's rows
+            for o in self.rows[other].get(r[self.on[side]], ()):
+                out.append(self._pair(r, o) if side == 0 else self._pair(o, r))
+        if out and collector is not None:
+            cols = {k: np.array([x[k] for x in out]) for k in out[0]}
+            collector.collect(Batch(cols))
+        return out

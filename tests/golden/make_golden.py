@@ -125,6 +125,9 @@ def main():
             state[after["id"]] = after
     acc["debezium_agg"] = [{"product": products[v["id"][2:]], "c": v["c"], "d": v["d"], "q": v["q"]}
                            for _, v in sorted(state.items())]
+    # updating_inner_join.sql: impulse A JOIN impulse_odd B ON A.counter = B.counter (append-only inputs, inner join)
+    acc["updating_inner_join"] = [r["after"] for r in lines(os.path.join(BASE, "golden_outputs", "updating_inner_join.json"))
+                                  if r["op"] == "c"]
     with open(os.path.join(OUT, "accumulators.json"), "w") as f:
         json.dump(acc, f, separators=(",", ":"), sort_keys=True)
     print({q: len(v) for q, v in acc.items()})

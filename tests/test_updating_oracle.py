@@ -93,3 +93,23 @@ def test_random_retractions_against_brute_force(seed):
         out = run(U.IncrementalAggregatingFunc(U.UpdatingAggConfig(["k"], aggs)), batches, flush_every)
         got = {r["k"]: r for r in U.merge_change_stream(out, ["k"])}
         assert got == want
+
+
+@pytest.mark.parametrize("order", ["left_first", "right_first", "alternating"])
+def test_updating_inner_join_golden(golden, accumulator_golden, order):
+    """SURVEY.md 8(f) rank 3 (inner case): impulse A JOIN impulse_odd B ON A.counter = B.counter -- every matching
+    pair leaves exactly once, whichever side's row arrives later."""
+    from tests.golden_cases import multiset
+    counter, ts = golden[0]["impulse_counter"], golden[0]["impulse_ts"]
+    odd = counter % 2 == 1
+    left = O.source_batches({"counter": counter, O.TIMESTAMP: ts}, BATCH)
+    right = O.source_batches({"counter": counter[odd], O.TIMESTAMP: ts[odd]}, BATCH)
+    join = U.JoinWithExpiration("counter", "counter")
+    feed = {"left_first": [(0, b) for b in left] + [(1, b) for b in right],
+            "right_first": [(1, b) for b in right] + [(0, b) for b in left],
+            "alternating": [x for pair in zip([(0, b) for b in left], [(1, b) for b in right] + [None] * len(left)) for x in pair if x]}[order]
+    out = []
+    for side, b in feed:
+        out += join.process_batch_index(side, 2, b)
+    got = [{"left_count": r["counter"], "right_count": r["counter_right"]} for r in out]
+    assert multiset(got) == multiset(accumulator_golden["updating_inner_join"])
