@@ -268,14 +268,31 @@ int32_t arroyo_b200_op_run_batches(ArroyoB200Op* op, struct ArrowArray* batches,
       if (async_emit) {
         collect(true);  // windows leave in order: the previous emission first
         o->pending_out = new BatchesPriv();
-        o->begin_watermark(wm);
+        try {
+          o->begin_watermark(wm);
+        } catch (...) {
+          // same clean-up as arroyo_b200_op_handle_watermark_begin: nothing half-emitted stays pending
+          o->poll_watermark(true);
+          ArroyoB200Batches tmp{};
+          batches_finish(o->pending_out, &tmp);
+          batches_release(&tmp);
+          o->pending_out = nullptr;
+          throw;
+        }
       } else {
         o->handle_watermark(wm, acc, nullptr);
       }
     }
     if (async_emit) collect(false);
   });
-  batches_finish(acc, out);
+  if (out) {
+    batches_finish(acc, out);
+  } else {
+    // null `out` was rejected above: drop whatever was accumulated instead of writing through it
+    ArroyoB200Batches tmp{};
+    batches_finish(acc, &tmp);
+    batches_release(&tmp);
+  }
   return st;
 }
 

@@ -414,6 +414,9 @@ static void* d2h(const void* dev, size_t bytes, cudaStream_t s, uint64_t* acc) {
 
 void InstantJoinOp::handle_watermark(int64_t wm, BatchesPriv* out_host, std::vector<ArroyoB200DeviceBatch>* out_dev) {
   AB_CUDA(cudaSetDevice(device_));
+  // validated before any state changes: a refused call must leave the eligible rows where they are
+  AB_REQUIRE(out_host != nullptr || join_type_ == ARROYO_B200_JOIN_INNER, ARROYO_B200_UNSUPPORTED,
+             "device-resident join output is only available for inner joins (no validity bitmaps)");
   Side& L = side_[0];
   Side& R = side_[1];
   unsigned long long* sc = scalars_.as<unsigned long long>();

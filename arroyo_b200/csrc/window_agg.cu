@@ -53,7 +53,7 @@ struct Counters {
   unsigned long long late_rows;
   unsigned long long deferred;
   unsigned long long lost;
-  unsigned long long reserved0;
+  unsigned long long neg_ts;  // rows with _timestamp < 0 (pre-epoch): the reference panics on them
   unsigned long long max_q;  // newest on-time pane number (ts / slide) seen
   unsigned long long big_vals;  // rows deferred because a value exceeded the exact-AVG guard
   unsigned int n_keys;
@@ -462,8 +462,10 @@ __global__ void __launch_bounds__(THREADS, AB_INGEST_MIN_BLOCKS) ingest_kernel(c
 #endif
       // K1: pane = ts / slide, i.e. bin = ts - ts % slide (tumbling_aggregating_window.rs:65-73)
       const uint64_t q = sd.div((uint64_t)ts);
+      // pre-epoch timestamps have no pane (the division is unsigned): reported, never aggregated
+      if (valid && ts < 0) atomicAdd(&p.counters->neg_ts, 1ull);
       // K7: late bins are dropped (tumbling :282-291, sliding :631-633)
-      const bool live = valid && q >= p.late_q;
+      const bool live = valid && ts >= 0 && q >= p.late_q;
       late += (valid && !live) ? 1u : 0u;
       // refresh the cached pane when this lane moved to another pane; the vote keeps the warp-combined
       // count flush convergent
@@ -957,11 +959,13 @@ class WindowAggOp final : public OpBase {
   PinnedBuf h_out_count_;
 
   ArroyoB200Stats st_{};
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> emit_events_;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> emit_events_;  // pooled: [0, emit_events_used_) are recorded
+  size_t emit_events_used_ = 0;
 
   // helpers
   void set_device() { AB_CUDA(cudaSetDevice(device_)); }
   void alloc_dictionary(uint64_t id_cap);
+  void preallocate();
   void grow_ids();
   void apply_l2_policy();
   void promote_avg();
@@ -988,6 +992,7 @@ class WindowAggOp final : public OpBase {
                    std::vector<ArroyoB200DeviceBatch>* out_dev);
   void export_window(OutSet* os, int64_t n, BatchesPriv* out_host);
   void export_partial(OutSet* os, int64_t n, BatchesPriv* out);
+  void collect_emit_times();
   void lookahead();
 };
 
@@ -1154,7 +1159,28 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
   d_emit_panes_.alloc(MAX_MERGE * sizeof(void*));
   d_out_count_.alloc(sizeof(unsigned int));
   h_out_count_.alloc(sizeof(unsigned int));
+  preallocate();
   AB_CUDA(cudaStreamSynchronize(stream_));
+}
+
+// Everything the steady state needs is allocated when the operator is created: the panes of one full window
+// plus the look-ahead panes, the running-window block, one set of deferred-row columns and two output sets.
+// cudaMalloc inside process_batch / handle_watermark serialises the device and showed up as milliseconds per
+// step in short runs (the driver's 5-warm-up / 20-step scaling runs timed little else).
+void WindowAggOp::preallocate() {
+  const size_t block_bytes = (size_t)n_acc_ * id_cap_ * sizeof(unsigned long long);
+  size_t want = (sliding_ ? (size_t)(width_ / slide_) : 1) + 4 + (running_mode_ ? 1 : 0);
+  const size_t budget = (size_t)4 << 30;
+  want = std::min<size_t>(std::min<size_t>(want, 64), std::max<size_t>(budget / std::max<size_t>(block_bytes, 1), 4));
+  for (size_t i = 0; i < want; ++i) {
+    pane_storage_.emplace_back(block_bytes);
+    auto* blk = pane_storage_.back().as<unsigned long long>();
+    init_block(blk, id_cap_);
+    free_panes_.emplace_back(blk, 0);  // already holds the identity: nothing to reset when it is acquired
+  }
+  for (int c = 0; c < 2 + n_vals_; ++c) defer_[0][c].alloc(defer_cap_ * 8);
+  out_set(0, id_cap_);
+  out_set(1, id_cap_);
 }
 
 WindowAggOp::~WindowAggOp() {
@@ -1474,7 +1500,7 @@ void WindowAggOp::flush_copies() {
   const size_t n = copy_dst_.size();
   if (n == 0) return;
   bool done = false;
-#if CUDART_VERSION >= 12080
+#if CUDART_VERSION >= 12080 && CUDART_VERSION < 13000  // CUDA 13 dropped the failIdx parameter
   if (batch_copy_ok_ && n > 1) {
     cudaMemcpyAttributes at{};
     at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;  // the sources stay valid until the release event
@@ -1921,6 +1947,8 @@ void WindowAggOp::absorb(int li) {
     }
   }
   if (c.lost) throw Error(ARROYO_B200_RUNTIME, "deferred-row buffer overflowed; rows were lost");
+  if (c.neg_ts)
+    throw Error(ARROYO_B200_PANIC, "batch holds a negative _timestamp (before the Unix epoch): the reference panics on it");
   lookahead();
 }
 
@@ -2047,7 +2075,7 @@ WindowAggOp::OutSet* WindowAggOp::out_set(size_t i, uint64_t cap) {
   while (out_sets_.size() <= i) out_sets_.emplace_back(new OutSet());
   OutSet* os = out_sets_[i].get();
   if (os->cap < cap) {
-    uint64_t c = std::max<uint64_t>(cap, 1024);
+    uint64_t c = std::max<uint64_t>(std::max<uint64_t>(cap, id_cap_), 1024);
     os->key.alloc(c * 8);
     os->wstart.alloc(c * 8);
     os->wend.alloc(c * 8);
@@ -2111,11 +2139,14 @@ int64_t WindowAggOp::run_emit(const std::vector<const unsigned long long*>& bloc
   }
   const uint32_t n_iter = ((n_ids + 1) / 2 + EMIT_THREADS - 1) / EMIT_THREADS;
   int grid = (int)std::min<uint32_t>(std::max<uint32_t>(n_iter, 1u), (uint32_t)num_sms_ * 8);
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (profile_) {
-    AB_CUDA(cudaEventCreate(&e0));
-    AB_CUDA(cudaEventCreate(&e1));
-    AB_CUDA(cudaEventRecord(e0, stream_));
+    if (emit_events_used_ == emit_events_.size()) {
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      AB_CUDA(cudaEventCreate(&e0));
+      AB_CUDA(cudaEventCreate(&e1));
+      emit_events_.emplace_back(e0, e1);
+    }
+    AB_CUDA(cudaEventRecord(emit_events_[emit_events_used_].first, stream_));
   }
 #define AB_EMIT(N)                                                               \
   do {                                                                          \
@@ -2137,8 +2168,8 @@ int64_t WindowAggOp::run_emit(const std::vector<const unsigned long long*>& bloc
 #undef AB_EMIT
   AB_CUDA(cudaGetLastError());
   if (profile_) {
-    AB_CUDA(cudaEventRecord(e1, stream_));
-    emit_events_.emplace_back(e0, e1);
+    AB_CUDA(cudaEventRecord(emit_events_[emit_events_used_].second, stream_));
+    ++emit_events_used_;
     st_.emit_rows_timed += n_ids;
   }
   ++st_.kernel_launches;
@@ -2401,6 +2432,18 @@ void WindowAggOp::handle_watermark(int64_t wm, BatchesPriv* out_host, std::vecto
   for (auto& kv : panes_)
     if (kv.first < late_bin_ && !kv.second.in_tier && !execs.count(kv.first)) dead.push_back(kv.first);
   for (int64_t b : dead) drop_pane(b);
+  // Panes below the late bin can no longer receive rows: they give their ring slot back (the block stays with the
+  // pane).  The ring then only ever spans [late bin, newest bin], so a pane the planner never visits again -- the
+  // reference leaks those too (sliding :176-187) -- cannot collide with a pane 4096 slides later.
+  for (auto& kv : panes_) {
+    if (kv.first >= late_bin_) break;
+    Pane& p = kv.second;
+    if (p.slot < 0) continue;
+    h_pane_bins_[p.slot] = FREE_BIN;
+    h_pane_ptrs_[p.slot] = nullptr;
+    p.slot = -1;
+    ring_dirty_ = true;
+  }
   // make the pane at the watermark resident so the next rows do not defer
   if (wm != INT64_MAX && max_bin_seen_ != LLONG_MIN) {
     if (!panes_.count(late_bin_)) {
@@ -2408,16 +2451,19 @@ void WindowAggOp::handle_watermark(int64_t wm, BatchesPriv* out_host, std::vecto
       if (h_pane_bins_[slot] == FREE_BIN && late_bin_ <= max_bin_seen_ + 2 * slide_) ensure_pane(late_bin_);
     }
   }
-  if (profile_) {
-    for (auto& e : emit_events_) {
-      float ms = 0;
-      AB_CUDA(cudaEventElapsedTime(&ms, e.first, e.second));
-      st_.emit_ms += ms;
-      cudaEventDestroy(e.first);
-      cudaEventDestroy(e.second);
-    }
-    emit_events_.clear();
+  collect_emit_times();
+}
+
+// Adds up the emit kernels' CUDA-event times (FLAG_PROFILE); the events go back to the pool.
+void WindowAggOp::collect_emit_times() {
+  if (!profile_ || emit_events_used_ == 0) return;
+  AB_CUDA(cudaEventSynchronize(emit_events_[emit_events_used_ - 1].second));
+  for (size_t i = 0; i < emit_events_used_; ++i) {
+    float ms = 0;
+    AB_CUDA(cudaEventElapsedTime(&ms, emit_events_[i].first, emit_events_[i].second));
+    st_.emit_ms += ms;
   }
+  emit_events_used_ = 0;
 }
 
 void WindowAggOp::handle_checkpoint(int64_t wm, BatchesPriv* out) {
@@ -2469,6 +2515,7 @@ void WindowAggOp::handle_checkpoint(int64_t wm, BatchesPriv* out) {
     p.exported = true;
   }
   AB_CUDA(cudaStreamSynchronize(stream_));
+  collect_emit_times();
 }
 
 // Restore (tumbling :228-248, sliding :556-595): partial batches go back into pane blocks.
@@ -2550,8 +2597,15 @@ void WindowAggOp::on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, i
         pp.state[acc] = keep.back().as<unsigned long long>();
       }
     }
-    AB_REQUIRE(pp.state[0] != nullptr, ARROYO_B200_UNSUPPORTED,
-               "restore needs a COUNT(*) or AVG state column to recover per-key row counts");
+    if (pp.state[0] == nullptr) {
+      // SUM / MIN / MAX-only plans carry no row count in their partial state; the rows accumulator is only the
+      // "this key is present in the pane" flag for them, so every restored state row counts as one
+      std::vector<unsigned long long> ones((size_t)rows, 1ull);
+      keep.emplace_back((size_t)rows * 8);
+      AB_CUDA(cudaMemcpyAsync(keep.back().p, ones.data(), (size_t)rows * 8, cudaMemcpyHostToDevice, stream_));
+      AB_CUDA(cudaStreamSynchronize(stream_));
+      pp.state[0] = keep.back().as<unsigned long long>();
+    }
     direct_decided_ = true;  // ids are being handed out by the restore: too late to reserve a direct range
     while (keyed_ && (uint64_t)n_keys_host_ + (uint64_t)rows >= id_cap_ / 2) {
       AB_CUDA(cudaStreamSynchronize(stream_));

@@ -32,7 +32,11 @@ NO_WM = -(1 << 63)
 class DevicePartitioner:
     """arroyo_b200_partition over torch device tensors (the product path)."""
 
-    def __init__(self, torch, world: int, n_cols: int, key_col: int, max_rows: int, device: int, stream: int = 0):
+    def __init__(self, torch, world: int, n_cols: int, key_col: int, max_rows: int, device: int, stream: int):
+        if not stream:
+            # stream 0 would make the library create a private stream with no ordering against the torch stream
+            # that produces `cols` and reads `counts` (include/arroyo_b200.h, stream-ordering contract)
+            raise ValueError("DevicePartitioner needs the explicit CUDA stream its inputs are produced on")
         self.torch = torch
         self.lib = ffi.load()
         self.h = C.c_void_p()
@@ -515,33 +519,14 @@ def _e2e_partials(args, torch, dist, B, ab, native, rank, world, local, device, 
                     "-> host Arrow windows"}
 
 
-def bench(args, torch, dist, rank, world, local):
-    """Weak scaling: every GPU ingests its own 16 Mi-row/pane shard of the stream.
-
-    --shuffle partials (default): partial -> shuffle -> final.  Each GPU pre-aggregates its shard per pane
-        (the same ingest kernel), and when a pane can no longer receive rows its partial rows
-        (key, sum, count) are hash-partitioned on the device and exchanged with an NCCL all-to-all; the
-        owner of a key merges the partials into its sliding-window state and emits.  Same results as
-        shuffling raw rows (SURVEY.md 8(e): combiner), 1/16 of the bytes over NVLink.
-    --shuffle rows: the reference's plan shape -- raw rows are partitioned and exchanged, each GPU
-        aggregates only the keys it owns."""
-    import json
-
+def _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, panes, W, K, collect=False):
+    """One pass of the N-GPU plan over this rank's `panes`: W warm-up steps, K timed steps (CUDA events, max over
+    ranks).  With `collect` every window this rank emits is reduced to checksums on the device (a verification pass;
+    its time means nothing).  Returns a dict."""
     import pyarrow as pa
 
-    import arroyo_b200 as ab
-    import bench as B
-    from . import operators as native
-
-    device = torch.device("cuda", local)
-    # torch, NCCL's ordering, the partitioner and the owner stage share the explicit stream bench.py installed
-    # (passing the legacy default stream's handle, 0, would make every native handle create a private stream)
-    assert torch.cuda.current_stream().cuda_stream != 0
-    W, K = max(args.warmup, 3), args.steps
-    rows = args.rows_per_pane
+    rows = panes[0][0].numel()
     nb = rows // B.BATCH_ROWS
-    gen_pane = B.make_generator(torch, device, rows, args.keys, args.dist, 42 + rank, args.keyspace)
-    panes = [gen_pane(p) for p in range(W + K)]
     mins, maxs = [], []
     for (_, _, t) in panes:
         tb = t.view(nb, B.BATCH_ROWS)
@@ -571,15 +556,19 @@ def bench(args, torch, dist, rank, world, local):
         part = DevicePartitioner(torch, world, 3, 0, part_rows, local, stream)
         ex = ShuffleExchange(torch, dist, rank, world, part, device, max_recv_rows=2 * part_rows, n_cols=3)
     rows_out = 0
+    sums = {}
 
     def emit(eff):
         nonlocal rows_out
-        for n, _ in owner_op.handle_watermark_device(eff):
+        emitted = owner_op.handle_watermark_device(eff)
+        for n, _ in emitted:
             rows_out += n
+        if collect:
+            for ws, we, n, cnt, sm, av in B.window_checksums(torch, device, emitted):
+                sums[ws] = (we, n, cnt, sm, av)
 
     native_ex = None
     if plan is not None and not args.sync_plan and getattr(args, "native_exchange", False):
-        # opt-in: the shuffle round as one C call (csrc/exchange.cu); not the measured default
         from .native_exchange import NativeExchange
         native_ex = NativeExchange(torch, dist, rank, world, local, stream, plan.N_COLS, 0, plan.part_rows,
                                    2 * plan.part_rows)
@@ -629,6 +618,9 @@ def bench(args, torch, dist, rank, world, local):
 
     step = step_partials if mode == "partials" else step_rows
     timed_op = local_op if mode == "partials" else owner_op
+    sampler = B.ClockSampler(local)
+    if rank == 0 and not collect:
+        sampler.start()
     for p in range(W):
         step(p)
     if pipe is not None:
@@ -638,12 +630,11 @@ def bench(args, torch, dist, rank, world, local):
     dist.barrier()
     st0 = timed_op.stats()
     so0 = owner_op.stats()
+    rows_out_warm = rows_out
     rows_out = 0
     sent0 = ex.bytes_sent
-    sampler = B.ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.begin()
     e0.record()
     for p in range(W, W + K):
         step(p)
@@ -654,11 +645,12 @@ def bench(args, torch, dist, rank, world, local):
         local_op.flush()
     e1.record()
     torch.cuda.synchronize()
+    sampler.end()
     dist.barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and not collect) else None
     st1 = timed_op.stats()
     so1 = owner_op.stats()
     d = {k: st1[k] - st0[k] for k in st1}
@@ -675,6 +667,75 @@ def bench(args, torch, dist, rank, world, local):
     else:
         owner_op.close()
         part.close()
+    torch.cuda.empty_cache()
+    return {"ms": ms, "d": d, "launches": int(tot[0].item()), "rows_out": int(tot[1].item()), "sent": sent,
+            "clocks": clocks, "sums": sums, "pipelined": pipe is not None, "rows_out_warm": rows_out_warm}
+
+
+def _gather_window_sums(torch, dist, device, sums):
+    """Sums the per-window checksums over the ranks (keys are disjoint across owners, so a window's global
+    checksum is the sum of the owners').  Every rank emits the same windows (same effective watermarks)."""
+    ws_sorted = sorted(sums)
+    n = torch.tensor([len(ws_sorted)], dtype=torch.int64, device=device)
+    nmax = n.clone()
+    dist.all_reduce(nmax, op=dist.ReduceOp.MAX)
+    nmin = n.clone()
+    dist.all_reduce(nmin, op=dist.ReduceOp.MIN)
+    if int(nmax.item()) != int(nmin.item()):
+        return None, f"ranks emitted different numbers of windows ({int(nmin.item())}..{int(nmax.item())})"
+    if not ws_sorted:
+        return {}, None
+    ints = torch.tensor([[ws, sums[ws][0], sums[ws][1], sums[ws][2], (sums[ws][3] + (1 << 63)) % (1 << 64) - (1 << 63)]
+                         for ws in ws_sorted], dtype=torch.int64, device=device)
+    flt = torch.tensor([sums[ws][4] for ws in ws_sorted], dtype=torch.float64, device=device)
+    first = ints[:, :2].clone()
+    dist.broadcast(first, src=0)
+    same = torch.tensor([int(torch.equal(first, ints[:, :2]))], dtype=torch.int64, device=device)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    if int(same.item()) != 1:
+        return None, "ranks emitted different windows"
+    acc = ints[:, 2:].clone()
+    dist.all_reduce(acc)  # int64 adds wrap: the sum checksum stays a wrapping sum
+    dist.all_reduce(flt)
+    out = {}
+    for i, ws in enumerate(ws_sorted):
+        out[ws] = (sums[ws][0], int(acc[i, 0].item()), int(acc[i, 1].item()), int(acc[i, 2].item()) & ((1 << 64) - 1),
+                   float(flt[i].item()))
+    return out, None
+
+
+def bench(args, torch, dist, rank, world, local, all_cpus=None):
+    """Weak scaling: every GPU ingests its own 16 Mi-row/pane shard of the stream.
+
+    --shuffle partials (default): partial -> shuffle -> final.  Each GPU pre-aggregates its shard per pane
+        (the same ingest kernel), and when a pane can no longer receive rows its partial rows
+        (key, sum, count) are hash-partitioned on the device and exchanged with an NCCL all-to-all; the
+        owner of a key merges the partials into its sliding-window state and emits.  Same results as
+        shuffling raw rows (SURVEY.md 8(e): combiner), 1/16 of the bytes over NVLink.
+    --shuffle rows: the reference's plan shape -- raw rows are partitioned and exchanged, each GPU
+        aggregates only the keys it owns."""
+    import json
+    import os
+    import sys
+
+    import arroyo_b200 as ab
+    import bench as B
+    from . import operators as native
+
+    device = torch.device("cuda", local)
+    # torch, NCCL's ordering, the partitioner and the owner stage share the explicit stream bench.py installed
+    # (passing the legacy default stream's handle, 0, would make every native handle create a private stream)
+    assert torch.cuda.current_stream().cuda_stream != 0
+    # the combiner pipeline closes panes `lag` rounds late: that many more warm-up panes reach the steady state
+    W, K = B.steady_warmup(args.warmup, extra=2), args.steps
+    rows = args.rows_per_pane
+    mode = args.shuffle
+    gen_pane = B.make_generator(torch, device, rows, args.keys, args.dist, 42 + rank, args.keyspace)
+    panes = [gen_pane(p) for p in range(W + K)]
+    res = _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, panes, W, K)
+    del panes
+    ms, d = res["ms"], res["d"]
+
     e2e = None
     if mode == "partials" and not args.skip_e2e:
         # repeated like the single-GPU pass (the host links are shared with the box's other tenants): median reported
@@ -685,34 +746,71 @@ def bench(args, torch, dist, rank, world, local):
         trials.sort(key=lambda r: r["value"])
         e2e = dict(trials[len(trials) // 2])
         e2e["trials"] = [round(r["value"]) for r in trials]
+        e2e["host_buffers"] = "pinned"
         del feed
+
+    # ---- verify: the same N-GPU plan over the panes the oracle consumes on rank 0 (union of the shards) ----
+    verify = cpu = None
+    if not args.skip_cpu:
+        VP = B.WIDTH // B.SLIDE + 6
+        n_rows = torch.zeros(1, dtype=torch.int64, device=device)
+        if rank == 0:
+            if all_cpus:
+                os.sched_setaffinity(0, all_cpus)
+            cpu = B.run_cpu(torch, args, device, budget_s=40.0, warm_panes=VP - 2, timed_panes=2,
+                            seeds=tuple(42 + r for r in range(world)))
+            n_rows[0] = cpu["rows_per_step"]
+        dist.broadcast(n_rows, src=0)
+        vrows = int(n_rows.item())
+        vp = [B.sample_pane(torch, device, gen_pane(p), vrows) for p in range(VP)]
+        vres = _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, vp, VP, 0, collect=True)
+        del vp
+        merged, err = _gather_window_sums(torch, dist, device, vres["sums"])
+        if rank == 0:
+            if err:
+                verify = {"verified": False, "mismatches": [err]}
+            else:
+                verify = B.compare_windows(merged, cpu["windows"], min_windows=VP - 7)
+            verify["rows_per_pane_per_gpu"] = vrows
+            verify["panes"] = VP
+            verify["plan"] = f"{world} GPUs, --shuffle {mode}: window checksums summed over the owners (all-reduce)"
+
     if rank == 0:
         peak, peak_kind = B.measured_peak()
+        traffic = B.ncu_traffic()
         ingest_gbs = 24.0 * d["ingest_rows_timed"] / (d["ingest_ms"] * 1e-3) / 1e9 if d["ingest_ms"] else None
         out = {"metric": "rows/sec sliding-window SUM (1M keys)", "value": world * K * rows / (ms * 1e-3),
-               "unit": "rows/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+               "unit": "rows/s", "n_gpus": world, "steps": K, "warmup": W, "warmup_requested": args.warmup,
+               "ms_per_step": ms / K,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-               "config": {"workload": "BASELINE configs[2]: hop(1s slide,10s width) SUM/AVG/COUNT GROUP BY key, "
-                                      f"{args.keys} i64 keys ({args.dist}); every GPU ingests {rows} rows/pane "
-                                      f"({rows // B.BATCH_ROWS} batches of {B.BATCH_ROWS}); key-hash shuffle over an NCCL "
-                                      "all-to-all; each GPU emits the windows of the keys it owns",
-                          "keys": args.keys, "rows_per_step_per_gpu": rows, "batch_rows": B.BATCH_ROWS,
-                          "shuffle": ("partial aggregates per pane (partial -> shuffle -> final)" if mode == "partials"
-                                      else "raw rows (reference plan shape)"),
-                          "l2": "inputs larger than L2, never re-read", "parallelism": f"key-partitioned x{world}",
-                          "numa": getattr(args, "numa", None)},
+               "config": B.workload_config(args, world),
+               "impl": {"shuffle": ("partial aggregates per pane (partial -> shuffle -> final)" if mode == "partials"
+                                    else "raw rows (reference plan shape)"),
+                        "numa": getattr(args, "numa", None),
+                        "warmup_note": "warm-up = max(--warmup, width/slide + 5) panes: the timed steps see the steady state"},
                "plan": (None if mode != "partials" else
                         "local stage and shuffle+owner stage on two host threads, watermarks ride on the data rounds, "
-                        "local stage closes panes 2 rounds behind (LaggedCombiner)" if pipe is not None else
+                        "local stage closes panes 2 rounds behind (LaggedCombiner)" if res["pipelined"] else
                         "synchronous: watermark exchange, local close, shuffle, owner stage in sequence"),
-               "rows_out_per_step": int(tot[1].item()) / max(K, 1), "gpu_launches": int(tot[0].item()),
-               "roofline": {"bound": "hbm", "kernel": "ingest_kernel<1>",
+               "rows_out_per_step": res["rows_out"] / max(K, 1), "gpu_launches": res["launches"],
+               "roofline": {"bound": "hbm", "kernel": (traffic or {}).get("kernel", "ingest"),
                             "achieved": round(ingest_gbs, 1) if ingest_gbs else None, "peak": peak,
                             "peak_kind": peak_kind, "unit": "GB/s",
-                            "frac": round(ingest_gbs / peak, 4) if ingest_gbs else None, "traffic": None,
+                            "frac": round(ingest_gbs / peak, 4) if ingest_gbs else None,
+                            "traffic": (round(traffic["dram_bytes_per_row"] * d["ingest_rows_timed"] /
+                                              max(d["ingest_launches"], 1))
+                                        if traffic and traffic.get("dram_bytes_per_row") else None),
+                            "algorithmic_bytes_per_launch": 24.0 * d["ingest_rows_timed"] / max(d["ingest_launches"], 1),
                             "note": "rank 0's raw-row ingest kernel"},
-               "e2e": e2e, "clocks": clocks,
-               "shuffle_bytes_sent_per_step_per_gpu": sent // max(K, 1)}
+               "e2e": e2e, "clocks": res["clocks"],
+               "shuffle_bytes_sent_per_step_per_gpu": res["sent"] // max(K, 1)}
+        if cpu is not None:
+            out["cpu_baseline"] = {"value": cpu["rows_per_s"], "unit": "rows/s", "cores": cpu["threads"], "kind": "port",
+                                   "sample": cpu["sample"]}
+            out["verify"] = verify
+            out["verified"] = verify["verified"]
         print(json.dumps(out), flush=True)
     dist.barrier()
     dist.destroy_process_group()
+    if rank == 0 and verify is not None and not verify["verified"]:
+        sys.exit("bench.py: GPU windows differ from the oracle's -- see the verify block of the line above")

@@ -67,6 +67,7 @@ def parse():
     ap.add_argument("--no-numa-bind", action="store_true",
                     help="do not bind the process to the CPUs local to its GPU (NVML affinity)")
     ap.add_argument("--e2e-trials", type=int, default=3, help="e2e passes (median reported, all listed)")
+    ap.add_argument("--skip-pageable", action="store_true", help="e2e: skip the extra pass over pageable host buffers")
     ap.add_argument("--sync-emit", action="store_true",
                     help="e2e: blocking arroyo_b200_op_handle_watermark instead of the begin / poll pair")
     ap.add_argument("--no-direct", action="store_true", help="measurement knob: hash dense keys as well")
@@ -134,21 +135,25 @@ def watermark_schedule(ts_min_max):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region.  The sampler process is started before
+    the warm-up (nvidia-smi needs tens of milliseconds to print its first line, longer than a 20-step timed region);
+    every line is stamped on arrival and `stop()` keeps the ones that arrived inside [begin(), end()]."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    PERIOD_MS = 5
 
     def __init__(self, index):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []  # (arrival time, text)
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", str(self.PERIOD_MS)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -156,18 +161,35 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        if self.t1 is None:
+            self.end()
+        time.sleep(2.5 * self.PERIOD_MS * 1e-3)  # the sample that was being taken when the region ended
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0 = self.t0 if self.t0 is not None else 0.0
+        slack = 2.0 * self.PERIOD_MS * 1e-3  # a line describes the period that ended when it was printed
+        inside = [ln for (t, ln) in self.lines if t0 <= t <= self.t1 + slack]
+        note = None
+        if not inside and self.lines:
+            # region shorter than the sampling period: the sample nearest to it
+            inside = [min(self.lines, key=lambda x: abs(x[0] - self.t1))[1]]
+            note = "timed region shorter than the sampling period: nearest sample"
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -180,8 +202,11 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+               "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def measured_peak():
@@ -211,6 +236,26 @@ def op_flags(args):
             (ffi.FLAG_AVG_F64 if args.avg_f64 else 0) | (ffi.FLAG_NO_DIRECT if args.no_direct else 0))
 
 
+def steady_warmup(requested, extra=0):
+    """Warm-up panes actually run: never fewer than one full window (width / slide panes) plus the pipeline lag and a
+    margin, whatever --warmup says.  The timed region must see the steady state (every pane of the window resident,
+    the running window primed, all buffers allocated); with fewer warm-up panes it times the cold start instead."""
+    return max(int(requested), WIDTH // SLIDE + 3 + extra)
+
+
+def workload_config(args, world):
+    """`config` of the JSON line: identical for both arms (--impl ours / reference)."""
+    rows = args.rows_per_pane
+    return {"workload": "BASELINE configs[2]: hop(1s slide,10s width) SUM/AVG/COUNT GROUP BY key, "
+                        f"{args.keys} i64 keys ({args.dist}, {args.keyspace}); every GPU's source shard delivers {rows} "
+                        f"rows per 1-s pane in {rows // BATCH_ROWS} Arrow-shaped batches of {BATCH_ROWS}; 1 step = 1 pane "
+                        "ingested per GPU + the 10-s window it closes emitted",
+            "keys": args.keys, "rows_per_step_per_gpu": rows, "batch_rows": BATCH_ROWS, "width_s": WIDTH // S,
+            "slide_s": SLIDE // S, "dist": args.dist, "keyspace": args.keyspace, "n_gpus": world,
+            "parallelism": "1 gpu" if world == 1 else f"key-partitioned x{world} (key-hash shuffle, NCCL all-to-all)",
+            "l2": f"inputs larger than L2 ({rows * 24 // 1000000} MB per step per GPU, never re-read)"}
+
+
 def window_config():
     import arroyo_b200 as ab
     return ab.WindowAggConfig(width=WIDTH, slide=SLIDE, key_names=["key"],
@@ -229,44 +274,116 @@ def host_panes(torch, gen_pane, n):
     return out
 
 
-def run_cpu(torch, args, device, budget_s, warm_panes, timed_panes):
+def sample_pane(torch, device, pane, n_rows):
+    """The bounded sample of one pane: whole BATCH_ROWS-row batches dropped uniformly (every batch keeps its shape).
+    n_rows == the pane's row count returns the pane itself."""
+    k, v, t = pane
+    rows = k.numel()
+    if n_rows >= rows:
+        return k, v, t
+    nb = rows // BATCH_ROWS
+    keep = torch.linspace(0, nb - 1, n_rows // BATCH_ROWS, device=device).round().to(torch.int64)
+    idx = (keep[:, None] * BATCH_ROWS + torch.arange(BATCH_ROWS, device=device)[None, :]).reshape(-1)
+    return k[idx], v[idx], t[idx]
+
+
+def run_cpu(torch, args, device, budget_s, warm_panes, timed_panes, seeds=(42,)):
     """Times the oracle port on all host cores over `timed_panes` panes after `warm_panes` warm-up panes.
-    If a full pane is too slow for the budget the timed panes carry fewer rows (bounded sample)."""
+    If a full pane is too slow for the budget the panes carry fewer rows (bounded sample).  `seeds`: the source
+    shards whose union the subtasks consume (one per GPU of the run being checked).  Also returns the per-window
+    checksums of everything it emitted: the GPU verify pass runs the same panes and must reproduce them."""
     from oracle import c_oracle
     threads = c_oracle.load().oracle_max_threads()
     threads = max(1, min(threads, 1024))
     rows = args.rows_per_pane
-    gen_pane = make_generator(torch, device, rows, args.keys, args.dist, 42)
     r = c_oracle.Runner(threads, WIDTH, SLIDE, WM_DELAY, BATCH_ROWS)
-    k, v, t = [x.cpu().numpy() for x in gen_pane(0)]
-    dt0 = r.feed(k, v, t)
-    # bounded sample: shrink the per-pane row count so the rest of the run fits the budget
-    est = dt0 * 2.5  # later panes also pay a 10-pane merge per slide
-    total = warm_panes + timed_panes - 1
-    frac = 1.0
-    if est * total > budget_s:
-        frac = max(budget_s / (est * total), 1.0 / 64)
-    n_rows = max(BATCH_ROWS, int(rows * frac) // BATCH_ROWS * BATCH_ROWS)
+    total = warm_panes + timed_panes
     step_s = []
-    for p in range(1, warm_panes + timed_panes):
-        k, v, t = gen_pane(p)
-        if n_rows < rows:
-            # every BATCH_ROWS-row batch keeps its shape; whole batches are dropped uniformly over the pane
-            nb = rows // BATCH_ROWS
-            keep = torch.linspace(0, nb - 1, n_rows // BATCH_ROWS, device=device).round().to(torch.int64)
-            idx = (keep[:, None] * BATCH_ROWS + torch.arange(BATCH_ROWS, device=device)[None, :]).reshape(-1)
-            k, v, t = k[idx], v[idx], t[idx]
-        dt = r.feed(k.cpu().numpy(), v.cpu().numpy(), t.cpu().numpy())
+    n_rows = rows
+    gens = {}
+
+    def pane_of(seed, p):
+        # one generator (2 GB of pooled keys / values) alive at a time
+        if seed not in gens:
+            gens.clear()
+            torch.cuda.empty_cache() if device.type == "cuda" else None
+            gens[seed] = make_generator(torch, device, rows, args.keys, args.dist, seed, args.keyspace)
+        return gens[seed](p)
+
+    # pane 0 at full size calibrates the sample
+    dt0 = 0.0
+    for seed in seeds:
+        k, v, t = [x.cpu().numpy() for x in pane_of(seed, 0)]
+        dt0 += r.feed(k, v, t)
+    est = dt0 * 2.5  # later panes also pay a 10-pane merge per slide
+    if est * (total - 1) > budget_s:
+        frac = max(budget_s / (est * (total - 1)), 1.0 / 64)
+        n_rows = max(BATCH_ROWS, int(rows * frac) // BATCH_ROWS * BATCH_ROWS)
+    if n_rows < rows:
+        # the calibration pane does not belong to the sampled stream: start over
+        r.close()
+        r = c_oracle.Runner(threads, WIDTH, SLIDE, WM_DELAY, BATCH_ROWS)
+        first = 0
+    else:
+        first = 1
+    for p in range(first, total):
+        dt = 0.0
+        for seed in seeds:
+            k, v, t = sample_pane(torch, device, pane_of(seed, p), n_rows)
+            dt += r.feed(k.cpu().numpy(), v.cpu().numpy(), t.cpu().numpy())
         if p >= warm_panes:
             step_s.append(dt)
     res = r.result()
+    windows = r.windows()
     r.close()
+    gens.clear()
     secs = sum(step_s)
-    return {"rows_per_s": n_rows * len(step_s) / secs, "threads": threads, "rows_per_step": n_rows,
+    return {"rows_per_s": len(seeds) * n_rows * len(step_s) / secs, "threads": threads, "rows_per_step": n_rows,
             "steps": len(step_s), "ms_per_step": 1e3 * secs / len(step_s), "rows_out": int(res.rows_out),
-            "sample": (f"{len(step_s)} panes x {n_rows} rows ({n_rows // BATCH_ROWS} batches of {BATCH_ROWS}) after "
-                       f"{warm_panes} warm-up panes, {args.keys} keys, hop(1s,10s); "
+            "windows": windows, "panes": total, "seeds": list(seeds),
+            "sample": (f"{len(step_s)} panes x {len(seeds)} shard(s) x {n_rows} rows ({n_rows // BATCH_ROWS} batches of "
+                       f"{BATCH_ROWS}) after {warm_panes} warm-up panes, {args.keys} keys, hop(1s,10s); "
                        f"{threads} key-partitioned single-threaded subtasks")}
+
+
+def window_checksums(torch, device, emitted):
+    """Checksums of windows left on the device by handle_watermark_device: `emitted` = [(n_rows, [column pointers])]
+    in the operator's output order [key, window.start, window.end, sum, avg, count, _timestamp].
+    Returns [(wstart, wend, rows_out, sum of counts, wrapping sum of sums, sum of avgs)]."""
+    from arroyo_b200.multi_gpu import _Ptr
+    out = []
+    for n, cols in emitted:
+        if n == 0:
+            continue
+        view = lambda c: torch.as_tensor(_Ptr(cols[c], n), device=device)  # noqa: E731
+        ws, we = view(1), view(2)
+        out.append((int(ws[0].item()), int(we[0].item()), int(n), int(view(5).sum().item()),
+                    int(view(3).sum().item()) & ((1 << 64) - 1), float(view(4).view(torch.float64).sum().item())))
+    return out
+
+
+def compare_windows(got, want, min_windows):
+    """got: {wstart: (wend, rows_out, counts, sums, avgs)} from the GPU run; want: the oracle's window list.
+    Bit-exact rows / counts / sums (wrapping), AVG checksum within 1e-6 relative (north-star tolerance)."""
+    ref = {w["wstart"]: w for w in want}
+    bad, checked = [], 0
+    for ws, (we, n, cnt, sm, av) in sorted(got.items()):
+        w = ref.get(ws)
+        if w is None:
+            bad.append(f"window {ws}: not emitted by the oracle")
+            continue
+        checked += 1
+        if (we, n, cnt, sm) != (w["wend"], w["rows_out"], w["sum_of_rows"], w["sum_of_sums"]):
+            bad.append(f"window {ws}: gpu (end {we}, rows {n}, count {cnt}, sum {sm}) != oracle (end {w['wend']}, rows "
+                       f"{w['rows_out']}, count {w['sum_of_rows']}, sum {w['sum_of_sums']})")
+        elif abs(av - w["sum_of_avgs"]) > 1e-6 * max(abs(w["sum_of_avgs"]), 1.0):
+            bad.append(f"window {ws}: avg checksum {av} vs {w['sum_of_avgs']}")
+    if checked < min_windows:
+        bad.append(f"only {checked} windows compared (expected at least {min_windows})")
+    return {"verified": not bad, "windows_checked": checked,
+            "against": "oracle/window_oracle.c (C restatement of the reference algorithm) on the same panes",
+            "checks": "per window: rows out, sum COUNT(*), wrapping sum SUM(value) bit-exact; sum AVG(value) 1e-6 relative",
+            **({"mismatches": bad[:8]} if bad else {})}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -326,11 +443,12 @@ def bind_to_gpu_numa_node(local):
         return f"unchanged ({type(e).__name__}: {e})"
 
 
-def device_resident(args, torch, native, ffi, local, gen_pane, W, K, rows):
-    """W warm-up + K timed steps with the input already in HBM; CUDA events on the operator's stream.
-    Returns (ms, stats delta, rows emitted, clocks)."""
+def device_resident(args, torch, native, ffi, local, panes, W, K, rows, collect=False):
+    """W warm-up + K timed steps over `panes` (already in HBM); CUDA events on the operator's stream.
+    Returns (ms, stats delta, rows emitted, clocks, per-window checksums if `collect`).  With `collect` every emitted
+    window is reduced to checksums on the device (torch kernels inside the loop): that pass verifies, it is not timed."""
     import pyarrow as pa
-    panes = [gen_pane(p) for p in range(W + K)]
+    device = torch.device("cuda", local)
     plans = build_batch_lists(torch, panes, rows)
     torch.cuda.synchronize()
     schema = pa.schema([("key", pa.int64()), ("value", pa.int64()), ("_timestamp", pa.timestamp("ns"))])
@@ -339,37 +457,45 @@ def device_resident(args, torch, native, ffi, local, gen_pane, W, K, rows):
     op = native.SlidingAggregatingWindowFunc(window_config(), input_schema=schema, device=local, stream=stream,
                                              flags=flags, expected_keys=args.keys, chunk_log2=args.chunk_log2)
     rows_out = 0
+    sums = {}
 
     def step(p):
         nonlocal rows_out
         for cols, nrows, wm in plans[p]:
             op.process_device_batches(cols, nrows, 3)
             if wm is not None:
-                for n, _ in op.handle_watermark_device(wm):
+                emitted = op.handle_watermark_device(wm)
+                for n, _ in emitted:
                     rows_out += n
+                if collect:
+                    for ws, we, n, cnt, sm, av in window_checksums(torch, device, emitted):
+                        sums[ws] = (we, n, cnt, sm, av)
 
+    sampler = ClockSampler(local)
+    if not collect:
+        sampler.start()
     for p in range(W):
         step(p)
     op.flush()
     torch.cuda.synchronize()
     st0 = op.stats()
     rows_out = 0
-    sampler = ClockSampler(local)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.begin()
     e0.record()
     for p in range(W, W + K):
         step(p)
     op.flush()
     e1.record()
     torch.cuda.synchronize()
+    sampler.end()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if not collect else None
     st1 = op.stats()
     op.close()
-    del panes, plans
+    del plans
     torch.cuda.empty_cache()
-    return ms, {k: st1[k] - st0[k] for k in st1}, rows_out, clocks
+    return ms, {k: st1[k] - st0[k] for k in st1}, rows_out, clocks, sums
 
 
 def run_ours(args):
@@ -397,13 +523,15 @@ def run_ours(args):
     torch.cuda.set_stream(torch.cuda.Stream(device=device, priority=-1))
     if world > 1:
         from arroyo_b200 import multi_gpu
-        return multi_gpu.bench(args, torch, dist, rank, world, local)
+        return multi_gpu.bench(args, torch, dist, rank, world, local, all_cpus)
 
-    W, K = max(args.warmup, 3), args.steps
+    W, K = steady_warmup(args.warmup), args.steps
     rows = args.rows_per_pane
     assert rows % BATCH_ROWS == 0
     gen_pane = make_generator(torch, device, rows, args.keys, args.dist, 42 + rank, args.keyspace)
-    ms, d, rows_out, clocks = device_resident(args, torch, native, ffi, local, gen_pane, W, K, rows)
+    panes = [gen_pane(p) for p in range(W + K)]
+    ms, d, rows_out, clocks, _ = device_resident(args, torch, native, ffi, local, panes, W, K, rows)
+    del panes
 
     value = K * rows / (ms * 1e-3)
     peak, peak_kind = measured_peak()
@@ -411,11 +539,17 @@ def run_ours(args):
     emit_share = d["emit_ms"] / ms if ms else None
     step_bytes = 24.0 * rows + 72.0 * args.keys + 48.0 * (rows_out / max(K, 1))
     traffic = ncu_traffic()
-    roof = {"bound": "hbm", "kernel": "ingest_kernel<1>", "achieved": round(ingest_gbs, 1) if ingest_gbs else None,
+    alg_per_launch = 24.0 * d["ingest_rows_timed"] / max(d["ingest_launches"], 1)
+    roof = {"bound": "hbm", "kernel": (traffic or {}).get("kernel", "ingest"),
+            "achieved": round(ingest_gbs, 1) if ingest_gbs else None,
             "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
             "frac": round(ingest_gbs / peak, 4) if ingest_gbs else None,
-            "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
-            "algorithmic_bytes_per_launch": 24.0 * d["ingest_rows_timed"] / max(d["ingest_launches"], 1),
+            # DRAM bytes of the ncu capture scaled to this run's launch size (the capture's own launch is recorded
+            # beside it), so `traffic` and `algorithmic_bytes_per_launch` describe the same launch
+            "traffic": (round(traffic["dram_bytes_per_row"] * d["ingest_rows_timed"] / max(d["ingest_launches"], 1))
+                        if traffic and traffic.get("dram_bytes_per_row") else None),
+            "traffic_source": (traffic or {}).get("source"),
+            "algorithmic_bytes_per_launch": alg_per_launch,
             "ingest_ms_per_step": d["ingest_ms"] / K, "emit_ms_per_step": d["emit_ms"] / K,
             "ingest_share_of_step": round(d["ingest_ms"] / ms, 3), "emit_share_of_step": round(emit_share, 3),
             "pipeline_frac": round(step_bytes * K / (ms * 1e-3) / 1e9 / peak, 4),
@@ -423,17 +557,13 @@ def run_ours(args):
             "host_watermark_ms_per_step": round(d["host_watermark_ms"] / K, 4)}
 
     out = {"metric": "rows/sec sliding-window SUM (1M keys)", "value": value, "unit": "rows/s", "n_gpus": 1,
-           "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-           "config": {"workload": "BASELINE configs[2]: hop(1s slide,10s width) SUM/AVG/COUNT GROUP BY key, "
-                                  f"{args.keys} i64 keys ({args.dist}, {args.keyspace}), {rows} rows/pane in {rows // BATCH_ROWS} "
-                                  f"batches of {BATCH_ROWS}, 1 step = 1 pane + 1 emitted window",
-                      "keys": args.keys, "rows_per_step": rows, "batch_rows": BATCH_ROWS, "width_s": 10, "slide_s": 1,
-                      "emission": "remerge" if args.remerge else "running add/evict",
-                      "avg": "f64 accumulator" if args.avg_f64 else "exact integer sum (guarded)",
-                      "combine": not args.no_combine,
-                      "l2": "inputs larger than L2 (402 MB per step, never re-read)", "parallelism": "1 gpu",
-                      "numa": args.numa},
+           "steps": K, "warmup": W, "warmup_requested": args.warmup, "ms_per_step": ms / K, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+           "config": workload_config(args, 1),
+           "impl": {"emission": "remerge" if args.remerge else "running add/evict",
+                    "avg": "f64 accumulator" if args.avg_f64 else "exact integer sum (guarded)",
+                    "combine": not args.no_combine, "numa": args.numa,
+                    "warmup_note": "warm-up = max(--warmup, width/slide + 3) panes: the timed steps see the steady state"},
            "rows_out_per_step": rows_out / max(K, 1), "gpu_launches": int(d["kernel_launches"]),
            "roofline": roof, "clocks": clocks}
 
@@ -442,12 +572,13 @@ def run_ours(args):
         # onto its ids and skips the dictionary probe.  Reported beside the headline, not instead of it.
         K2 = min(K, 30)
         gen2 = make_generator(torch, device, rows, args.keys, args.dist, 42 + rank, "dense")
-        ms2, d2, _, _ = device_resident(args, torch, native, ffi, local, gen2, W, K2, rows)
+        panes2 = [gen2(p) for p in range(W + K2)]
+        ms2, d2, _, _, _ = device_resident(args, torch, native, ffi, local, panes2, W, K2, rows)
         g2 = 24.0 * d2["ingest_rows_timed"] / (d2["ingest_ms"] * 1e-3) / 1e9 if d2["ingest_ms"] else None
         out["dense_keys"] = {"value": K2 * rows / (ms2 * 1e-3), "unit": "rows/s", "steps": K2, "ms_per_step": ms2 / K2,
                              "ingest_ms_per_step": d2["ingest_ms"] / K2, "roofline_frac": round(g2 / peak, 4) if g2 else None,
                              "keys": "1000 + n, n < 2^20 (direct-mapped ids, no dictionary probe)"}
-        del gen2
+        del gen2, panes2
 
     # ---- e2e: host Arrow batches in, host Arrow batches out, through the reference-facing call ----
     if not args.skip_e2e:
@@ -457,12 +588,23 @@ def run_ours(args):
         cpu = run_cpu(torch, args, device, budget_s=25.0, warm_panes=11, timed_panes=3)
         out["cpu_baseline"] = {"value": cpu["rows_per_s"], "unit": "rows/s", "cores": cpu["threads"], "kind": "port",
                                "sample": cpu["sample"]}
+        # ---- verify: the GPU operator over the very panes the oracle just consumed, window by window ----
+        vp = [sample_pane(torch, device, gen_pane(p), cpu["rows_per_step"]) for p in range(cpu["panes"])]
+        _, _, _, _, sums = device_resident(args, torch, native, ffi, local, vp, cpu["panes"], 0, cpu["rows_per_step"],
+                                           collect=True)
+        out["verify"] = compare_windows(sums, cpu["windows"], min_windows=cpu["panes"] - 4)
+        out["verify"]["rows_per_pane"] = cpu["rows_per_step"]
+        out["verify"]["panes"] = cpu["panes"]
+        out["verified"] = out["verify"]["verified"]
     print(json.dumps(out), flush=True)
+    if out.get("verified") is False:
+        sys.exit("bench.py: GPU windows differ from the oracle's -- see the verify block of the line above")
 
 
-def host_feed(torch, gen_pane, pane_ids, rows):
-    """Pinned host copies of the given panes as Arrow batches of BATCH_ROWS rows (zero copy: the Arrow buffers
-    *are* the pinned memory) and the watermark each batch triggers (fresh WatermarkGenerator)."""
+def host_feed(torch, gen_pane, pane_ids, rows, pinned=True):
+    """Host copies of the given panes as Arrow batches of BATCH_ROWS rows (zero copy: the Arrow buffers *are* the
+    host memory: page-locked by default, what a shim gets from arroyo_b200_host_alloc; `pinned=False` = ordinary
+    pageable allocations, what arrow-rs hands out by itself) and the watermark each batch triggers."""
     import pyarrow as pa
     nb = rows // BATCH_ROWS
     host_pool = {}
@@ -470,12 +612,12 @@ def host_feed(torch, gen_pane, pane_ids, rows):
     for p in pane_ids:
         k, v, t = gen_pane(p)
         if p % POOL not in host_pool:
-            hk = torch.empty(rows, dtype=torch.int64, pin_memory=True)
-            hv = torch.empty(rows, dtype=torch.int64, pin_memory=True)
+            hk = torch.empty(rows, dtype=torch.int64, pin_memory=pinned)
+            hv = torch.empty(rows, dtype=torch.int64, pin_memory=pinned)
             hk.copy_(k)
             hv.copy_(v)
             host_pool[p % POOL] = (hk, hv)
-        ht = torch.empty(rows, dtype=torch.int64, pin_memory=True)
+        ht = torch.empty(rows, dtype=torch.int64, pin_memory=pinned)
         ht.copy_(t)
         host.append([host_pool[p % POOL][0], host_pool[p % POOL][1], ht])
     torch.cuda.synchronize()
@@ -502,10 +644,11 @@ def run_e2e(args, torch, device, local, gen_pane):
     import arroyo_b200 as ab
     from arroyo_b200 import ffi, operators as native
     K = args.e2e_steps or min(args.steps, 10)
-    W = 11
+    W = steady_warmup(0)
     rows = args.rows_per_pane
     nb = rows // BATCH_ROWS
     batches, wms, _keep = host_feed(torch, gen_pane, range(W + K), rows)
+    host_kind = "pinned"
 
     def trial():
         """One fresh operator over the same pinned host batches: W warm-up panes, K timed panes."""
@@ -589,7 +732,7 @@ def run_e2e(args, torch, device, local, gen_pane):
                "arroyo_b200_op_handle_watermark_begin / _poll (windows copied back while the next batches are copied in)")
         loop = ("arroyo_b200_op_run_batches (run loop inside the library)" if args.e2e_host == "library" else
                 "arroyo_b200_op_process_batch per batch from Python")
-        return {"value": K * rows / dt, "unit": "rows/s", "h2d_bytes_per_step": rows * 24,
+        return {"value": K * rows / dt, "unit": "rows/s", "host_buffers": host_kind, "h2d_bytes_per_step": rows * 24,
                 "d2h_bytes_per_step": d2h // max(K, 1), "steps": K, "ms_per_step": 1e3 * dt / K,
                 "host_process_ms_per_step": round((st1["host_process_ms"] - st0["host_process_ms"]) / K, 3),
                 "host_watermark_ms_per_step": round((st1["host_watermark_ms"] - st0["host_watermark_ms"]) / K, 3),
@@ -603,28 +746,38 @@ def run_e2e(args, torch, device, local, gen_pane):
     out = dict(results[len(results) // 2])
     out["trials"] = [round(r["value"]) for r in results]
     out["trials_note"] = f"median of {n_trials} passes (fresh operator each, same pinned host batches)"
+    out["host_buffers_note"] = ("Arrow buffers are page-locked (cudaHostAlloc; a shim allocates its batch buffers with "
+                                "arroyo_b200_host_alloc).  `pageable` = the same pass over ordinary pageable buffers, "
+                                "which the driver stages through its own bounce buffers")
+    if not args.skip_pageable:
+        # arrow-rs allocates pageable memory unless told otherwise: the same run over pageable buffers, one pass
+        del batches, _keep
+        K = min(K, 5)
+        batches, wms, _keep = host_feed(torch, gen_pane, range(W + K), rows, pinned=False)
+        host_kind = "pageable"
+        pg = trial()
+        out["pageable"] = {"value": pg["value"], "unit": "rows/s", "steps": K, "ms_per_step": pg["ms_per_step"]}
     return out
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path on the host cores.  The Rust
     reference cannot be built in this image (no rustc/cargo, DataFusion/arrow-rs not vendored), so this is
-    the C port of its algorithm (oracle/window_oracle.c), pinned by the reference's golden vectors."""
+    the C port of its algorithm (oracle/window_oracle.c), pinned by the reference's golden vectors.
+    At --gpus N the subtasks consume the union of the N source shards (the same stream the N GPUs consume)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if torch.cuda.is_available() else torch.device("cpu")
-    W, K = max(args.warmup, 3), args.steps
-    cpu = run_cpu(torch, args, device, budget_s=150.0, warm_panes=W, timed_panes=K)
+    world = max(1, args.gpus)
+    W, K = steady_warmup(args.warmup), args.steps
+    cpu = run_cpu(torch, args, device, budget_s=150.0, warm_panes=W, timed_panes=K, seeds=tuple(42 + r for r in range(world)))
     line = {"impl": "reference", "metric": "rows/sec sliding-window SUM (1M keys)", "value": cpu["rows_per_s"],
-            "unit": "rows/s", "n_gpus": args.gpus, "steps": cpu["steps"], "warmup": W,
+            "unit": "rows/s", "n_gpus": args.gpus, "steps": cpu["steps"], "warmup": W, "warmup_requested": args.warmup,
             "ms_per_step": cpu["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[2]: hop(1s slide,10s width) SUM/AVG/COUNT GROUP BY key, "
-                                   f"{args.keys} i64 keys ({args.dist}); bounded sample per step: "
-                                   f"{cpu['rows_per_step']} rows", "keys": args.keys,
-                       "rows_per_step": cpu["rows_per_step"], "batch_rows": BATCH_ROWS},
+            "config": workload_config(args, world),
             "cpu_baseline": {"value": cpu["rows_per_s"], "unit": "rows/s", "cores": cpu["threads"], "kind": "port",
                              "sample": cpu["sample"]},
             "e2e": {"value": cpu["rows_per_s"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -121,7 +121,15 @@ typedef struct ArroyoB200Agg {
 typedef struct ArroyoB200OpConfig {
   int32_t kind;          /* ArroyoB200OpKind                                            */
   int32_t device;        /* CUDA ordinal                                                */
-  uint64_t stream;       /* optional caller-owned cudaStream_t (0 = library creates one) */
+  uint64_t stream;       /* caller-owned cudaStream_t, or 0: the library creates a private non-blocking stream.
+                          * STREAM-ORDERING CONTRACT: every kernel and copy of the handle is enqueued on this one
+                          * stream.  Device buffers passed to process_device_batch(es) must have been produced on it
+                          * (or the producer must have been synchronised with it before the call), and device output
+                          * (handle_watermark_device) is ready for work enqueued on it.  With stream = 0 the private
+                          * stream has NO ordering against any caller stream (the legacy default stream included): the
+                          * caller must synchronise its producer before the call and arroyo_b200_op_flush before it
+                          * reads device output or reuses the input buffers.  Host (Arrow) entry points need nothing:
+                          * they synchronise internally before they return host data.                                 */
   uint32_t task_index;   /* TaskInfo.task_index  (arroyo-types/src/lib.rs TaskInfo)     */
   uint32_t parallelism;  /* TaskInfo.parallelism                                        */
 

@@ -25,6 +25,12 @@ class RunResult(C.Structure):
                 ("sum_of_rows", C.c_uint64), ("sum_of_avgs", C.c_double), ("threads", C.c_int)]
 
 
+class WindowSum(C.Structure):
+    """Checksums of one emitted window (OracleWindowSum)."""
+    _fields_ = [("wstart", C.c_int64), ("wend", C.c_int64), ("rows_out", C.c_uint64), ("sum_of_rows", C.c_uint64),
+                ("sum_of_sums", C.c_uint64), ("sum_of_avgs", C.c_double)]
+
+
 def load():
     global _lib
     if _lib is not None:
@@ -56,6 +62,8 @@ def load():
     lib.oracle_runner_finish.argtypes = [C.c_void_p]
     lib.oracle_runner_result.argtypes = [C.c_void_p, C.POINTER(RunResult)]
     lib.oracle_runner_destroy.argtypes = [C.c_void_p]
+    lib.oracle_runner_windows.restype = C.c_int64
+    lib.oracle_runner_windows.argtypes = [C.c_void_p, C.POINTER(WindowSum), C.c_int64]
     _lib = lib
     return lib
 
@@ -408,6 +416,13 @@ class Runner:
         r = RunResult()
         self.lib.oracle_runner_result(self.h, C.byref(r))
         return r
+
+    def windows(self):
+        """[{wstart, wend, rows_out, sum_of_rows, sum_of_sums (wrapping u64), sum_of_avgs}] per emitted window."""
+        n = self.lib.oracle_runner_windows(self.h, None, 0)
+        buf = (WindowSum * max(n, 1))()
+        self.lib.oracle_runner_windows(self.h, buf, n)
+        return [{f: getattr(buf[i], f) for f, _ in WindowSum._fields_} for i in range(n)]
 
     def close(self):
         if self.h:

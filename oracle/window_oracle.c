@@ -469,33 +469,78 @@ int oracle_max_threads(void) {
   return n > 0 ? (int)n : 1;
 }
 
-/* minimal fork-join: items are claimed from a shared counter by `threads` pthreads */
+/* fork-join over a persistent pool: the workers are created once per process and parked on a condition
+ * variable between calls (a thread per call and worker cost ~1 000 pthread_create per pane and made the CPU
+ * figure pessimistic).  Items are claimed from a shared counter. */
 typedef struct {
   void (*fn)(int64_t item, void* ctx);
   void* ctx;
   int64_t n;
   int64_t next;
 } ParFor;
-static void* parfor_worker(void* arg) {
-  ParFor* pf = (ParFor*)arg;
+
+#define POOL_MAX 1024
+static struct {
+  pthread_mutex_t mu;
+  pthread_cond_t go, done;
+  pthread_t th[POOL_MAX];
+  int n_threads;      /* workers created so far */
+  int want;           /* workers that take part in the current job */
+  uint64_t gen;       /* job generation */
+  int running;        /* workers still inside the current job */
+  ParFor* job;
+} g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, {0}, 0, 0, 0, 0, NULL};
+
+static void parfor_drain(ParFor* pf) {
   for (;;) {
     int64_t i = __atomic_fetch_add(&pf->next, 1, __ATOMIC_RELAXED);
     if (i >= pf->n) break;
     pf->fn(i, pf->ctx);
   }
+}
+
+static void* pool_worker(void* arg) {
+  const int me = (int)(intptr_t)arg;
+  uint64_t seen = 0;
+  pthread_mutex_lock(&g_pool.mu);
+  for (;;) {
+    while (g_pool.gen == seen) pthread_cond_wait(&g_pool.go, &g_pool.mu);
+    seen = g_pool.gen;
+    if (me >= g_pool.want) continue;
+    ParFor* pf = g_pool.job;
+    pthread_mutex_unlock(&g_pool.mu);
+    parfor_drain(pf);
+    pthread_mutex_lock(&g_pool.mu);
+    if (--g_pool.running == 0) pthread_cond_signal(&g_pool.done);
+  }
   return NULL;
 }
+
 static void parallel_for(int64_t n, int threads, void (*fn)(int64_t, void*), void* ctx) {
   ParFor pf = {fn, ctx, n, 0};
   if (threads > n) threads = (int)n;
+  if (threads > POOL_MAX) threads = POOL_MAX;
   if (threads <= 1) {
-    parfor_worker(&pf);
+    parfor_drain(&pf);
     return;
   }
-  pthread_t th[1024];
-  for (int t = 1; t < threads; ++t) pthread_create(&th[t], NULL, parfor_worker, &pf);
-  parfor_worker(&pf);
-  for (int t = 1; t < threads; ++t) pthread_join(th[t], NULL);
+  const int helpers = threads - 1;  /* the caller works too */
+  pthread_mutex_lock(&g_pool.mu);
+  while (g_pool.n_threads < helpers) {
+    pthread_create(&g_pool.th[g_pool.n_threads], NULL, pool_worker, (void*)(intptr_t)g_pool.n_threads);
+    pthread_detach(g_pool.th[g_pool.n_threads]);
+    ++g_pool.n_threads;
+  }
+  g_pool.job = &pf;
+  g_pool.want = helpers;
+  g_pool.running = helpers;
+  ++g_pool.gen;
+  pthread_cond_broadcast(&g_pool.go);
+  pthread_mutex_unlock(&g_pool.mu);
+  parfor_drain(&pf);
+  pthread_mutex_lock(&g_pool.mu);
+  while (g_pool.running > 0) pthread_cond_wait(&g_pool.done, &g_pool.mu);
+  pthread_mutex_unlock(&g_pool.mu);
 }
 
 typedef struct {
@@ -557,13 +602,38 @@ static void final_flush(int64_t d, void* vctx) {
 /* A resumable run: p key-partitioned window subtasks on p threads, fed any number of row chunks.
  * Watermarks: WatermarkGenerator rule (watermark_generator.rs:150-197) with delay `wm_delay`, interval 1 s.
  * slide == 0 => tumbling. */
+/* checksums of one emitted window (all subtasks): what a GPU run of the same input is compared with */
+typedef struct {
+  int64_t wstart, wend;
+  uint64_t rows_out;
+  uint64_t sum_of_rows;  /* sum of COUNT(*) */
+  uint64_t sum_of_sums;  /* wrapping sum of SUM(value) */
+  double sum_of_avgs;
+} OracleWindowSum;
+
 typedef struct OracleRunner {
   RunCtx c;
   int64_t R;
   int64_t last_emitted_at;
   int64_t wm_delay;
   OracleRunResult acc;
+  OracleWindowSum* wins;
+  int64_t n_wins, cap_wins;
 } OracleRunner;
+
+static OracleWindowSum* runner_window(OracleRunner* r, int64_t wstart, int64_t wend) {
+  for (int64_t i = r->n_wins - 1; i >= 0; --i)
+    if (r->wins[i].wstart == wstart) return &r->wins[i];
+  if (r->n_wins == r->cap_wins) {
+    r->cap_wins = r->cap_wins ? r->cap_wins * 2 : 64;
+    r->wins = (OracleWindowSum*)realloc(r->wins, (size_t)r->cap_wins * sizeof(OracleWindowSum));
+  }
+  OracleWindowSum* w = &r->wins[r->n_wins++];
+  memset(w, 0, sizeof *w);
+  w->wstart = wstart;
+  w->wend = wend;
+  return w;
+}
 
 OracleRunner* oracle_runner_create(int p, int64_t width, int64_t slide, int64_t wm_delay, int64_t batch_rows) {
   if (p < 1 || p > 1024 || batch_rows < 1) return NULL;
@@ -595,10 +665,16 @@ static void runner_sink(OracleRunner* r) {
   for (int d = 0; d < c->p; ++d) {
     OracleOut* o = c->outs[d];
     int64_t last_w = NO_TIME;
+    OracleWindowSum* ws = NULL;
     for (int64_t i = 0; i < o->n; ++i) {
       r->acc.sum_of_sums += (uint64_t)o->sum[i];
       r->acc.sum_of_rows += (uint64_t)o->rows[i];
       r->acc.sum_of_avgs += o->avg[i];
+      if (!ws || ws->wstart != o->wstart[i]) ws = runner_window(r, o->wstart[i], o->wend[i]);
+      ws->rows_out += 1;
+      ws->sum_of_rows += (uint64_t)o->rows[i];
+      ws->sum_of_sums += (uint64_t)o->sum[i];
+      ws->sum_of_avgs += o->avg[i];
       if (d == 0 && o->wstart[i] != last_w) { ++r->acc.windows_out; last_w = o->wstart[i]; }
     }
     r->acc.rows_out += (uint64_t)o->n;
@@ -666,8 +742,15 @@ void oracle_runner_result(OracleRunner* r, OracleRunResult* res) {
   res->late_rows = late;
 }
 
+/* per-window checksums, in emission order; returns how many exist (copies at most `cap`) */
+int64_t oracle_runner_windows(OracleRunner* r, OracleWindowSum* out, int64_t cap) {
+  for (int64_t i = 0; i < r->n_wins && i < cap; ++i) out[i] = r->wins[i];
+  return r->n_wins;
+}
+
 void oracle_runner_destroy(OracleRunner* r) {
   if (!r) return;
+  free(r->wins);
   RunCtx* c = &r->c;
   for (int i = 0; i < c->p; ++i) {
     oracle_window_destroy(c->ops[i]);

@@ -592,6 +592,8 @@ def test_device_partitioner_matches_repartition(G, n_dest):
     import torch
     from arroyo_b200.multi_gpu import DevicePartitioner
     rng = np.random.default_rng(n_dest)
+    # the partitioner works on the stream that produces its inputs (stream-ordering contract, arroyo_b200.h)
+    torch.cuda.set_stream(torch.cuda.Stream())
     for n in (0, 1, 2047, 2048, 100_003):
         key = rng.integers(-2**63, 2**63 - 1, n, dtype=np.int64)
         val = rng.integers(0, 10**9, n, dtype=np.int64)
