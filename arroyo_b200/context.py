@@ -54,6 +54,13 @@ class StateTable:
     def get_min_time(self) -> Optional[int]:
         return min(self.batches) if self.batches else None
 
+    def flush(self, watermark: Optional[int]):
+        """ExpiringTimeKeyView::flush (expiring_time_key_map.rs:853-893): what a checkpoint keeps = the entries at
+        or after watermark - retention."""
+        if watermark is not None:
+            cutoff = watermark - self.retention
+            self.batches = {t: b for t, b in self.batches.items() if t >= cutoff}
+
     def all_batches_for_watermark(self, watermark: Optional[int]):
         cutoff = 0 if watermark is None else watermark - self.retention
         for t in sorted(self.batches):
@@ -79,6 +86,13 @@ class OperatorContext:
         if name not in self.tables:
             self.tables[name] = StateTable(retention)
         return self.tables[name]
+
+    def global_table(self, name: str) -> dict:
+        """GlobalKeyedView (arroyo-state/src/tables/global_keyed_map.rs): one value per subtask, all of them
+        visible to every subtask on restore."""
+        if not hasattr(self, "global_tables"):
+            self.global_tables = {}
+        return self.global_tables.setdefault(name, {})
 
 
 class Collector:

@@ -217,10 +217,16 @@ class InstantJoinOp final : public OpBase {
  public:
   explicit InstantJoinOp(const ArroyoB200OpConfig& c);
   ~InstantJoinOp() override;
-  void on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, int64_t, int64_t) override {
-    AB_REQUIRE(n == 0, ARROYO_B200_UNSUPPORTED, "InstantJoin restore: replay the 'left'/'right' tables through process_batch");
+  // on_start (instant_join.rs:205-247) IS a replay: the reference feeds every batch of table "left" to process_left and
+  // every batch of table "right" to process_right.  The shim does the same through process_batch (the two tables need
+  // two input indices, which this entry point does not carry); here only the restored watermark arrives, so that rows
+  // older than it are refused exactly as process_side refuses them (:129-139).
+  void on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, int64_t watermark, int64_t) override {
+    AB_REQUIRE(n == 0, ARROYO_B200_UNSUPPORTED,
+               "InstantJoin restore: pass the watermark here and replay the 'left' / 'right' tables through process_batch");
     (void)state;
     (void)schemas;
+    if (watermark != INT64_MIN) last_wm_ = watermark;
   }
   void process_batch(uint32_t index, uint32_t in_partitions, ArrowArray* batch, const ArrowSchema* schema) override;
   void process_device_batch(uint32_t index, uint32_t in_partitions, const uint64_t* cols, int32_t n_cols,

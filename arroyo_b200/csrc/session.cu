@@ -376,12 +376,14 @@ struct PrepParams {
   unsigned long long* ctr;
   unsigned long long arena_cap;
   unsigned long long* late;
+  long long* earliest;  // min _timestamp of every row ever accepted (what `keys_by_start_time.first_key_value()` holds)
 };
 
 __global__ void __launch_bounds__(ST) prep_kernel(const __grid_constant__ PrepParams p) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   unsigned long long late = 0;
+  long long min_ts = LLONG_MAX;
   const int lane = threadIdx.x & 31;
   // uniform trip count: the arena slots of a warp's rows come from one atomic per warp iteration
   const long long n_round = (p.n + stride - 1) / stride * stride;
@@ -418,10 +420,14 @@ __global__ void __launch_bounds__(ST) prep_kernel(const __grid_constant__ PrepPa
     p.a_id[o] = id;
     p.a_seq[o] = p.seq;
     p.a_ts[o] = ts;
+    min_ts = min(min_ts, ts);
     for (int v = 0; v < p.n_vals; ++v) p.a_val[v][o] = __ldcs(p.val[v] + i);
     atomicAdd(p.count + id, 1u);
   }
   if (late) atomicAdd(p.late, late);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) min_ts = min(min_ts, __shfl_xor_sync(0xffffffffu, min_ts, o));
+  if (lane == 0 && min_ts != LLONG_MAX) atomicMin(p.earliest, min_ts);
 }
 
 struct GroupParams {
@@ -588,14 +594,11 @@ class SessionOp final : public OpBase {
  public:
   explicit SessionOp(const ArroyoB200OpConfig& c);
   ~SessionOp() override;
-  void on_start(ArrowArray*, ArrowSchema*, int64_t n, int64_t, int64_t) override {
-    AB_REQUIRE(n == 0, ARROYO_B200_UNSUPPORTED,
-               "session restore: replay the batches of table 's' through process_batch (the reference checkpoints raw rows)");
-  }
+  void on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, int64_t watermark, int64_t start_time) override;
   void process_batch(uint32_t, uint32_t, ArrowArray* batch, const ArrowSchema* schema) override;
   void process_device_batch(uint32_t, uint32_t, const uint64_t* cols, int32_t n_cols, int64_t n_rows) override;
   void handle_watermark(int64_t wm, BatchesPriv* out_host, std::vector<ArroyoB200DeviceBatch>* out_dev) override;
-  void handle_checkpoint(int64_t, BatchesPriv*) override { flush(); }
+  void handle_checkpoint(int64_t, BatchesPriv* out) override;
   void on_close(int, BatchesPriv*) override { flush(); }
   void flush() override;
   void stats(ArroyoB200Stats* out) override {
@@ -642,7 +645,7 @@ class SessionOp final : public OpBase {
   DevBuf o_key_, o_start_, o_end_, o_ts_, o_agg_[ARROYO_B200_MAX_AGGS];
   std::vector<std::pair<cudaEvent_t, ArrowArray>> pending_;
   ArroyoB200Stats st_{};
-  DevBuf late_;
+  DevBuf late_, earliest_;
   uint64_t compact_min_ = 1u << 16;  // pools smaller than this are never compacted (ARROYO_B200_SESSION_COMPACT_MIN)
 
   void set_device() { AB_CUDA(cudaSetDevice(device_)); }
@@ -736,6 +739,11 @@ SessionOp::SessionOp(const ArroyoB200OpConfig& c) {
   ctr_.alloc(8 * sizeof(unsigned long long));
   h_ctr_.alloc(8 * sizeof(unsigned long long));
   late_.alloc(8);
+  earliest_.alloc(8);
+  {
+    const long long none = LLONG_MAX;
+    AB_CUDA(cudaMemcpyAsync(earliest_.p, &none, 8, cudaMemcpyHostToDevice, stream_));
+  }
   AB_CUDA(cudaMemsetAsync(ctr_.p, 0, 8 * sizeof(unsigned long long), stream_));
   AB_CUDA(cudaMemsetAsync(late_.p, 0, 8, stream_));
   n_keys_dev_.alloc(sizeof(unsigned int));
@@ -982,6 +990,7 @@ void SessionOp::prep(const long long* key, const long long* ts, const long long*
   p.ctr = ctr_.as<unsigned long long>();
   p.arena_cap = arena_cap_;
   p.late = late_.as<unsigned long long>();
+  p.earliest = earliest_.as<long long>();
   prep_kernel<<<grid_for((uint64_t)n, ST), ST, 0, stream_>>>(p);
   AB_CUDA(cudaGetLastError());
   ++st_.kernel_launches;
@@ -1115,6 +1124,65 @@ void SessionOp::flush() {
   apply_pending();
   AB_CUDA(cudaStreamSynchronize(stream_));
   release_inputs(true);
+}
+
+// handle_checkpoint (session_aggregating_window.rs:907-925): table "s" (the raw input batches) is written by the
+// shim as the batches arrive; what the operator contributes is its entry of the global table "e",
+// `earliest_batch_time()` = the first key of `keys_by_start_time` (:162-166).  Entries of that map are never
+// removed (only the key sets inside them are emptied, :125-141, :244-262), so the value is the earliest data start
+// the subtask has ever held = the smallest _timestamp of any row it accepted.  Returned as a one-column batch
+// [earliest_batch_time: timestamp ns] with one row, or no rows when the subtask has not seen data.
+void SessionOp::handle_checkpoint(int64_t, BatchesPriv* out) {
+  flush();
+  long long e = LLONG_MAX;
+  AB_CUDA(cudaMemcpyAsync(&e, earliest_.p, 8, cudaMemcpyDeviceToHost, stream_));
+  AB_CUDA(cudaStreamSynchronize(stream_));
+  const int64_t n = e == LLONG_MAX ? 0 : 1;
+  OutColumn c;
+  c.name = "earliest_batch_time";
+  c.format = "tsn:";
+  long long* h = (long long*)PinnedPool::get().alloc(8);
+  h[0] = e;
+  c.data = h;
+  std::vector<OutColumn> cols{c};
+  out->arrays.emplace_back();
+  out->schemas.emplace_back();
+  export_batch(cols, n, &out->arrays.back(), &out->schemas.back());
+}
+
+// on_start (session_aggregating_window.rs:802-847).  `start_time` = the minimum over the subtasks' entries of table
+// "e" (INT64_MIN: none, nothing is restored); `state` = the batches of table "s" from `start_time` on.  Every batch
+// is filtered to rows at or after `start_time` and added exactly like a newly arrived batch under the watermark
+// `start_time` (:826-835); then the sessions the restored watermark already closes are evicted and DROPPED (:837-845:
+// they were emitted before the checkpoint).
+void SessionOp::on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, int64_t watermark, int64_t start_time) {
+  set_device();
+  if (start_time != INT64_MIN) {
+    has_wm_ = true;
+    wm_ = start_time;
+    for (int64_t i = 0; i < n; ++i) {
+      process_batch(0, 1, &state[i], &schemas[i]);
+      apply_pending();  // every stored batch is its own input batch
+    }
+  } else {
+    AB_REQUIRE(n == 0, ARROYO_B200_INVALID_ARGUMENT, "session restore: state batches without a start time (table 'e')");
+  }
+  if (watermark == INT64_MIN) {
+    has_wm_ = false;  // no watermark has been seen yet: later batches are not filtered (:858-868)
+    flush();
+    return;
+  }
+  if (start_time != INT64_MIN) {
+    const ArroyoB200Stats before = st_;
+    std::vector<ArroyoB200DeviceBatch> evicted;
+    handle_watermark(watermark, nullptr, &evicted);
+    AB_CUDA(cudaStreamSynchronize(stream_));
+    st_.rows_out = before.rows_out;  // evicted results are not output
+    st_.windows_out = before.windows_out;
+  }
+  has_wm_ = true;
+  wm_ = watermark;
+  flush();
 }
 
 // Pools are bump allocated; when more than half of what has been handed out is dead they are rebuilt from the

@@ -385,9 +385,7 @@ class SessionAggregatingWindowFunc(_NativeOperator):
         names.insert(min(max(c.window_index, 0), len(names)), "window")
         return names + [a.name for a in c.aggs] + [TIMESTAMP]
 
-    def process_batch(self, batch: pa.RecordBatch, ctx: OperatorContext, collector: Collector):
-        if not self.created:
-            self._build(batch.schema.names)
+    def _send(self, batch: pa.RecordBatch):
         arr, sch = export_batch(batch)
         st = self._lib.arroyo_b200_op_process_batch(self._h, 0, 1, C.byref(arr), C.byref(sch))
         if st != ffi.OK and arr.release:
@@ -396,9 +394,67 @@ class SessionAggregatingWindowFunc(_NativeOperator):
             C.CFUNCTYPE(None, C.c_void_p)(sch.release)(C.addressof(sch))
         _check(self._lib, self._h, st)
 
+    def process_batch(self, batch: pa.RecordBatch, ctx: OperatorContext, collector: Collector):
+        if not self.created:
+            self._build(batch.schema.names)
+        # Table "s" holds the raw input rows that passed the late filter, keyed by the batch's newest timestamp
+        # (session_aggregating_window.rs:858-883).  The shim owns the table: it keeps the on-time rows of the batch it
+        # is about to hand over (the reference also sorts them; restore re-sorts, :829, so the order is not state).
+        wm = ctx.last_present_watermark()
+        kept = batch
+        if wm is not None:
+            import pyarrow.compute as pc
+            ts = batch.column(batch.schema.names.index(TIMESTAMP)).cast(pa.int64())
+            kept = batch.filter(pc.greater_equal(ts, min(wm, (1 << 63) - 1)))
+        if kept.num_rows:
+            ts = kept.column(kept.schema.names.index(TIMESTAMP)).cast(pa.int64())
+            import pyarrow.compute as pc
+            ctx.table("s", int(self.config.gap) * 100).insert(int(pc.max(ts).as_py()), kept)
+        self._send(batch)
+
     def process_device_batch(self, cols: List[int], n_rows: int):
+        """Device-resident input (operator chaining): the rows never reach the host, so table "s" is not maintained
+        and such a subtask cannot be restored from a checkpoint."""
         arr = (C.c_uint64 * len(cols))(*cols)
         _check(self._lib, self._h, self._lib.arroyo_b200_op_process_device_batch(self._h, 0, 1, arr, len(cols), n_rows))
+
+    def handle_checkpoint(self, barrier, ctx: OperatorContext, collector: Collector):
+        """session_aggregating_window.rs:907-925: flush table "s" at the watermark, publish this subtask's
+        earliest_batch_time() in the global table "e"."""
+        wm = ctx.last_present_watermark()
+        ctx.table("s", int(self.config.gap) * 100).flush(wm)
+        earliest = None
+        if self.created:
+            out = ffi.Batches()
+            st = self._lib.arroyo_b200_op_handle_checkpoint(self._h, ffi.INT64_MIN if wm is None else clamp_watermark(wm),
+                                                            C.byref(out))
+            _check(self._lib, self._h, st)
+            for b in import_batches(self._lib, out):
+                if b.num_rows:
+                    earliest = int(b.column(0).cast(pa.int64())[0].as_py())
+        ctx.global_table("e")[ctx.task_index] = earliest
+
+    def on_start(self, ctx: OperatorContext):
+        """session_aggregating_window.rs:802-847."""
+        starts = [v for v in ctx.global_table("e").values() if v is not None]
+        if not starts:
+            return
+        start_time = min(starts)
+        table = ctx.table("s", int(self.config.gap) * 100)
+        batches = [b for _, b in table.all_batches_for_watermark(start_time)]
+        if not self.created:
+            if not batches:
+                return
+            self._build(batches[0].schema.names)
+        n = len(batches)
+        arrs = (ffi.ArrowArray * max(n, 1))()
+        schs = (ffi.ArrowSchema * max(n, 1))()
+        for i, b in enumerate(batches):
+            b._export_to_c(C.addressof(arrs[i]), C.addressof(schs[i]))
+        wm = ctx.last_present_watermark()
+        st = self._lib.arroyo_b200_op_on_start(self._h, arrs, schs, n,
+                                               ffi.INT64_MIN if wm is None else clamp_watermark(wm), start_time)
+        _check(self._lib, self._h, st)
 
     def handle_watermark(self, watermark, ctx: OperatorContext, collector: Collector):
         wm = ctx.last_present_watermark()
@@ -485,9 +541,36 @@ class InstantJoin(_NativeOperator):
             C.CFUNCTYPE(None, C.c_void_p)(sch.release)(C.addressof(sch))
         _check(self._lib, self._h, st)
 
+    def on_start(self, ctx: OperatorContext):
+        """instant_join.rs:205-247: every batch of table "left" goes back through process_left, every batch of table
+        "right" through process_right (which also re-inserts them into the tables, :116-128)."""
+        wm = ctx.last_present_watermark()
+        replay = []
+        for side, name in enumerate(("left", "right")):
+            replay.append([b for _, b in ctx.table(name, 0).all_batches_for_watermark(wm)])
+        if self.created and wm is not None:
+            empty = (ffi.ArrowArray * 1)()
+            emptys = (ffi.ArrowSchema * 1)()
+            _check(self._lib, self._h, self._lib.arroyo_b200_op_on_start(self._h, empty, emptys, 0, clamp_watermark(wm),
+                                                                          ffi.INT64_MIN))
+        for side, batches in enumerate(replay):
+            for b in batches:
+                self.process_batch_index(side, 2, b, ctx, None)
+
+    def handle_checkpoint(self, barrier, ctx: OperatorContext, collector: Collector):
+        """instant_join.rs:285-303: both tables are flushed at the watermark (retention 0)."""
+        wm = ctx.last_present_watermark()
+        ctx.table("left", 0).flush(wm)
+        ctx.table("right", 0).flush(wm)
+
     def process_batch_index(self, index: int, in_partitions: int, batch: pa.RecordBatch, ctx: OperatorContext,
                             collector: Collector):
         side = index // (in_partitions // 2)
+        if batch.num_rows:
+            # process_side (:116-128): the raw batch goes into the side's table under its newest timestamp
+            import pyarrow.compute as pc
+            ts = batch.column(batch.schema.names.index(TIMESTAMP)).cast(pa.int64())
+            ctx.table("left" if side == 0 else "right", 0).insert(int(pc.max(ts).as_py()), batch)
         if self._schemas[side] is None:
             self._schemas[side] = batch.schema
         if not self.created:

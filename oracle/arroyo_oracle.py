@@ -247,6 +247,12 @@ class OperatorContext:
             self.tables[name] = ExpiringTimeKeyView(retention)
         return self.tables[name]
 
+    def global_table(self, name: str) -> dict:
+        """GlobalKeyedView (arroyo-state/src/tables/global_keyed_map.rs): one value per subtask."""
+        if not hasattr(self, "global_tables"):
+            self.global_tables = {}
+        return self.global_tables.setdefault(name, {})
+
 
 class Collector:
     """arroyo-operator/src/context.rs:490-494: collects output batches in emission order."""
@@ -817,6 +823,44 @@ class SessionAggregatingWindowFunc:
         self.cfg = cfg
         self.key_computations: Dict[tuple, _KeyComputingHolder] = {}
         self.keys_by_next_watermark_action: Dict[int, set] = {}
+        # `keys_by_start_time` (:50-54): only its first key is ever read (earliest_batch_time, :162-166), and its
+        # entries are never removed -- :125-141 and :244-262 empty the key *sets* -- so the first key is the smallest
+        # start time that was ever registered
+        self.start_times_seen: Optional[int] = None
+
+    def _note_start(self, t: Optional[int]):
+        if t is not None and (self.start_times_seen is None or t < self.start_times_seen):
+            self.start_times_seen = t
+
+    def earliest_batch_time(self) -> Optional[int]:
+        return self.start_times_seen
+
+    def tables(self):
+        return {"s": self.cfg.gap * 100, "e": 0}
+
+    def on_start(self, ctx: OperatorContext):
+        """:802-847."""
+        starts = [v for v in ctx.global_table("e").values() if v is not None]
+        if not starts:
+            return
+        start_time = min(starts)
+        table = ctx.table("s", self.cfg.gap * 100)
+        for _t, batches in list(table.all_batches_for_watermark(start_time)):
+            for batch in list(batches):
+                batch = batch.take(batch[TIMESTAMP] >= start_time)
+                if batch.num_rows == 0:
+                    continue
+                self._add_at_watermark(self._sort(batch), start_time)
+        wm = ctx.last_present_watermark()
+        if wm is None:
+            return
+        self._results_at_watermark(wm)  # evicted results are dropped (:837-845)
+
+    def handle_checkpoint(self, ctx: OperatorContext):
+        """:907-925."""
+        wm = ctx.last_present_watermark()
+        ctx.table("s", self.cfg.gap * 100).flush(wm)
+        ctx.global_table("e")[ctx.task_index] = self.earliest_batch_time()
 
     def name(self):
         return "session_window"
@@ -848,6 +892,7 @@ class SessionAggregatingWindowFunc:
             kc.add_batch(kb, watermark)
             after = kc.next_watermark_action()
             assert after is not None
+            self._note_start(kc.earliest_data())  # :228-262
             if before is not None and before != after:
                 self.keys_by_next_watermark_action[before].discard(key)
                 if not self.keys_by_next_watermark_action[before]:
@@ -880,6 +925,7 @@ class SessionAggregatingWindowFunc:
                 if kc.is_empty():
                     del self.key_computations[key]
                 else:
+                    self._note_start(kc.earliest_data())  # :127-141
                     nxt = kc.next_watermark_action()
                     if nxt == first:
                         raise RuntimeError("next watermark action did not advance")
@@ -1007,10 +1053,28 @@ class InstantJoin:
     def name(self):
         return "InstantJoin"
 
+    def tables(self):
+        return {"left": 0, "right": 0}  # :305-328
+
+    def on_start(self, ctx: OperatorContext):
+        """:205-247: replay both tables through process_left / process_right."""
+        wm = ctx.last_present_watermark()
+        for side, name in enumerate(("left", "right")):
+            batches = [b for _t, bs in ctx.table(name, 0).all_batches_for_watermark(wm) for b in bs]
+            for b in batches:
+                self._process_side(side, b, ctx)
+
+    def handle_checkpoint(self, ctx: OperatorContext):
+        """:285-303."""
+        wm = ctx.last_present_watermark()
+        ctx.table("left", 0).flush(wm)
+        ctx.table("right", 0).flush(wm)
+
     def _process_side(self, side: int, batch: Batch, ctx: OperatorContext):
         if batch.num_rows == 0:
             raise RuntimeError("should have max timestamp")  # :123 expect()
         ts = batch[TIMESTAMP]
+        ctx.table("left" if side == 0 else "right", 0).insert(int(ts.max()), batch)  # :116-128
         wm = ctx.last_present_watermark()
         if wm is not None and wm > int(ts.min()):
             raise RuntimeError("shouldn't have a batch with timestamp before the watermark")  # :129-139

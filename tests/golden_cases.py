@@ -116,11 +116,13 @@ def _drive_join(ops, join, left_out, right_out):
     InstantJoin.  Upstream window operators stamp every row of a window with one `_timestamp`
     and forward their watermark after the rows it released; here each side delivers all its
     batches, then the final watermark (order across sides does not matter to the join)."""
-    ctx = O.OperatorContext(2)
+    ctx = ops.join_ctx() if hasattr(ops, "join_ctx") else O.OperatorContext(2)
     out = O.Collector()
     for side, stream in ((0, left_out), (1, right_out)):
         for b in stream:
             join.process_batch_index(side, 2, b, ctx, out)
+        if side == 0 and hasattr(ops, "restart_join"):
+            join = ops.restart_join(join, ctx)  # checkpoint + restore between the two input streams
     for side in (0, 1):
         ctx.watermarks.set(side, O.FINAL_WATERMARK)
     join.handle_watermark(O.FINAL_WATERMARK, ctx, out)

@@ -46,3 +46,14 @@ def test_cuda_accumulators_match_reference_updating_aggregate_goldens(golden, ac
     from tests.golden_cases import ACCUMULATOR_CASES
     got = ACCUMULATOR_CASES[case](gpu_ops, golden[0])
     assert multiset(got) == multiset(accumulator_golden[case[0]])
+
+
+@pytest.mark.parametrize("frac", [0.3, 0.6])
+@pytest.mark.parametrize("name", WINDOW_ONLY)
+def test_cuda_operators_match_reference_golden_across_a_checkpoint_and_restore(golden, gpu_ops, name, frac):
+    """As the reference's smoke tests run every query (smoke_tests.rs): checkpoint mid-stream, throw the operator away,
+    restore a fresh one from the state tables ("t"; "s" + "e"; "left" / "right") and continue: still the golden."""
+    from tests.restart_ops import GpuKit, RestartOps
+    inputs, expected = golden
+    got = CASES[name](RestartOps(gpu_ops, GpuKit, frac), inputs)
+    assert multiset(got) == multiset(expected[name]), name

@@ -15,6 +15,18 @@ def test_oracle_matches_reference_golden(golden, name):
     assert multiset(got) == multiset(expected[name]), name
 
 
+@pytest.mark.parametrize("frac", [0.3, 0.6])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_reference_golden_across_a_checkpoint_and_restore(golden, name, frac):
+    """The reference's smoke tests checkpoint every query mid-stream, stop it and resume it from the checkpoint;
+    the output must still be the golden file (smoke_tests.rs).  Same here: pins handle_checkpoint / on_start of
+    the restated operators, state tables "t" (tumbling / sliding), "s" + "e" (session) and "left" / "right" (join)."""
+    from tests.restart_ops import OracleKit, RestartOps
+    inputs, expected = golden
+    got = CASES[name](RestartOps(O, OracleKit, frac), inputs)
+    assert multiset(got) == multiset(expected[name]), name
+
+
 @pytest.mark.parametrize("impl", ["numpy", "c"])
 @pytest.mark.parametrize("case", sorted(__import__("tests.golden_cases", fromlist=["x"]).ACCUMULATOR_CASES))
 def test_accumulators_match_reference_updating_aggregate_goldens(golden, accumulator_golden, case, impl):

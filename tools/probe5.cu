@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #define CK(x)                                                                               \
@@ -147,6 +148,7 @@ struct alignas(16) KSlot {
 };
 constexpr long long EMPTY_KEY = LLONG_MIN;
 constexpr uint32_t IDX_UNSET = 0xFFFFFFFFu;
+__device__ unsigned long long g_trap_code;
 
 // bucketed dictionary: B buckets x KS slots (global), ids = b * CAPB + idx
 constexpr int KS = 2048;
@@ -185,9 +187,14 @@ __device__ __noinline__ uint32_t bdict_insert(const BDict& d, uint32_t b, long l
       idx = IDX_UNSET;
     }
     if (k == key) {
-      while (idx == IDX_UNSET) {
+      for (long long spin = 0; idx == IDX_UNSET; ++spin) {
         __nanosleep(20);
         idx = *(volatile uint32_t*)&sp->idx;
+        if (spin > (1ll << 22)) {
+          g_trap_code = 0x1D2ull;
+          __threadfence_system();
+          __trap();
+        }
       }
       return idx;
     }
@@ -358,18 +365,27 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
                "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (long long spin = 0; !mbar_try(bar, parity); ++spin) {
+    if (spin > (1ll << 24)) {  // a second or so: the copy never completed
+      g_trap_code = 0xBA2ull;
+      __threadfence_system();
+      __trap();
+    }
+  }
 }
 
 template <int NW, int NST, int CH>
@@ -500,6 +516,22 @@ __global__ void __launch_bounds__(NW * 32, 1) agg2_kernel(const __grid_constant_
   if (miss) atomicAdd(p.misses, miss);
 }
 
+// smallest possible TMA round trip: one warp, one bulk copy, one mbarrier
+__global__ void tma_selftest(const Rec* src, Rec* dst, int n) {
+  __shared__ __align__(128) Rec buf[64];
+  __shared__ __align__(8) unsigned long long bar;
+  const uint32_t b = smem_u32(&bar);
+  if (threadIdx.x == 0) mbar_init(b, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(b, n * 16);
+    tma_load_1d(smem_u32(buf), src, n * 16, b);
+  }
+  mbar_wait(b, 0);
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = buf[threadIdx.x];
+}
+
 // reference: direct global atomics through the same dictionary
 __global__ void direct_kernel(const long long* key, const long long* val, long long n, BDict d, unsigned long long* rows,
                               unsigned long long* sum) {
@@ -530,15 +562,34 @@ __global__ void gen_kernel(long long* key, long long* val, long long* ts, long l
 }
 
 int main(int argc, char** argv) {
+  setvbuf(stdout, nullptr, _IOLBF, 0);
   const int rows_log2 = argc > 1 ? atoi(argv[1]) : 23;
   const int keys_log2 = argc > 2 ? atoi(argv[2]) : 20;
   const int hot = argc > 3 ? atoi(argv[3]) : 0;
+  const char* mode = argc > 4 ? argv[4] : "all";  // micro | tma | p1 | p2 | all
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;
   const double ghz = prop.clockRate * 1e-6;
-  printf("device %s, %d SMs, %.3f GHz\n", prop.name, sms, ghz);
-  run_micro(sms, ghz);
+  printf("device %s, %d SMs, %.3f GHz, mode %s\n", prop.name, sms, ghz, mode);
+  auto is = [&](const char* m) { return !strcmp(mode, m) || !strcmp(mode, "all"); };
+  if (is("micro")) run_micro(sms, ghz);
+  if (is("tma")) {
+    Rec *a, *b;
+    CK(cudaMalloc(&a, 64 * sizeof(Rec)));
+    CK(cudaMalloc(&b, 64 * sizeof(Rec)));
+    std::vector<Rec> h(64);
+    for (int i = 0; i < 64; ++i) h[i] = Rec{i, 100 + i};
+    CK(cudaMemcpy(a, h.data(), 64 * sizeof(Rec), cudaMemcpyHostToDevice));
+    tma_selftest<<<1, 64>>>(a, b, 64);
+    CK(cudaDeviceSynchronize());
+    std::vector<Rec> g(64);
+    CK(cudaMemcpy(g.data(), b, 64 * sizeof(Rec), cudaMemcpyDeviceToHost));
+    int ok = 1;
+    for (int i = 0; i < 64; ++i) ok &= g[i].key == i && g[i].val == 100 + i;
+    printf("tma self test: %s\n", ok ? "ok" : "WRONG DATA");
+  }
+  if (!is("p1") && !is("p2")) return 0;
 
   const long long n = 1ll << rows_log2;
   const unsigned long long n_keys = 1ull << keys_log2;
@@ -623,8 +674,26 @@ int main(int argc, char** argv) {
     k2<<<std::min(B, sms), NW * 32, sh2>>>(p2);
     ++runs;
   };
+  {
+    float t1only = time_ms([&] {
+      CK(cudaMemsetAsync(cursor, 0, B * sizeof(unsigned)));
+      k1<<<sms, P1_THREADS, sh1>>>(p1);
+    }, 5);
+    std::vector<unsigned> hc(B);
+    CK(cudaMemcpy(hc.data(), cursor, B * 4, cudaMemcpyDeviceToHost));
+    unsigned long long tot = 0;
+    unsigned mx = 0;
+    for (unsigned c : hc) {
+      tot += c;
+      mx = std::max(mx, c);
+    }
+    printf("pass 1 alone: %8.3f ms  %7.2f G rows/s; partitioned rows %llu of %lld, max region %u (cap %u)\n", t1only,
+           (double)n / (t1only * 1e-3) / 1e9, tot, n, mx, cap);
+  }
+  if (!strcmp(mode, "p1")) return 0;
   // cold run (every key is new), then timed warm runs
   float cold = time_ms(two_pass, 1);
+  printf("cold two-pass done: %.3f ms\n", cold);
   runs = 0;
   CK(cudaMemset(rows_a, 0, ids * 8));
   CK(cudaMemset(sum_a, 0, ids * 8));
