@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libarroyo_b200.so")
 SOURCES = ["abi.cu", "window_agg.cu", "shuffle.cu", "join.cu", "session.cu"]
-HEADERS = ["common.cuh", "dict.cuh", "scan.cuh", "planner.h", "arrow_io.h", "op.h", os.path.join("..", "..", "include", "arroyo_b200.h")]
+HEADERS = ["common.cuh", "dict.cuh", "bdict.cuh", "ingest_two_pass.cuh", "scan.cuh", "planner.h", "arrow_io.h", "op.h", os.path.join("..", "..", "include", "arroyo_b200.h")]
 
 
 def nvcc_path() -> str:
@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     ]
     if verbose:
         flags += ["-Xptxas", "-v"]
-    for knob in ("AB_INGEST_MIN_BLOCKS", "AB_INGEST_PREFETCH"):  # tuning knobs for experiments
+    for knob in ("AB_INGEST_MIN_BLOCKS", "AB_INGEST_PREFETCH", "AB_P1_THREADS"):  # tuning knobs for experiments
         if os.environ.get(knob):
             flags += [f"-D{knob}=" + os.environ[knob]]
     build_dir = os.path.join(HERE, "build")

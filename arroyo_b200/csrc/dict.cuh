@@ -11,9 +11,12 @@
 
 namespace ab {
 
+#ifndef AB_ID_CONSTANTS
+#define AB_ID_CONSTANTS
 constexpr uint32_t ID_UNSET = 0xFFFFFFFFu;
 constexpr uint32_t ID_OVERFLOW = 0xFFFFFFFEu;
 constexpr long long EMPTY_KEY = LLONG_MIN;
+#endif
 constexpr int MAX_PROBE = 4096;
 
 struct alignas(16) Slot {

@@ -28,7 +28,7 @@
 #include <memory>
 #include <set>
 
-#include "dict.cuh"
+#include "bdict.cuh"
 #include "op.h"
 #include "planner.h"
 
@@ -56,8 +56,9 @@ struct Counters {
   unsigned long long neg_ts;  // rows with _timestamp < 0 (pre-epoch): the reference panics on them
   unsigned long long max_q;  // newest on-time pane number (ts / slide) seen
   unsigned long long big_vals;  // rows deferred because a value exceeded the exact-AVG guard
-  unsigned int n_keys;
-  unsigned int pad;
+  unsigned int n_keys;     // keys in the dictionary (BDict::n_total)
+  unsigned int dict_full;  // rows deferred because their bucket was out of ids: the host grows the dictionary
+  unsigned long long part_overflow;  // two-pass ingest: rows that did not fit their partition region (skew)
 };
 
 struct Segment {
@@ -75,7 +76,7 @@ struct IngestParams {
   int n_segs;
   int keyed;
   long long n_tiles;
-  DictView dict;
+  BDict dict;
   FastDivU64 slide_div;
   long long slide;
   long long late_bin;
@@ -249,11 +250,11 @@ __device__ __noinline__ void slow_row(const IngestParams& p, long long key, long
   uint32_t id = 0;
   bool ok = ring_bin(p, slot) == (long long)(q * (uint64_t)p.slide);
   if (ok && p.keyed) {
-    ulonglong2 raw = {0, 0};
-    if (!dict_is_direct(p.dict, key))
-      raw = __ldcg(reinterpret_cast<const ulonglong2*>(p.dict.slots + dict_home((uint64_t)key, p.dict.cap)));
-    id = resolve_id(p.dict, key, raw.x, (uint32_t)raw.y);
+    const uint64_t h = mix64((uint64_t)key);
+    const ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(bd_home(p.dict, h)));
+    id = bd_resolve(p.dict, key, h, raw.x, (uint32_t)raw.y);
     ok = id < ID_OVERFLOW;
+    if (!ok) atomicAdd(&p.counters->dict_full, 1u);
   }
   const Vals v{v0, v1, v2, v3};
   if (ok && NV > 0 && p.guard_vals && big_value(p.guard_vals, v)) {
@@ -291,10 +292,10 @@ __device__ __forceinline__ void flush_counts(const IngestParams& p, PaneCache& p
 // accumulate into, or ID_OVERFLOW when the row was handled out of line (slow path / deferred).
 template <int NV, int SIG>
 __device__ __forceinline__ uint32_t hot_resolve(const IngestParams& p, const PaneCache& pc, uint64_t& maxq, bool keyed,
-                                                long long key, long long ts, uint64_t q, const Vals& v,
+                                                long long key, long long ts, uint64_t q, const Vals& v, uint64_t h,
                                                 unsigned long long k0, uint32_t id0) {
   uint32_t id = ID_OVERFLOW;
-  if (q == pc.q && pc.ptr != nullptr) id = keyed ? resolve_id(p.dict, key, k0, id0) : 0u;
+  if (q == pc.q && pc.ptr != nullptr) id = keyed ? bd_resolve(p.dict, key, h, k0, id0) : 0u;
   if (NV > 0 && p.guard_vals && big_value(p.guard_vals, v)) {
     // AVG is being derived from the exact integer sum: a value this large could overflow it.  Park the
     // row; the host promotes the operator to f64 AVG accumulators and re-ingests it.
@@ -450,8 +451,8 @@ __global__ void __launch_bounds__(THREADS, AB_INGEST_MIN_BLOCKS) ingest_kernel(c
 #pragma unroll
       for (int x = 0; x < (NV > 0 ? NV : 1); ++x) v[x] = nv[x];
       ulonglong2 raw = {0, 0};
-      if (valid && keyed && !dict_is_direct(p.dict, key))
-        raw = __ldcg(reinterpret_cast<const ulonglong2*>(p.dict.slots + dict_home((uint64_t)key, p.dict.cap)));
+      const uint64_t h = keyed ? mix64((uint64_t)key) : 0ull;
+      if (valid && keyed) raw = __ldcg(reinterpret_cast<const ulonglong2*>(bd_home(p.dict, h)));
 #if AB_INGEST_PREFETCH
       if (i + THREADS < cnt) {
         if (keyed) nkey = __ldcs(ldg_ptr(&sg->key) + base + i + THREADS);
@@ -481,7 +482,7 @@ __global__ void __launch_bounds__(THREADS, AB_INGEST_MIN_BLOCKS) ingest_kernel(c
       }
       const Vals pv = pack_vals<NV>(v);
       uint32_t id = ID_OVERFLOW;
-      if (live) id = hot_resolve<NV, SIG>(p, pc, maxq, keyed, key, ts, q, pv, raw.x, (uint32_t)raw.y);
+      if (live) id = hot_resolve<NV, SIG>(p, pc, maxq, keyed, key, ts, q, pv, h, raw.x, (uint32_t)raw.y);
       const bool fast = id < ID_OVERFLOW;
       if (fast) ++pc.cnt;
       if (p.combine) combine_accumulate<NV, SIG>(p, pc, fast, id, pv, lane);
@@ -521,6 +522,8 @@ __global__ void __launch_bounds__(THREADS, AB_INGEST_MIN_BLOCKS) ingest_kernel(c
   }
 }
 
+#include "ingest_two_pass.cuh"
+
 // Restore: merge a partial-state batch (AggregateExec(Partial) output written at a checkpoint,
 // sliding_aggregating_window.rs:725-733) into one pane block.
 struct PartialParams {
@@ -530,7 +533,7 @@ struct PartialParams {
   int keyed;
   int n_acc;
   int acc_kind[MAX_ACC];
-  DictView dict;
+  BDict dict;
   unsigned long long* pane;
   unsigned long long id_cap;
   Counters* counters;
@@ -542,7 +545,7 @@ __global__ void ingest_partial_kernel(const __grid_constant__ PartialParams p) {
   for (; i < p.n; i += stride) {
     uint32_t id = 0;
     if (p.keyed) {
-      id = dict_lookup_or_insert(p.dict, p.key[i]);
+      id = bd_lookup_or_insert(p.dict, p.key[i]);
       if (id >= ID_OVERFLOW) {
         atomicAdd(&p.counters->lost, 1ull);
         continue;
@@ -867,12 +870,23 @@ class WindowAggOp final : public OpBase {
   bool own_stream_ = false;
   int num_sms_ = 148;
 
-  // dictionary
+  // dictionary (bdict.cuh): n_buckets_ buckets of BD_KS slots; ids = BD_ID_BASE + bucket * BD_CAPB + index
   uint64_t id_cap_ = 0;
-  uint64_t dict_cap_ = 0;
-  DevBuf slots_, id_keys_, counters_, slot_rows_;
-  uint32_t n_keys_host_ = 1;
-  // direct-mapped key range (dict.cuh): decided once, from the first rows, before any id exists
+  uint64_t n_buckets_ = 1;
+  DevBuf slots_, bucket_nkeys_, id_keys_, counters_, slot_rows_;
+  uint32_t n_keys_host_ = 1;       // ids in use = the id range the element-wise kernels walk (all of it: bucket ranges)
+  uint32_t total_keys_host_ = 0;   // keys in the dictionary (statistics, growth policy)
+  uint32_t dict_full_seen_ = 0;
+  // two-pass ingest (ingest_two_pass.cuh)
+  DevBuf part_, part_cursor_;
+  uint32_t part_cap_ = 0;
+  bool two_pass_attr_set_ = false;
+  bool two_pass_enabled_ = true;
+  uint64_t part_overflow_seen_ = 0;
+  mutable int two_pass_pause_ = 0;  // launches left on the one-pass kernel after a skewed launch
+  bool two_pass_eligible(uint64_t rows) const;
+  void launch_two_pass(IngestParams& p, uint64_t rows, long long tiles_direct);
+  BDict dict_view() const;
   // asynchronous emission (begin_watermark / poll_watermark): windows are copied back on a second stream so the
   // device->host traffic overlaps the host->device traffic of the batches that follow
   cudaStream_t out_stream_ = nullptr;
@@ -888,10 +902,6 @@ class WindowAggOp final : public OpBase {
   std::vector<ArrowArray> open_release_;  // staged inputs whose copies have no release event yet
   std::vector<cudaEvent_t> ev_pool_;
   void seal_release();
-  bool direct_decided_ = false;
-  long long direct_base_ = 0;
-  uint32_t direct_n_ = 0;
-  void decide_direct(const std::vector<Segment>& segs);
 
   // ring
   uint32_t ring_ = 16;
@@ -964,7 +974,7 @@ class WindowAggOp final : public OpBase {
 
   // helpers
   void set_device() { AB_CUDA(cudaSetDevice(device_)); }
-  void alloc_dictionary(uint64_t id_cap);
+  void alloc_dictionary(uint64_t n_buckets);
   void preallocate();
   void grow_ids();
   void apply_l2_policy();
@@ -1113,15 +1123,17 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
   slot_rows_.alloc(MAX_RING * sizeof(unsigned long long));
   Counters init{};
   init.max_q = 0;
-  init.n_keys = 1;
+  init.n_keys = 0;
   AB_CUDA(cudaMemcpyAsync(counters_.p, &init, sizeof init, cudaMemcpyHostToDevice, stream_));
   last_counters_ = init;
 
-  // dense id space: the expected key count + 12.5 % head-room (grown by doubling when it runs out)
+  // one bucket per ~BD_MEAN expected keys (the bucket count doubles when a bucket runs out of ids)
   uint64_t want = c.expected_keys ? c.expected_keys : (1ull << 16);
-  uint64_t cap = ((want + want / 8 + 2 + 1023) / 1024) * 1024;
-  if (!keyed_) cap = 1024;
-  alloc_dictionary(cap);
+  alloc_dictionary(keyed_ ? bd_buckets_for(want) : 1);
+  {
+    const char* e = getenv("ARROYO_B200_NO_TWO_PASS");
+    two_pass_enabled_ = !(e && atoi(e) != 0) && !(c.flags & ARROYO_B200_FLAG_NO_TWO_PASS);
+  }
 
   h_pane_bins_.assign(MAX_RING, FREE_BIN);
   h_pane_ptrs_.assign(MAX_RING, nullptr);
@@ -1224,20 +1236,33 @@ WindowAggOp::~WindowAggOp() {
   if (own_stream_ && stream_) cudaStreamDestroy(stream_);
 }
 
-void WindowAggOp::alloc_dictionary(uint64_t id_cap) {
-  id_cap_ = id_cap;
+void WindowAggOp::alloc_dictionary(uint64_t n_buckets) {
+  n_buckets_ = n_buckets;
+  id_cap_ = bd_id_cap(n_buckets_);
+  AB_REQUIRE(id_cap_ < (1ull << 31), ARROYO_B200_RUNTIME, "key dictionary too large");
+  n_keys_host_ = (uint32_t)(BD_ID_BASE + n_buckets_ * BD_CAPB);
   id_keys_.alloc(id_cap_ * sizeof(long long));
   long long k0 = EMPTY_KEY;
   AB_CUDA(cudaMemcpyAsync(id_keys_.p, &k0, sizeof k0, cudaMemcpyHostToDevice, stream_));
+  bucket_nkeys_.alloc(n_buckets_ * sizeof(unsigned int));
+  AB_CUDA(cudaMemsetAsync(bucket_nkeys_.p, 0, n_buckets_ * sizeof(unsigned int), stream_));
   if (keyed_) {
-    dict_cap_ = dict_slots_for(id_cap_);
-    AB_REQUIRE(dict_cap_ <= (1ull << 31), ARROYO_B200_RUNTIME, "key dictionary too large");
-    slots_.alloc(dict_cap_ * sizeof(Slot));
-    dict_init_kernel<<<num_sms_ * 4, 256, 0, stream_>>>(slots_.as<Slot>(), dict_cap_);
+    slots_.alloc(n_buckets_ * BD_KS * sizeof(BSlot));
+    bd_init_kernel<<<num_sms_ * 4, 256, 0, stream_>>>(slots_.as<BSlot>(), n_buckets_ * BD_KS);
     AB_CUDA(cudaGetLastError());
     ++st_.kernel_launches;
     apply_l2_policy();
   }
+}
+
+BDict WindowAggOp::dict_view() const {
+  BDict d{};
+  d.slots = slots_.as<BSlot>();
+  d.nkeys = bucket_nkeys_.as<unsigned int>();
+  d.id_keys = id_keys_.as<long long>();
+  d.n_total = (unsigned int*)((char*)counters_.p + offsetof(Counters, n_keys));
+  d.n_buckets = (uint32_t)n_buckets_;
+  return d;
 }
 
 // ARROYO_B200_L2_PERSIST=1: ask L2 to keep the key dictionary resident (persisting access-policy window on the
@@ -1248,7 +1273,7 @@ void WindowAggOp::apply_l2_policy() {
   int max_persist = 0, max_window = 0;
   cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device_);
   cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device_);
-  size_t bytes = std::min<size_t>(dict_cap_ * sizeof(Slot), (size_t)std::max(max_window, 0));
+  size_t bytes = std::min<size_t>(n_buckets_ * BD_KS * sizeof(BSlot), (size_t)std::max(max_window, 0));
   if (bytes == 0 || max_persist <= 0) return;
   cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(bytes, (size_t)max_persist));
   cudaStreamAttrValue attr{};
@@ -1293,24 +1318,52 @@ void WindowAggOp::release_block(unsigned long long* blk) {
   free_panes_.emplace_back(blk, std::min<uint64_t>(id_cap_, (uint64_t)n_keys_host_ + 1));
 }
 
-// Doubles the dense id space: id_keys, every live pane block and the slot array are re-created.
+// new[a][map[i]] = old[a][i] for every old id that holds a key
+__global__ void permute_block_kernel(const unsigned long long* __restrict__ old_blk, unsigned long long* __restrict__ new_blk,
+                                     const uint32_t* __restrict__ map, uint32_t old_ids, uint64_t old_cap, uint64_t new_cap,
+                                     int n_acc) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (; i < old_ids; i += stride) {
+    const uint32_t m = map[i];
+    if (m == ID_UNSET || m >= ID_OVERFLOW) continue;
+    for (int a = 0; a < n_acc; ++a) new_blk[(uint64_t)a * new_cap + m] = old_blk[(uint64_t)a * old_cap + i];
+  }
+}
+
+// Doubles the bucket count: every key is re-inserted into the new dictionary (its id changes), and every live pane
+// block is permuted with the old -> new id map.
 void WindowAggOp::grow_ids() {
+  AB_REQUIRE(keyed_, ARROYO_B200_RUNTIME, "grow_ids on an unkeyed aggregate");
   const uint64_t old_cap = id_cap_;
-  const uint64_t new_cap = old_cap * 2;
-  const uint32_t n_valid = (uint32_t)std::min<uint64_t>(n_keys_host_, old_cap);
-  DevBuf new_keys(new_cap * sizeof(long long));
-  AB_CUDA(cudaMemcpyAsync(new_keys.p, id_keys_.p, (size_t)n_valid * sizeof(long long), cudaMemcpyDeviceToDevice, stream_));
-  // pane blocks
+  const uint32_t old_ids = n_keys_host_;
+  BDict old_d = dict_view();
+  DevBuf old_slots = std::move(slots_), old_nkeys = std::move(bucket_nkeys_), old_keys = std::move(id_keys_);
+  old_d.slots = old_slots.as<BSlot>();
+  old_d.nkeys = old_nkeys.as<unsigned int>();
+  old_d.id_keys = old_keys.as<long long>();
+  const unsigned int zero = 0;
+  AB_CUDA(cudaMemcpyAsync((char*)counters_.p + offsetof(Counters, n_keys), &zero, sizeof zero, cudaMemcpyHostToDevice, stream_));
+  alloc_dictionary(n_buckets_ * 2);
+  const uint64_t new_cap = id_cap_;
+  DevBuf map((size_t)old_cap * sizeof(uint32_t));
+  {
+    const int grid = (int)std::min<uint64_t>((old_ids + 255) / 256, (uint64_t)num_sms_ * 8);
+    bd_rehash_kernel<<<std::max(grid, 1), 256, 0, stream_>>>(old_d, dict_view(), old_ids, map.as<uint32_t>());
+    AB_CUDA(cudaGetLastError());
+    ++st_.kernel_launches;
+  }
   std::vector<DevBuf> new_storage;
-  id_cap_ = new_cap;
   auto migrate = [&](unsigned long long* old_blk) -> unsigned long long* {
     if (!old_blk) return nullptr;
     new_storage.emplace_back((size_t)n_acc_ * new_cap * sizeof(unsigned long long));
     auto* nb = new_storage.back().as<unsigned long long>();
     init_block(nb, new_cap);
-    for (int a = 0; a < n_acc_; ++a)
-      AB_CUDA(cudaMemcpyAsync(nb + (size_t)a * new_cap, old_blk + (size_t)a * old_cap,
-                              (size_t)n_valid * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream_));
+    const int grid = (int)std::min<uint64_t>((old_ids + 255) / 256, (uint64_t)num_sms_ * 8);
+    permute_block_kernel<<<std::max(grid, 1), 256, 0, stream_>>>(old_blk, nb, map.as<uint32_t>(), old_ids, old_cap, new_cap,
+                                                               n_acc_);
+    AB_CUDA(cudaGetLastError());
+    ++st_.kernel_launches;
     return nb;
   };
   for (auto& kv : panes_) {
@@ -1323,31 +1376,15 @@ void WindowAggOp::grow_ids() {
     kv.second.frozen = migrate(kv.second.frozen);
   }
   running_ = migrate(running_);
+  Counters c{};
+  AB_CUDA(cudaMemcpyAsync(&c, counters_.p, sizeof c, cudaMemcpyDeviceToHost, stream_));
   AB_CUDA(cudaStreamSynchronize(stream_));
+  total_keys_host_ = c.n_keys;
   free_panes_.clear();
   pane_storage_ = std::move(new_storage);
-  id_keys_ = std::move(new_keys);
+  out_sets_.clear();  // sized by id_cap_
+  part_cap_ = 0;      // the partition buffer is sized by the bucket count
   ring_dirty_ = true;
-  if (keyed_) {
-    dict_cap_ = dict_slots_for(new_cap);
-    AB_REQUIRE(dict_cap_ <= (1ull << 31), ARROYO_B200_RUNTIME, "key dictionary too large");
-    slots_.alloc(dict_cap_ * sizeof(Slot));
-    dict_init_kernel<<<num_sms_ * 4, 256, 0, stream_>>>(slots_.as<Slot>(), dict_cap_);
-    AB_CUDA(cudaGetLastError());
-    if (n_valid > 1) {
-      int blocks = (int)std::min<uint32_t>((n_valid + 255) / 256, (uint32_t)num_sms_ * 8);
-      dict_rebuild_kernel<<<blocks, 256, 0, stream_>>>(slots_.as<Slot>(), (uint32_t)dict_cap_,
-                                                       id_keys_.as<long long>(), n_valid, direct_n_ + 1);
-      AB_CUDA(cudaGetLastError());
-    }
-    st_.kernel_launches += 2;
-    apply_l2_policy();
-  }
-  // ids handed out beyond the old capacity were never usable: clamp the device counter
-  unsigned int nk = n_valid;
-  AB_CUDA(cudaMemcpyAsync((char*)counters_.p + offsetof(Counters, n_keys), &nk, sizeof nk, cudaMemcpyHostToDevice, stream_));
-  n_keys_host_ = n_valid;
-  AB_CUDA(cudaStreamSynchronize(stream_));
 }
 
 // fsum[id] = (double)(int64)sum[id]
@@ -1708,70 +1745,81 @@ void WindowAggOp::process_device_batch(uint32_t, uint32_t, const uint64_t* cols,
   }
 }
 
-// min / max of a key column (direct-range decision)
-__global__ void __launch_bounds__(256) key_minmax_kernel(const long long* __restrict__ key, long long n,
-                                                         long long* __restrict__ out /* [min, max] */) {
-  long long mn = LLONG_MAX, mx = LLONG_MIN;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long k = key[i];
-    mn = min(mn, k);
-    mx = max(mx, k);
+// The two-pass ingest handles the plans whose accumulators are {rows} or {rows, wrapping SUM(Int64) of one column}
+// over raw input rows (COUNT(*), SUM, AVG-from-exact-sum: the headline), when the launch is large enough to pay for
+// the per-bucket set-up and the dictionary fits the partition kernel's histograms.  Everything else -- and every row
+// the two passes hand back -- runs through the one-pass kernel.
+bool WindowAggOp::two_pass_eligible(uint64_t rows) const {
+  if (!two_pass_enabled_ || !keyed_ || rows_slot_ >= 0 || n_vals_ > 1 || n_acc_ > 2) return false;
+  if (n_acc_ == 2 && acc_kind_[1] != ACC_SUM_I64) return false;
+  if (n_buckets_ > (uint64_t)P1_NR) return false;
+  if (max_bin_seen_ == LLONG_MIN) return false;  // no pane known yet: the first launch finds out where the stream is
+  if (two_pass_pause_ > 0) {
+    --two_pass_pause_;
+    return false;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  }
-  if ((threadIdx.x & 31) == 0 && mn <= mx) {
-    atomicMin(out, mn);
-    atomicMax(out + 1, mx);
-  }
+  static const uint64_t min_rows = [] {
+    const char* e = getenv("ARROYO_B200_TWO_PASS_MIN_ROWS");
+    return e ? strtoull(e, nullptr, 10) : (1ull << 19);
+  }();
+  return rows >= min_rows || (cfg.flags & ARROYO_B200_FLAG_TWO_PASS_ALWAYS);
 }
 
-__global__ void fill_direct_keys_kernel(long long* __restrict__ id_keys, long long base, uint32_t n) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (; i < n; i += stride) id_keys[1 + i] = (long long)((unsigned long long)base + i);
-}
-
-// Dense integer keys (Nexmark's auction / bidder ids, most surrogate keys) need no hash table: if the keys
-// of the first rows span less than the id space that is already allocated, [min, min + span) is mapped
-// straight onto the ids [1, span].  Keys outside the range -- now or later -- go through the slot array as
-// before, so this only ever removes probes.  Decided once, before any id exists.
-void WindowAggOp::decide_direct(const std::vector<Segment>& segs) {
-  direct_decided_ = true;
-  if (!keyed_ || n_keys_host_ != 1 || !in_flight_.empty() || (cfg.flags & ARROYO_B200_FLAG_NO_DIRECT)) return;
-  const char* e = getenv("ARROYO_B200_NO_DIRECT");
-  if (e && atoi(e) != 0) return;
-  DevBuf mm(2 * sizeof(long long));
-  const long long init[2] = {LLONG_MAX, LLONG_MIN};
-  AB_CUDA(cudaMemcpyAsync(mm.p, init, sizeof init, cudaMemcpyHostToDevice, stream_));
-  const size_t step = std::max<size_t>(segs.size() / 32, 1);  // a sample of the launch is enough
-  for (size_t i = 0; i < segs.size(); i += step) {
-    if (segs[i].n <= 0) continue;
-    int grid = (int)std::min<long long>((segs[i].n + 255) / 256, (long long)num_sms_ * 4);
-    key_minmax_kernel<<<grid, 256, 0, stream_>>>(segs[i].key, segs[i].n, mm.as<long long>());
+void WindowAggOp::launch_two_pass(IngestParams& p, uint64_t rows, long long tiles) {
+  TwoPassParams tp{};
+  // fast panes: the newest pane seen and the next one (in-order streams write nothing else)
+  int nf = 0;
+  for (int k = 0; k < 3 && nf < TP_NP; ++k) {
+    const int64_t b = max_bin_seen_ + (int64_t)(k == 2 ? -1 : k) * slide_;
+    auto it = panes_.find(b);
+    if (b < late_bin_ || it == panes_.end() || it->second.slot < 0) continue;
+    tp.fast_q[nf] = (unsigned long long)b / (unsigned long long)slide_;
+    tp.fast_ptr[nf] = it->second.dev;
+    tp.fast_slot[nf] = (uint32_t)it->second.slot;
+    ++nf;
+  }
+  for (int f = nf; f < TP_NP; ++f) {
+    tp.fast_q[f] = ~0ull;
+    tp.fast_ptr[f] = nullptr;
+    tp.fast_slot[f] = 0;
+  }
+  const uint32_t n_regions = (uint32_t)(TP_NP * n_buckets_);
+  // a region holds a bucket's share of one pane's rows: mean rows / buckets, plus slack for the spread
+  const uint64_t mean = (uint64_t)chunk_rows_ / n_buckets_ + 1;
+  const uint32_t cap = (uint32_t)std::min<uint64_t>(((mean + mean / 4 + 2048 + 63) / 64) * 64, 1u << 30);
+  if (part_cap_ != cap || !part_.p) {
+    AB_CUDA(cudaStreamSynchronize(stream_));
+    part_.alloc((size_t)n_regions * cap * sizeof(Rec));
+    part_cursor_.alloc((size_t)n_regions * sizeof(unsigned int));
+    part_cap_ = cap;
+  }
+  tp.part = part_.as<Rec>();
+  tp.cursor = part_cursor_.as<unsigned int>();
+  tp.cap = cap;
+  // blocks per region in pass 2: enough blocks to fill the GPU when there are few buckets
+  const uint32_t want_blocks = (uint32_t)num_sms_ * 2;
+  tp.slices = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((want_blocks + n_buckets_ - 1) / n_buckets_,
+                                                                 std::max<uint64_t>(1, rows / n_buckets_ / 4096)));
+  if (!two_pass_attr_set_) {
+    AB_CUDA(cudaFuncSetAttribute(part_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P1_SMEM));
+    AB_CUDA(cudaFuncSetAttribute(part_kernel<1, sig_of(ACC_SUM_I64)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P1_SMEM));
+    AB_CUDA(cudaFuncSetAttribute(agg_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2_SMEM));
+    AB_CUDA(cudaFuncSetAttribute(agg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2_SMEM));
+    two_pass_attr_set_ = true;
+  }
+  AB_CUDA(cudaMemsetAsync(part_cursor_.p, 0, (size_t)n_regions * sizeof(unsigned int), stream_));
+  const int grid1 = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)num_sms_ * P1_BLOCKS_PER_SM));
+  const int grid2 = (int)std::max<uint32_t>(1, std::min<uint32_t>(n_regions * tp.slices, (uint32_t)num_sms_ * P2_BLOCKS_PER_SM));
+  if (n_vals_ == 0) {
+    part_kernel<0, 0><<<grid1, P1_THREADS, P1_SMEM, stream_>>>(p, tp);
     AB_CUDA(cudaGetLastError());
-    ++st_.kernel_launches;
+    agg_kernel<0><<<grid2, P2_NW * 32, P2_SMEM, stream_>>>(p, tp);
+  } else {
+    part_kernel<1, sig_of(ACC_SUM_I64)><<<grid1, P1_THREADS, P1_SMEM, stream_>>>(p, tp);
+    AB_CUDA(cudaGetLastError());
+    agg_kernel<1><<<grid2, P2_NW * 32, P2_SMEM, stream_>>>(p, tp);
   }
-  long long h[2];
-  AB_CUDA(cudaMemcpyAsync(h, mm.p, sizeof h, cudaMemcpyDeviceToHost, stream_));
-  AB_CUDA(cudaStreamSynchronize(stream_));
-  if (h[0] > h[1]) return;
-  const unsigned long long span = (unsigned long long)h[1] - (unsigned long long)h[0] + 1ull;  // 0 = the whole i64 range
-  const uint64_t room = id_cap_ - id_cap_ / 16 - 1;  // leave ids for keys outside the range
-  if (span == 0 || span > room) return;
-  const uint64_t dn = std::min<uint64_t>((span + 1023) / 1024 * 1024, room);
-  direct_base_ = h[0];
-  direct_n_ = (uint32_t)dn;
-  int grid = (int)std::min<uint64_t>((dn + 255) / 256, (uint64_t)num_sms_ * 8);
-  fill_direct_keys_kernel<<<grid, 256, 0, stream_>>>(id_keys_.as<long long>(), direct_base_, direct_n_);
-  AB_CUDA(cudaGetLastError());
-  ++st_.kernel_launches;
-  const unsigned int nk = direct_n_ + 1;
-  AB_CUDA(cudaMemcpyAsync((char*)counters_.p + offsetof(Counters, n_keys), &nk, sizeof nk, cudaMemcpyHostToDevice, stream_));
-  AB_CUDA(cudaStreamSynchronize(stream_));
-  n_keys_host_ = nk;
+  ++st_.kernel_launches;  // (the second kernel is counted by the caller)
 }
 
 void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk) {
@@ -1783,7 +1831,6 @@ void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk
     while (!in_flight_.empty()) absorb(in_flight_.front());
     drain_deferred();
   }
-  if (!direct_decided_) decide_direct(segs_in);
   const int li = next_launch_;
   next_launch_ = (next_launch_ + 1) % NLAUNCH;
   LaunchRec& L = launches_[li];
@@ -1813,13 +1860,7 @@ void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk
   p.n_segs = (int)segs_in.size();
   p.keyed = keyed_ ? 1 : 0;
   p.n_tiles = tiles;
-  p.dict.slots = slots_.as<Slot>();
-  p.dict.id_keys = id_keys_.as<long long>();
-  p.dict.n_keys = (unsigned int*)((char*)counters_.p + offsetof(Counters, n_keys));
-  p.dict.cap = keyed_ ? (uint32_t)dict_cap_ : 1;
-  p.dict.id_cap = (uint32_t)std::min<uint64_t>(id_cap_, 0xFFFFFFF0ull);
-  p.dict.dbase = direct_base_;
-  p.dict.dn = direct_n_;
+  p.dict = dict_view();
   p.slide_div = FastDivU64::make((uint64_t)slide_);
   p.slide = slide_;
   p.late_bin = late_bin_;
@@ -1852,6 +1893,18 @@ void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk
   int grid = (int)std::min<long long>(tiles, (long long)num_sms_ * 8);
   if (grid < 1) grid = 1;
   if (profile_) AB_CUDA(cudaEventRecord(L.t0, stream_));
+  const bool two_pass = two_pass_eligible(rows);
+  if (two_pass) {
+    // tiles of the partition kernel are larger: the segment table is re-cut for them
+    long long t2 = 0;
+    for (size_t i = 0; i < segs_in.size(); ++i) {
+      hs[i].tile_start = t2;
+      t2 += (hs[i].n + P1_TILE - 1) / P1_TILE;
+    }
+    AB_CUDA(cudaMemcpyAsync(d_segs_[li].p, hs, segs_in.size() * sizeof(Segment), cudaMemcpyHostToDevice, stream_));
+    p.n_tiles = t2;
+    launch_two_pass(p, rows, t2);
+  }
   // straight-line specialisations for the common accumulator signatures, generic otherwise
   int sig = GENERIC_SIG;
   if (n_vals_ <= 1 && n_acc_ <= 4) {
@@ -1860,7 +1913,9 @@ void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk
     sig = sig_of(k[0], k[1], k[2]);
   }
 #define AB_LAUNCH(NV, SIG) ingest_kernel<NV, SIG><<<grid, THREADS, 0, stream_>>>(p)
-  if (n_vals_ == 0) AB_LAUNCH(0, 0);
+  if (two_pass) {
+    // launched above
+  } else if (n_vals_ == 0) AB_LAUNCH(0, 0);
   else if (n_vals_ == 1 && sig == sig_of(ACC_SUM_I64)) AB_LAUNCH(1, sig_of(ACC_SUM_I64));
   else if (n_vals_ == 1 && sig == sig_of(ACC_SUM_F64)) AB_LAUNCH(1, sig_of(ACC_SUM_F64));
   else if (n_vals_ == 1 && sig == sig_of(ACC_SUM_I64, ACC_SUM_F64)) AB_LAUNCH(1, sig_of(ACC_SUM_I64, ACC_SUM_F64));
@@ -1935,7 +1990,13 @@ void WindowAggOp::absorb(int li) {
   const Counters& c = *L.h_counters;
   last_counters_ = c;
   have_counters_ = true;
-  n_keys_host_ = (uint32_t)std::min<uint64_t>(c.n_keys, id_cap_);
+  total_keys_host_ = c.n_keys;
+  if (c.part_overflow != part_overflow_seen_) {
+    // a launch whose rows pile up in a few buckets (a hot key) is the one-pass kernel's case: its warp-combine turns
+    // the hot key's rows into one update per warp.  Skewed streams stay skewed: the two-pass path is retried later.
+    if (c.part_overflow - part_overflow_seen_ > L.rows / 64) two_pass_pause_ = 64;
+    part_overflow_seen_ = c.part_overflow;
+  }
   if (c.max_q) max_bin_seen_ = std::max<int64_t>(max_bin_seen_, (int64_t)(c.max_q * (uint64_t)slide_));
   for (uint32_t s = 0; s < ring_; ++s) {
     if (L.h_slot_rows[s]) {
@@ -1996,12 +2057,13 @@ void WindowAggOp::drain_deferred() {
     }
     for (int64_t b : bins) ensure_pane(b);
     if (last_counters_.big_vals && avg_exact_) promote_avg();
-    // dictionary pressure: grow when half full (keeps probes short) or when ids ran out
-    while (keyed_ && ((uint64_t)last_counters_.n_keys - direct_n_ + n / 2 >= id_cap_ / 2 + id_cap_ / 4 ||
-                      (uint64_t)last_counters_.n_keys + n / 2 >= id_cap_)) {
-      n_keys_host_ = (uint32_t)std::min<uint64_t>(last_counters_.n_keys, id_cap_);
+    // dictionary pressure: a bucket ran out of ids (its rows were deferred), or the mean bucket fill is past the
+    // point where that becomes likely: double the bucket count
+    if (keyed_ && (last_counters_.dict_full != dict_full_seen_ ||
+                   (uint64_t)last_counters_.n_keys > n_buckets_ * (uint64_t)(BD_MEAN + BD_MEAN / 8))) {
+      dict_full_seen_ = last_counters_.dict_full;
       grow_ids();
-      last_counters_.n_keys = n_keys_host_;
+      last_counters_.n_keys = total_keys_host_;
     }
     // re-ingest from the filled set while new deferrals go to the other set
     const int full = defer_cur_;
@@ -2606,18 +2668,12 @@ void WindowAggOp::on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, i
       AB_CUDA(cudaStreamSynchronize(stream_));
       pp.state[0] = keep.back().as<unsigned long long>();
     }
-    direct_decided_ = true;  // ids are being handed out by the restore: too late to reserve a direct range
-    while (keyed_ && (uint64_t)n_keys_host_ + (uint64_t)rows >= id_cap_ / 2) {
+    // room for every key of the batch at the target bucket fill (most of them are usually known already)
+    while (keyed_ && (uint64_t)total_keys_host_ + (uint64_t)rows > n_buckets_ * (uint64_t)BD_MEAN) {
       AB_CUDA(cudaStreamSynchronize(stream_));
       grow_ids();
     }
-    pp.dict.slots = slots_.as<Slot>();
-    pp.dict.id_keys = id_keys_.as<long long>();
-    pp.dict.n_keys = (unsigned int*)((char*)counters_.p + offsetof(Counters, n_keys));
-    pp.dict.cap = keyed_ ? (uint32_t)dict_cap_ : 1;
-    pp.dict.id_cap = (uint32_t)id_cap_;
-    pp.dict.dbase = direct_base_;
-    pp.dict.dn = direct_n_;
+    pp.dict = dict_view();
     pp.pane = panes_.at(bin).frozen;
     pp.id_cap = id_cap_;
     pp.counters = counters_.as<Counters>();
@@ -2629,7 +2685,7 @@ void WindowAggOp::on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, i
     AB_CUDA(cudaMemcpyAsync(&c, counters_.p, sizeof c, cudaMemcpyDeviceToHost, stream_));
     AB_CUDA(cudaStreamSynchronize(stream_));
     AB_REQUIRE(c.lost == 0, ARROYO_B200_RUNTIME, "dictionary overflow during restore");
-    n_keys_host_ = (uint32_t)std::min<uint64_t>(c.n_keys, id_cap_);
+    total_keys_host_ = c.n_keys;
     last_counters_ = c;
     max_bin_seen_ = std::max<int64_t>(max_bin_seen_, bin);
     if (state[bi].release) state[bi].release(&state[bi]);
@@ -2639,7 +2695,7 @@ void WindowAggOp::on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, i
 }
 
 void WindowAggOp::stats(ArroyoB200Stats* out) {
-  st_.n_keys = keyed_ ? (n_keys_host_ > 0 ? n_keys_host_ - 1 : 0) : 0;
+  st_.n_keys = keyed_ ? total_keys_host_ : 0;
   st_.rows_late = last_counters_.late_rows;
   *out = st_;
 }

@@ -16,7 +16,9 @@ TUMBLING_AGGREGATE, SLIDING_AGGREGATE, SESSION_AGGREGATE, INSTANT_JOIN = 1, 2, 3
 AGG_COUNT_STAR, AGG_SUM_I64, AGG_AVG_I64, AGG_MIN_I64, AGG_MAX_I64 = 1, 2, 3, 4, 5
 JOIN_INNER, JOIN_LEFT, JOIN_RIGHT, JOIN_FULL = 0, 1, 2, 3
 FLAG_PROFILE, FLAG_REMERGE_ONLY, FLAG_COMBINE, FLAG_AVG_F64, FLAG_NO_COMBINE, FLAG_ZERO_COPY = 1, 2, 4, 8, 16, 32
-FLAG_NO_DIRECT = 64
+FLAG_NO_DIRECT = 64  # accepted and ignored since round 2
+FLAG_NO_TWO_PASS = 128
+FLAG_TWO_PASS_ALWAYS = 256
 NO_WATERMARK = -(1 << 63)
 INT64_MIN = -(1 << 63)
 INT64_MAX = (1 << 63) - 1

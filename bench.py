@@ -70,7 +70,9 @@ def parse():
     ap.add_argument("--skip-pageable", action="store_true", help="e2e: skip the extra pass over pageable host buffers")
     ap.add_argument("--sync-emit", action="store_true",
                     help="e2e: blocking arroyo_b200_op_handle_watermark instead of the begin / poll pair")
-    ap.add_argument("--no-direct", action="store_true", help="measurement knob: hash dense keys as well")
+    ap.add_argument("--no-direct", action="store_true", help="accepted and ignored (every key is hashed since round 2)")
+    ap.add_argument("--one-pass", action="store_true",
+                    help="measurement knob: the one-pass ingest kernel (probe + REDs per row) instead of the two-pass ingest")
     ap.add_argument("--local-chunk-log2", type=int, default=23,
                     help="N>1, partials: rows per ingest launch of the local stage = 2^n; short launches let the owner "
                          "stage's kernels in between")
@@ -233,7 +235,7 @@ def ncu_traffic():
 def op_flags(args):
     from arroyo_b200 import ffi
     return ((ffi.FLAG_REMERGE_ONLY if args.remerge else 0) | (ffi.FLAG_NO_COMBINE if args.no_combine else 0) |
-            (ffi.FLAG_AVG_F64 if args.avg_f64 else 0) | (ffi.FLAG_NO_DIRECT if args.no_direct else 0))
+            (ffi.FLAG_AVG_F64 if args.avg_f64 else 0) | (ffi.FLAG_NO_TWO_PASS if args.one_pass else 0))
 
 
 def steady_warmup(requested, extra=0):
@@ -563,22 +565,11 @@ def run_ours(args):
            "impl": {"emission": "remerge" if args.remerge else "running add/evict",
                     "avg": "f64 accumulator" if args.avg_f64 else "exact integer sum (guarded)",
                     "combine": not args.no_combine, "numa": args.numa,
+                    "ingest": ("one pass: probe + one RED per accumulator per row" if args.one_pass else
+                               "two passes: radix partition by dictionary bucket, per-bucket aggregation in shared memory"),
                     "warmup_note": "warm-up = max(--warmup, width/slide + 3) panes: the timed steps see the steady state"},
            "rows_out_per_step": rows_out / max(K, 1), "gpu_launches": int(d["kernel_launches"]),
            "roofline": roof, "clocks": clocks}
-
-    if args.keyspace == "scattered" and not args.no_direct and not args.skip_e2e:
-        # same workload with Nexmark-shaped surrogate ids (1000 + n): the operator maps the dense range straight
-        # onto its ids and skips the dictionary probe.  Reported beside the headline, not instead of it.
-        K2 = min(K, 30)
-        gen2 = make_generator(torch, device, rows, args.keys, args.dist, 42 + rank, "dense")
-        panes2 = [gen2(p) for p in range(W + K2)]
-        ms2, d2, _, _, _ = device_resident(args, torch, native, ffi, local, panes2, W, K2, rows)
-        g2 = 24.0 * d2["ingest_rows_timed"] / (d2["ingest_ms"] * 1e-3) / 1e9 if d2["ingest_ms"] else None
-        out["dense_keys"] = {"value": K2 * rows / (ms2 * 1e-3), "unit": "rows/s", "steps": K2, "ms_per_step": ms2 / K2,
-                             "ingest_ms_per_step": d2["ingest_ms"] / K2, "roofline_frac": round(g2 / peak, 4) if g2 else None,
-                             "keys": "1000 + n, n < 2^20 (direct-mapped ids, no dictionary probe)"}
-        del gen2, panes2
 
     # ---- e2e: host Arrow batches in, host Arrow batches out, through the reference-facing call ----
     if not args.skip_e2e:

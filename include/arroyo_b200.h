@@ -181,8 +181,14 @@ typedef struct ArroyoB200OpConfig {
                                           /* instead of staging them with the copy engine */
 #define ARROYO_B200_FLAG_NO_COMBINE 16u   /* do not warp-combine equal keys before the     */
                                           /* atomics (measurement knob)                    */
-#define ARROYO_B200_FLAG_NO_DIRECT 64u    /* never map a dense key range straight onto ids */
-                                          /* (every key goes through the hash dictionary)  */
+#define ARROYO_B200_FLAG_NO_DIRECT 64u    /* accepted and ignored (round 1 mapped dense key ranges    */
+                                          /* straight onto ids; every key is hashed now)              */
+#define ARROYO_B200_FLAG_NO_TWO_PASS 128u /* always use the one-pass ingest kernel (probe + REDs per  */
+                                          /* row) instead of partition + shared-memory aggregation     */
+                                          /* (measurement knob; results are identical)                */
+#define ARROYO_B200_FLAG_TWO_PASS_ALWAYS 256u /* two-pass ingest for every eligible launch, however small  */
+                                          /* (by default launches under 2^19 rows use the one-pass kernel: */
+                                          /* the per-bucket set-up does not pay for them; test knob)       */
 
 typedef struct ArroyoB200Op ArroyoB200Op;
 

@@ -207,9 +207,9 @@ def test_dictionary_growth_and_far_future_rows(G):
 
 @pytest.mark.parametrize("direct", [True, False])
 def test_dense_key_range_is_direct_mapped_and_outsiders_still_hash(G, direct):
-    """Nexmark-shaped dense ids (1000 + n): the first rows' key range is mapped straight onto dense ids; keys
-    that show up later outside that range -- just below, just above, far away, the dictionary's empty
-    sentinel -- go through the hash dictionary.  Same results either way, and with the feature disabled."""
+    """Nexmark-shaped dense ids (1000 + n) next to keys far outside that range -- just below, just above, far away,
+    the dictionary's empty sentinel.  (Round 1 mapped the dense range straight onto ids; since the bucketed
+    dictionary every key is hashed, and FLAG_NO_DIRECT is accepted and ignored.)"""
     from arroyo_b200 import ffi
     rng = np.random.default_rng(77)
     batches = gen_stream(rng, 120_000, 10, rate_per_s=20_000, batch=4096)
@@ -233,8 +233,8 @@ def test_dense_key_range_is_direct_mapped_and_outsiders_still_hash(G, direct):
         want, got, gop = run_both(G, lambda: mk_o(cfg), lambda: mk_g(cfg, flags=flags), out)
         assert_same(want, got, float_cols=fc)
         n_ids = gop.stats()["n_keys"]
-        # 1000 dense keys + 7 outsiders; the direct range reserves ids for [1000, 1000 + 1024)
-        assert n_ids == (1024 + 6 if direct else 1007), n_ids
+        # 1000 dense keys + 2023 + 7 outsiders, one of which is the empty sentinel (it owns id 0, outside the dictionary)
+        assert n_ids == 1007, n_ids
 
 
 def test_unsupported_inputs_fail_loudly(G):

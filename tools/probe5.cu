@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(NW * 32, 1) agg2_kernel(const __grid_constant_
         uint32_t cv = 1;
         if (__any_sync(0xffffffffu, peers & (peers - 1))) {
           unsigned long long acc = 0;
-          for (unsigned m = peers; m; m &= m - 1) acc += __shfl_sync(0xffffffffu, sv, __ffs(m) - 1);
+          for (unsigned m = peers; m; m &= m - 1) acc += __shfl_sync(peers, sv, __ffs(m) - 1);  // mask = the group: trip counts differ between groups
           sv = acc;
           cv = __popc(peers);
         }
