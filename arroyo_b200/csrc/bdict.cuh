@@ -1,7 +1,7 @@
 // The window aggregate's key dictionary: a *bucketed* open-addressing table.
 //
 //   bucket(key) = mulhi32(hash >> 32, n_buckets)           BD_KS 16-byte slots {key, idx} per bucket,
-//   slot0(key)  = hash & (BD_KS - 1)                       linear probing that wraps inside the bucket
+//   slot0(key)  = (key * odd constant) >> 53                linear probing that wraps inside the bucket
 //   id(key)     = BD_ID_BASE + bucket * BD_CAPB + idx       idx = arrival order inside the bucket
 //
 // Why buckets: the two-pass ingest (ingest_two_pass.cuh) radix-partitions a launch's rows by bucket and aggregates
@@ -51,7 +51,13 @@ struct BDict {
 __host__ __device__ __forceinline__ uint32_t bd_bucket(uint64_t h, uint32_t n_buckets) {
   return (uint32_t)(((h >> 32) * (uint64_t)n_buckets) >> 32);
 }
-__host__ __device__ __forceinline__ uint32_t bd_slot0(uint64_t h) { return (uint32_t)h & (BD_KS - 1); }
+// slot inside the bucket: a second, cheap hash of the key itself (one multiply), independent of the bits that chose
+// the bucket -- the aggregation kernel computes only this one per row (its rows already sit in their bucket)
+constexpr int BD_KS_LOG2 = 11;
+static_assert((1 << BD_KS_LOG2) == BD_KS, "BD_KS_LOG2");
+__host__ __device__ __forceinline__ uint32_t bd_slot0(long long key) {
+  return (uint32_t)(((uint64_t)key * 0xD6E8FEB86659FD93ull) >> (64 - BD_KS_LOG2));
+}
 __host__ __device__ __forceinline__ uint32_t bd_id(uint32_t bucket, uint32_t idx) { return BD_ID_BASE + bucket * BD_CAPB + idx; }
 inline uint64_t bd_id_cap(uint64_t n_buckets) { return ((BD_ID_BASE + n_buckets * BD_CAPB + 1023) / 1024) * 1024; }
 inline uint64_t bd_buckets_for(uint64_t keys) {
@@ -116,24 +122,36 @@ static __device__ __noinline__ uint32_t bd_insert(const BDict& d, uint32_t b, lo
   return ID_OVERFLOW;
 }
 
-// Id of `key` given the contents of its home slot (already loaded: the hot path issues that load early).
+// Id of `key` given the contents of its home slot (already loaded: the hot path issues that load early).  Known keys
+// resolve with read-only probes inline; first sightings go out of line.
 __device__ __forceinline__ uint32_t bd_resolve(const BDict& d, long long key, uint64_t h, unsigned long long k0,
                                                uint32_t idx0) {
   if (key == EMPTY_KEY) return 0;  // id 0 is reserved for the one key that equals the empty sentinel
   const uint32_t b = bd_bucket(h, d.n_buckets);
   if ((long long)k0 == key && idx0 < ID_OVERFLOW) return bd_id(b, idx0);
-  return bd_insert(d, b, key, bd_slot0(h));
+  uint32_t s = bd_slot0(key);
+  if ((long long)k0 != EMPTY_KEY && (long long)k0 != key) {
+    const BSlot* tab = d.slots + (size_t)b * BD_KS;
+#pragma unroll 1
+    for (int probe = 1; probe < BD_KS; ++probe) {
+      s = (s + 1) & (BD_KS - 1);
+      const ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(tab + s));
+      if ((long long)raw.x == key && (uint32_t)raw.y < ID_OVERFLOW) return bd_id(b, (uint32_t)raw.y);
+      if ((long long)raw.x == EMPTY_KEY || (long long)raw.x == key) break;
+    }
+  }
+  return bd_insert(d, b, key, s);
 }
 
-__device__ __forceinline__ const BSlot* bd_home(const BDict& d, uint64_t h) {
-  return d.slots + (size_t)bd_bucket(h, d.n_buckets) * BD_KS + bd_slot0(h);
+__device__ __forceinline__ const BSlot* bd_home(const BDict& d, long long key, uint64_t h) {
+  return d.slots + (size_t)bd_bucket(h, d.n_buckets) * BD_KS + bd_slot0(key);
 }
 
 // Id of `key`, inserting it on first sight (cold paths: restore, partial-state merge).
 static __device__ __forceinline__ uint32_t bd_lookup_or_insert(const BDict& d, long long key) {
   if (key == EMPTY_KEY) return 0u;
   const uint64_t h = mix64((uint64_t)key);
-  return bd_insert(d, bd_bucket(h, d.n_buckets), key, bd_slot0(h));
+  return bd_insert(d, bd_bucket(h, d.n_buckets), key, bd_slot0(key));
 }
 
 // Rebuild after growth: every key of the old dictionary gets an id in the new one; map[old id] = new id

@@ -43,8 +43,8 @@ constexpr int P1_TILE = P1_THREADS * P1_RPT;  // rows per tile
 constexpr int P1_NWARP = P1_THREADS / 32;
 constexpr int P1_NR = 1024;              // buckets a tile can be ranked over (shared-memory histogram)
 constexpr int P1_BLOCKS_PER_SM = P1_THREADS <= 256 ? 2 : 1;
-constexpr int P2_NW = 8;                 // warps per aggregation block
-constexpr int P2_NST = 4;                // TMA ring stages per warp
+constexpr int P2_NW = 16;                // warps per aggregation block
+constexpr int P2_NST = 3;                // TMA ring stages per warp
 constexpr int P2_CH = 64;                // records per stage (1 KB)
 constexpr int P2_BLOCKS_PER_SM = 2;
 constexpr uint32_t NO_REGION = 0xFFFFu;
@@ -61,7 +61,7 @@ struct TwoPassParams {
 
 constexpr size_t P1_SMEM = (size_t)P1_TILE * 16 + (size_t)P1_TILE * 2 + (size_t)P1_NR * 12;
 constexpr size_t P2_SMEM = (size_t)BD_KS * 16 + (size_t)BD_CAPB * 12 + (size_t)P2_NW * P2_NST * P2_CH * 16 +
-                           (size_t)P2_NW * P2_NST * 8;
+                           (size_t)(P2_NW * P2_NST + 1) * 8;
 
 // A row that left the fast path after window assignment: accumulate it directly (global lookup + REDs).  `q` is its
 // pane number; the pane block is `pane`, its ring slot `slot`.  Rows that cannot get an id are deferred with the pane's
@@ -69,6 +69,11 @@ constexpr size_t P2_SMEM = (size_t)BD_KS * 16 + (size_t)BD_CAPB * 12 + (size_t)P
 template <int NV>
 __device__ __noinline__ void direct_rec(const IngestParams& p, unsigned long long* pane, uint32_t slot, uint64_t q,
                                         long long key, long long val) {
+  if (NV > 0 && p.guard_vals && big_one(val)) {  // exact-AVG guard: the host promotes the operator and re-ingests the row
+    atomicAdd(&p.counters->big_vals, 1ull);
+    defer_row(p, key, (long long)(q * (uint64_t)p.slide), val, 0, 0, 0);
+    return;
+  }
   const uint32_t id = bd_lookup_or_insert(p.dict, key);
   if (id >= ID_OVERFLOW) {
     atomicAdd(&p.counters->dict_full, 1u);
@@ -144,46 +149,58 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
     unsigned long long* fpane = psel >= 0 ? tp.fast_ptr[psel] : nullptr;
     const uint32_t fslot = psel >= 0 ? tp.fast_slot[psel] : 0u;
 
-    // ---- load, window-assign (K1), late filter (K7), guard; bucket + rank on the fast path, or handled here ----
+    // ---- load phase: every key and timestamp of the thread's 16 rows is requested before anything depends on one
+    // (the kernel is bound by the latency of these loads: 32 independent 8-byte loads per thread in flight) ----
     long long k[P1_RPT], v[P1_RPT];
     uint32_t rr[P1_RPT];  // bucket | rank inside the tile's bucket << 16
+    {
+      long long t[P1_RPT];
 #pragma unroll
-    for (int j = 0; j < P1_RPT; ++j) {
-      const int i = j * P1_THREADS + tid;
-      k[j] = 0;
-      v[j] = 0;
-      long long t = -1;
-      if (i < cnt) {
-        k[j] = __ldcs(kcol + i);
-        t = __ldcs(tcol + i);
-        if (NV > 0) v[j] = __ldcs(vcol + i);
+      for (int j = 0; j < P1_RPT; ++j) {
+        const int i = j * P1_THREADS + tid;
+        k[j] = 0;
+        t[j] = -1;
+        if (i < cnt) {
+          k[j] = __ldcs(kcol + i);
+          t[j] = __ldcs(tcol + i);
+        }
       }
-      uint32_t r = NO_REGION;
-      if (i < cnt) {
-        if (t < 0) {
-          atomicAdd(&p.counters->neg_ts, 1ull);  // pre-epoch: reported, never aggregated
-        } else {
-          const uint64_t q = sd.div((uint64_t)t);
-          if (q < p.late_q) {
-            ++late;
+      // ---- window-assign (K1), late filter (K7); bucket + rank on the fast path, or the direct path right here ----
+#pragma unroll
+      for (int j = 0; j < P1_RPT; ++j) {
+        const int i = j * P1_THREADS + tid;
+        uint32_t r = NO_REGION;
+        if (i < cnt) {
+          if (t[j] < 0) {
+            atomicAdd(&p.counters->neg_ts, 1ull);  // pre-epoch: reported, never aggregated
           } else {
-            maxq = max(maxq, q);
-            if (q != tq || psel < 0) {
-              // another pane than the tile's (pane boundary, disorder) or no fast pane: the direct path does everything
-              slow_row<NV, SIG>(p, k[j], t, q, v[j], 0, 0, 0);
-            } else if (NV > 0 && p.guard_vals && big_one(v[j])) {
-              atomicAdd(&p.counters->big_vals, 1ull);
-              defer_row(p, k[j], t, v[j], 0, 0, 0);
-            } else if (k[j] == EMPTY_KEY) {
-              direct_rec<NV>(p, fpane, fslot, q, k[j], v[j]);  // the sentinel key owns id 0, outside every bucket
+            const uint64_t q = sd.div((uint64_t)t[j]);
+            if (q < p.late_q) {
+              ++late;
             } else {
-              r = bd_bucket(mix64((uint64_t)k[j]), NB);
-              r |= atomicAdd(&hist[r], 1u) << 16;
+              maxq = max(maxq, q);
+              if (q != tq || psel < 0) {
+                // another pane than the tile's (pane boundary, disorder) or no fast pane: the direct path does everything
+                slow_row<NV, SIG>(p, k[j], t[j], q, NV > 0 ? __ldcs(vcol + i) : 0ll, 0, 0, 0);
+              } else if (k[j] == EMPTY_KEY) {
+                // the sentinel key owns id 0, outside every bucket
+                direct_rec<NV>(p, fpane, fslot, q, k[j], NV > 0 ? __ldcs(vcol + i) : 0ll);
+              } else {
+                r = bd_bucket(mix64((uint64_t)k[j]), NB);
+                r |= atomicAdd(&hist[r], 1u) << 16;
+              }
             }
           }
         }
+        rr[j] = r;
       }
-      rr[j] = r;
+    }
+    // the values: requested now, consumed after the scan (in flight across the barrier)
+#pragma unroll
+    for (int j = 0; j < P1_RPT; ++j) {
+      const int i = j * P1_THREADS + tid;
+      v[j] = 0;
+      if (NV > 0 && (rr[j] & 0xFFFFu) != NO_REGION) v[j] = __ldcs(vcol + i);
     }
     __syncthreads();
 
@@ -316,6 +333,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // included.  The 64-bit wrapping SUM is kept as two 32-bit words: the low word takes every row's low half (the
 // returned old value tells whether it wrapped), the high word takes the high half plus that carry -- for the small
 // positive values of a bid stream a second atomic is rare.  (A 64-bit shared atomicAdd is a CAS loop: 19-30 cycles.)
+// The dictionary slice arrives with one 32 KB TMA bulk copy, the records through per-warp TMA rings.
 template <int NV>
 __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const __grid_constant__ IngestParams p,
                                                                            const __grid_constant__ TwoPassParams tp) {
@@ -325,19 +343,22 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
   uint32_t* slo = scnt + BD_CAPB;                                                      // [BD_CAPB] sum, low word
   uint32_t* shi = slo + BD_CAPB;                                                       // [BD_CAPB] sum, high word
   Rec* ring = reinterpret_cast<Rec*>(shi + BD_CAPB);                                   // NW x NST x CH x 16
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + (size_t)P2_NW * P2_NST * P2_CH);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + (size_t)P2_NW * P2_NST * P2_CH);  // NW x NST + 1
   __shared__ unsigned long long s_rows;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t NB = p.dict.n_buckets;
   Rec* myring = ring + (size_t)w * P2_NST * P2_CH;
   const uint32_t bar0 = smem_u32(bars + (size_t)w * P2_NST);
+  const uint32_t kbar = smem_u32(bars + (size_t)P2_NW * P2_NST);  // the dictionary slice's barrier
   if (lane == 0)
     for (int s = 0; s < P2_NST; ++s) mbar_init(bar0 + 8 * s, 1);
+  if (tid == 0) mbar_init(kbar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   for (int i = tid; i < 3 * BD_CAPB; i += P2_NW * 32) scnt[i] = 0;
   if (tid == 0) s_rows = 0;
   __syncthreads();
   uint32_t phase = 0;  // bit s = parity of this warp's stage s
+  uint32_t kphase = 0;
 
   const uint32_t n_work = TP_NP * NB * tp.slices;
   for (uint32_t work = blockIdx.x; work < n_work; work += gridDim.x) {
@@ -356,13 +377,14 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
     unsigned long long* pane = tp.fast_ptr[psel];
     const uint64_t q = tp.fast_q[psel];
 
-    // the bucket's dictionary slice -> shared memory
-    {
-      const ulonglong2* src = reinterpret_cast<const ulonglong2*>(p.dict.slots + (size_t)b * BD_KS);
-      ulonglong2* dst = reinterpret_cast<ulonglong2*>(ktab);
-      for (int i = tid; i < BD_KS; i += P2_NW * 32) dst[i] = __ldcg(src + i);
+    // the bucket's dictionary slice -> shared memory: one bulk copy (the previous bucket's readers are past the
+    // barrier that ends the loop body)
+    if (tid == 0) {
+      // the slice was written through the generic proxy (local inserts); the bulk copy writes through the async proxy
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(kbar, BD_KS * 16);
+      tma_load_1d(smem_u32(ktab), p.dict.slots + (size_t)b * BD_KS, BD_KS * 16, kbar);
     }
-    __syncthreads();
 
     const unsigned n_chunks = (n + P2_CH - 1) / P2_CH;
     const unsigned my_chunks = n_chunks > (unsigned)w ? (n_chunks - w + P2_NW - 1) / P2_NW : 0;
@@ -375,6 +397,8 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
       }
     };
     for (unsigned ci = 0; ci < (unsigned)P2_NST && ci < my_chunks; ++ci) issue(ci, (int)ci);
+    mbar_wait(kbar, kphase);
+    kphase ^= 1u;
     unsigned int my_rows = 0;
     for (unsigned ci = 0; ci < my_chunks; ++ci) {
       const int s = (int)(ci % P2_NST);
@@ -387,30 +411,38 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
         const unsigned ri = sub * 32 + lane;
         if (ri < nr) {
           const Rec rec = chunk[ri];
-          const uint64_t h = mix64((uint64_t)rec.key);
-          uint32_t sl = bd_slot0(h);
+          uint32_t sl = bd_slot0(rec.key);
           uint32_t idx = ID_UNSET;
+          ulonglong2 e = *reinterpret_cast<const ulonglong2*>(ktab + sl);
+          if ((long long)e.x == rec.key && (uint32_t)e.y < ID_OVERFLOW) {
+            idx = (uint32_t)e.y;  // the common case: one shared-memory load
+          } else {
 #pragma unroll 1
-          for (int probe = 0; probe < BD_KS; ++probe) {
-            const ulonglong2 e = *reinterpret_cast<const ulonglong2*>(ktab + sl);
-            if ((long long)e.x == rec.key && (uint32_t)e.y < ID_OVERFLOW) {
-              idx = (uint32_t)e.y;
-              break;
-            }
-            if ((long long)e.x == EMPTY_KEY || (long long)e.x == rec.key) {
-              // first sight in this slice: global insert (race-free across blocks), then publish it locally
-              const uint32_t id = bd_insert(p.dict, b, rec.key, bd_slot0(h));
-              idx = id >= ID_OVERFLOW ? ID_OVERFLOW : id - bd_id(b, 0);
-              if ((long long)e.x == EMPTY_KEY && idx < ID_OVERFLOW) {
-                const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&ktab[sl].key),
-                                                         (unsigned long long)EMPTY_KEY, (unsigned long long)rec.key);
-                if (old == (unsigned long long)EMPTY_KEY) *(volatile uint32_t*)&ktab[sl].idx = idx;
+            for (int probe = 0; probe < BD_KS; ++probe) {
+              if ((long long)e.x == rec.key && (uint32_t)e.y < ID_OVERFLOW) {
+                idx = (uint32_t)e.y;
+                break;
               }
-              break;
+              if ((long long)e.x == EMPTY_KEY || (long long)e.x == rec.key) {
+                // first sight in this slice: global insert (race-free across blocks), then publish it locally
+                const uint32_t id = bd_insert(p.dict, b, rec.key, bd_slot0(rec.key));
+                idx = id >= ID_OVERFLOW ? ID_OVERFLOW : id - bd_id(b, 0);
+                if ((long long)e.x == EMPTY_KEY && idx < ID_OVERFLOW) {
+                  const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&ktab[sl].key),
+                                                           (unsigned long long)EMPTY_KEY, (unsigned long long)rec.key);
+                  if (old == (unsigned long long)EMPTY_KEY) *(volatile uint32_t*)&ktab[sl].idx = idx;
+                }
+                break;
+              }
+              sl = (sl + 1) & (BD_KS - 1);
+              e = *reinterpret_cast<const ulonglong2*>(ktab + sl);
             }
-            sl = (sl + 1) & (BD_KS - 1);
           }
-          if (idx < (uint32_t)BD_CAPB) {
+          if (NV > 0 && p.guard_vals && big_one(rec.val)) {
+            // exact-AVG guard (the partition pass does not look at values): park the row for the host's promotion
+            atomicAdd(&p.counters->big_vals, 1ull);
+            defer_row(p, rec.key, (long long)(q * (uint64_t)p.slide), rec.val, 0, 0, 0);
+          } else if (idx < (uint32_t)BD_CAPB) {
             atomicAdd(&scnt[idx], 1u);
             if (NV > 0) {
               const uint32_t vl = (uint32_t)(unsigned long long)rec.val;

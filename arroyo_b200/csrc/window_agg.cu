@@ -251,7 +251,7 @@ __device__ __noinline__ void slow_row(const IngestParams& p, long long key, long
   bool ok = ring_bin(p, slot) == (long long)(q * (uint64_t)p.slide);
   if (ok && p.keyed) {
     const uint64_t h = mix64((uint64_t)key);
-    const ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(bd_home(p.dict, h)));
+    const ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(bd_home(p.dict, key, h)));
     id = bd_resolve(p.dict, key, h, raw.x, (uint32_t)raw.y);
     ok = id < ID_OVERFLOW;
     if (!ok) atomicAdd(&p.counters->dict_full, 1u);
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(THREADS, AB_INGEST_MIN_BLOCKS) ingest_kernel(c
       for (int x = 0; x < (NV > 0 ? NV : 1); ++x) v[x] = nv[x];
       ulonglong2 raw = {0, 0};
       const uint64_t h = keyed ? mix64((uint64_t)key) : 0ull;
-      if (valid && keyed) raw = __ldcg(reinterpret_cast<const ulonglong2*>(bd_home(p.dict, h)));
+      if (valid && keyed) raw = __ldcg(reinterpret_cast<const ulonglong2*>(bd_home(p.dict, key, h)));
 #if AB_INGEST_PREFETCH
       if (i + THREADS < cnt) {
         if (keyed) nkey = __ldcs(ldg_ptr(&sg->key) + base + i + THREADS);
