@@ -98,6 +98,9 @@ int32_t arroyo_b200_op_create(const ArroyoB200OpConfig* config, ArroyoB200Op** o
       case ARROYO_B200_INSTANT_JOIN:
         impl = make_instant_join_op(*config);
         break;
+      case ARROYO_B200_UPDATING_AGGREGATE:
+        impl = make_updating_agg_op(*config);
+        break;
       default:
         set_err(err, err_len, "unknown operator kind");
         return ARROYO_B200_INVALID_ARGUMENT;
@@ -187,6 +190,23 @@ int32_t arroyo_b200_op_handle_watermark(ArroyoB200Op* op, int64_t watermark_ns, 
     auto* priv = new BatchesPriv();
     try {
       o->handle_watermark(watermark_ns, priv, nullptr);
+    } catch (...) {
+      ArroyoB200Batches tmp{};
+      batches_finish(priv, &tmp);
+      batches_release(&tmp);
+      throw;
+    }
+    batches_finish(priv, out);
+  });
+}
+
+int32_t arroyo_b200_op_handle_tick(ArroyoB200Op* op, ArroyoB200Batches* out) {
+  if (out) memset(out, 0, sizeof *out);
+  return guarded(op, [&](OpBase* o) {
+    AB_REQUIRE(out != nullptr, ARROYO_B200_INVALID_ARGUMENT, "null out");
+    auto* priv = new BatchesPriv();
+    try {
+      o->handle_tick(priv);
     } catch (...) {
       ArroyoB200Batches tmp{};
       batches_finish(priv, &tmp);

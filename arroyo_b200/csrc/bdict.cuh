@@ -55,8 +55,12 @@ __host__ __device__ __forceinline__ uint32_t bd_bucket(uint64_t h, uint32_t n_bu
 // the bucket -- the aggregation kernel computes only this one per row (its rows already sit in their bucket)
 constexpr int BD_KS_LOG2 = 11;
 static_assert((1 << BD_KS_LOG2) == BD_KS, "BD_KS_LOG2");
+// Home slots are aligned to groups of BD_GROUP slots (one 64-byte line): a key sits in its home group unless the
+// group overflowed, so a lookup is BD_GROUP straight-line compares (no divergent probe loop) and only the rare
+// overflow walks on.
+constexpr int BD_GROUP = 4;
 __host__ __device__ __forceinline__ uint32_t bd_slot0(long long key) {
-  return (uint32_t)(((uint64_t)key * 0xD6E8FEB86659FD93ull) >> (64 - BD_KS_LOG2));
+  return (uint32_t)(((uint64_t)key * 0xD6E8FEB86659FD93ull) >> (64 - BD_KS_LOG2)) & ~(uint32_t)(BD_GROUP - 1);
 }
 __host__ __device__ __forceinline__ uint32_t bd_id(uint32_t bucket, uint32_t idx) { return BD_ID_BASE + bucket * BD_CAPB + idx; }
 inline uint64_t bd_id_cap(uint64_t n_buckets) { return ((BD_ID_BASE + n_buckets * BD_CAPB + 1023) / 1024) * 1024; }
@@ -122,18 +126,21 @@ static __device__ __noinline__ uint32_t bd_insert(const BDict& d, uint32_t b, lo
   return ID_OVERFLOW;
 }
 
-// Id of `key` given the contents of its home slot (already loaded: the hot path issues that load early).  Known keys
-// resolve with read-only probes inline; first sightings go out of line.
+// Id of `key` given the contents of the first two slots of its home group (already loaded: the hot path issues those
+// loads early; they share one 32-byte sector).  Known keys resolve with read-only probes inline; first sightings go
+// out of line.
 __device__ __forceinline__ uint32_t bd_resolve(const BDict& d, long long key, uint64_t h, unsigned long long k0,
-                                               uint32_t idx0) {
+                                               uint32_t idx0, unsigned long long k1, uint32_t idx1) {
   if (key == EMPTY_KEY) return 0;  // id 0 is reserved for the one key that equals the empty sentinel
   const uint32_t b = bd_bucket(h, d.n_buckets);
   if ((long long)k0 == key && idx0 < ID_OVERFLOW) return bd_id(b, idx0);
+  if ((long long)k1 == key && idx1 < ID_OVERFLOW) return bd_id(b, idx1);
   uint32_t s = bd_slot0(key);
-  if ((long long)k0 != EMPTY_KEY && (long long)k0 != key) {
+  if ((long long)k0 != EMPTY_KEY && (long long)k0 != key && (long long)k1 != EMPTY_KEY && (long long)k1 != key) {
     const BSlot* tab = d.slots + (size_t)b * BD_KS;
+    s += 1;
 #pragma unroll 1
-    for (int probe = 1; probe < BD_KS; ++probe) {
+    for (int probe = 2; probe < BD_KS; ++probe) {
       s = (s + 1) & (BD_KS - 1);
       const ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(tab + s));
       if ((long long)raw.x == key && (uint32_t)raw.y < ID_OVERFLOW) return bd_id(b, (uint32_t)raw.y);

@@ -35,14 +35,17 @@ struct alignas(16) Rec {
 
 constexpr int TP_NP = 2;                 // fast panes per launch
 #ifndef AB_P1_THREADS
-#define AB_P1_THREADS 256
+#define AB_P1_THREADS 512
+#endif
+#ifndef AB_P1_RPT
+#define AB_P1_RPT 8
 #endif
 constexpr int P1_THREADS = AB_P1_THREADS;
-constexpr int P1_RPT = 16;
+constexpr int P1_RPT = AB_P1_RPT;
 constexpr int P1_TILE = P1_THREADS * P1_RPT;  // rows per tile
 constexpr int P1_NWARP = P1_THREADS / 32;
 constexpr int P1_NR = 1024;              // buckets a tile can be ranked over (shared-memory histogram)
-constexpr int P1_BLOCKS_PER_SM = P1_THREADS <= 256 ? 2 : 1;
+constexpr int P1_BLOCKS_PER_SM = P1_TILE <= 4096 ? 2 : 1;
 constexpr int P2_NW = 16;                // warps per aggregation block
 constexpr int P2_NST = 3;                // TMA ring stages per warp
 constexpr int P2_CH = 64;                // records per stage (1 KB)
@@ -54,7 +57,8 @@ struct TwoPassParams {
   unsigned long long* fast_ptr[TP_NP];  // their blocks
   uint32_t fast_slot[TP_NP];           // their ring slots (slot_rows index)
   Rec* part;                           // [TP_NP * n_buckets][cap]
-  unsigned int* cursor;                // [TP_NP * n_buckets]
+  unsigned int* cursor;                // [TP_NP * n_buckets], zero when the partition pass starts
+  unsigned int* cursor_next;           // the NEXT launch's cursors: the aggregation pass zeroes them
   uint32_t cap;                        // records per region
   uint32_t slices;                     // pass-2 blocks per region
 };
@@ -364,6 +368,7 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
   for (uint32_t work = blockIdx.x; work < n_work; work += gridDim.x) {
     const uint32_t region = work / tp.slices, slice = work % tp.slices;
     const uint32_t psel = region / NB, b = region % NB;
+    if (tid == 0) tp.cursor_next[region] = 0;  // nobody else touches the other cursor set during this launch
     const unsigned n_all = min(tp.cursor[region], tp.cap);
     if (n_all == 0 || tp.fast_ptr[psel] == nullptr) continue;  // block-uniform
     // this block's share of the region, in whole ring chunks
@@ -413,10 +418,19 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
           const Rec rec = chunk[ri];
           uint32_t sl = bd_slot0(rec.key);
           uint32_t idx = ID_UNSET;
-          ulonglong2 e = *reinterpret_cast<const ulonglong2*>(ktab + sl);
-          if ((long long)e.x == rec.key && (uint32_t)e.y < ID_OVERFLOW) {
-            idx = (uint32_t)e.y;  // the common case: one shared-memory load
-          } else {
+          {
+            // the key's home group: four slots, straight-line (a divergent probe loop here cost three quarters of the
+            // kernel's instructions: every warp has some lane that needs a second or third probe)
+            const ulonglong2* grp = reinterpret_cast<const ulonglong2*>(ktab + sl);
+            const ulonglong2 e0 = grp[0], e1 = grp[1], e2 = grp[2], e3 = grp[3];
+            idx = (long long)e0.x == rec.key ? (uint32_t)e0.y : idx;
+            idx = (long long)e1.x == rec.key ? (uint32_t)e1.y : idx;
+            idx = (long long)e2.x == rec.key ? (uint32_t)e2.y : idx;
+            idx = (long long)e3.x == rec.key ? (uint32_t)e3.y : idx;
+          }
+          if (idx >= ID_OVERFLOW) {
+            ulonglong2 e = *reinterpret_cast<const ulonglong2*>(ktab + sl);
+            idx = ID_UNSET;
 #pragma unroll 1
             for (int probe = 0; probe < BD_KS; ++probe) {
               if ((long long)e.x == rec.key && (uint32_t)e.y < ID_OVERFLOW) {

@@ -25,6 +25,7 @@ class OpBase {
   virtual void handle_watermark(int64_t watermark, BatchesPriv* out_host, std::vector<ArroyoB200DeviceBatch>* out_dev) = 0;
   virtual void handle_checkpoint(int64_t watermark, BatchesPriv* out) = 0;
   virtual void on_close(int end_of_data, BatchesPriv* out) = 0;
+  virtual void handle_tick(BatchesPriv* /*out*/) {}
   virtual void flush() = 0;
   // enqueue whatever input is still being batched on the host side; does not wait
   virtual void submit() {}
@@ -40,5 +41,6 @@ class OpBase {
 OpBase* make_window_agg_op(const ArroyoB200OpConfig& cfg);
 OpBase* make_instant_join_op(const ArroyoB200OpConfig& cfg);
 OpBase* make_session_op(const ArroyoB200OpConfig& cfg);
+OpBase* make_updating_agg_op(const ArroyoB200OpConfig& cfg);
 
 }  // namespace ab

@@ -251,8 +251,9 @@ __device__ __noinline__ void slow_row(const IngestParams& p, long long key, long
   bool ok = ring_bin(p, slot) == (long long)(q * (uint64_t)p.slide);
   if (ok && p.keyed) {
     const uint64_t h = mix64((uint64_t)key);
-    const ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(bd_home(p.dict, key, h)));
-    id = bd_resolve(p.dict, key, h, raw.x, (uint32_t)raw.y);
+    const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(bd_home(p.dict, key, h));
+    const ulonglong2 raw = __ldcg(hp), raw1 = __ldcg(hp + 1);
+    id = bd_resolve(p.dict, key, h, raw.x, (uint32_t)raw.y, raw1.x, (uint32_t)raw1.y);
     ok = id < ID_OVERFLOW;
     if (!ok) atomicAdd(&p.counters->dict_full, 1u);
   }
@@ -293,9 +294,9 @@ __device__ __forceinline__ void flush_counts(const IngestParams& p, PaneCache& p
 template <int NV, int SIG>
 __device__ __forceinline__ uint32_t hot_resolve(const IngestParams& p, const PaneCache& pc, uint64_t& maxq, bool keyed,
                                                 long long key, long long ts, uint64_t q, const Vals& v, uint64_t h,
-                                                unsigned long long k0, uint32_t id0) {
+                                                unsigned long long k0, uint32_t id0, unsigned long long k1, uint32_t id1) {
   uint32_t id = ID_OVERFLOW;
-  if (q == pc.q && pc.ptr != nullptr) id = keyed ? bd_resolve(p.dict, key, h, k0, id0) : 0u;
+  if (q == pc.q && pc.ptr != nullptr) id = keyed ? bd_resolve(p.dict, key, h, k0, id0, k1, id1) : 0u;
   if (NV > 0 && p.guard_vals && big_value(p.guard_vals, v)) {
     // AVG is being derived from the exact integer sum: a value this large could overflow it.  Park the
     // row; the host promotes the operator to f64 AVG accumulators and re-ingests it.
@@ -450,9 +451,13 @@ __global__ void __launch_bounds__(THREADS, AB_INGEST_MIN_BLOCKS) ingest_kernel(c
       long long v[NV > 0 ? NV : 1];
 #pragma unroll
       for (int x = 0; x < (NV > 0 ? NV : 1); ++x) v[x] = nv[x];
-      ulonglong2 raw = {0, 0};
+      ulonglong2 raw = {0, 0}, raw1 = {0, 0};
       const uint64_t h = keyed ? mix64((uint64_t)key) : 0ull;
-      if (valid && keyed) raw = __ldcg(reinterpret_cast<const ulonglong2*>(bd_home(p.dict, key, h)));
+      if (valid && keyed) {
+        const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(bd_home(p.dict, key, h));
+        raw = __ldcg(hp);
+        raw1 = __ldcg(hp + 1);
+      }
 #if AB_INGEST_PREFETCH
       if (i + THREADS < cnt) {
         if (keyed) nkey = __ldcs(ldg_ptr(&sg->key) + base + i + THREADS);
@@ -482,7 +487,7 @@ __global__ void __launch_bounds__(THREADS, AB_INGEST_MIN_BLOCKS) ingest_kernel(c
       }
       const Vals pv = pack_vals<NV>(v);
       uint32_t id = ID_OVERFLOW;
-      if (live) id = hot_resolve<NV, SIG>(p, pc, maxq, keyed, key, ts, q, pv, h, raw.x, (uint32_t)raw.y);
+      if (live) id = hot_resolve<NV, SIG>(p, pc, maxq, keyed, key, ts, q, pv, h, raw.x, (uint32_t)raw.y, raw1.x, (uint32_t)raw1.y);
       const bool fast = id < ID_OVERFLOW;
       if (fast) ++pc.cnt;
       if (p.combine) combine_accumulate<NV, SIG>(p, pc, fast, id, pv, lane);
@@ -576,8 +581,11 @@ __global__ void ingest_partial_kernel(const __grid_constant__ PartialParams p) {
 // -------------------------------------------------------------------------------------------
 // emission: pane merge (K4) + finalise + projection (K5) + compaction
 // -------------------------------------------------------------------------------------------
+constexpr int EMIT_INLINE = 16;
 struct EmitParams {
-  const unsigned long long* const* panes;  // device array of n_panes block pointers
+  const unsigned long long* const* panes;  // device array of n_panes block pointers (more than EMIT_INLINE panes)
+  const unsigned long long* inline_panes[EMIT_INLINE];  // ... or the pointers themselves
+  int panes_inline;
   int n_panes;
   int n_acc;
   unsigned long long id_cap;
@@ -595,7 +603,8 @@ struct EmitParams {
   long long* out_wend;
   long long* out_ts;
   long long wstart, wend, ts;
-  unsigned int* out_count;
+  unsigned int* out_count;  // cumulative over the operator's life (wraps); this emission's rows start at out_base
+  unsigned int out_base;
   // running-window mode: W (same layout as a pane) is updated in place with
   // W += add panes, W -= sub panes and the output is produced from W.
   unsigned long long* running;
@@ -682,7 +691,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(const __grid_constan
             acc1[a] = v.y;
           }
         for (int k = 0; k < p.n_panes; ++k) {
-          const unsigned long long* pane = p.panes[k];
+          const unsigned long long* pane = p.panes_inline ? p.inline_panes[k] : p.panes[k];
           const bool add = k < p.n_add;
 #pragma unroll
           for (int a = 0; a < NACC; ++a)
@@ -713,7 +722,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(const __grid_constan
             acc1[a] = ident;
           }
         for (int k = 0; k < p.n_panes; ++k) {
-          const unsigned long long* pane = p.panes[k];
+          const unsigned long long* pane = p.panes_inline ? p.inline_panes[k] : p.panes[k];
 #pragma unroll
           for (int a = 0; a < NACC; ++a)
             {
@@ -736,7 +745,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(const __grid_constan
         s_warp[i] = total;
         total += c;
       }
-      s_base = total ? atomicAdd(p.out_count, total) : 0u;
+      s_base = total ? atomicAdd(p.out_count, total) - p.out_base : 0u;
     }
     __syncthreads();
     const unsigned int lt = (1u << lane) - 1u;
@@ -807,8 +816,8 @@ struct Pane {
 struct LaunchRec {
   cudaEvent_t done = nullptr;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
-  Counters* h_counters = nullptr;  // pinned
-  unsigned long long* h_slot_rows = nullptr;  // pinned [MAX_RING]
+  Counters* h_counters = nullptr;  // pinned: [Counters | slot_rows[MAX_RING]] as copied back in one piece
+  unsigned long long* h_slot_rows = nullptr;
   uint64_t rows = 0;
   bool in_flight = false;
   int chunk = -1;  // staging chunk read by this launch (-1: none)
@@ -873,13 +882,22 @@ class WindowAggOp final : public OpBase {
   // dictionary (bdict.cuh): n_buckets_ buckets of BD_KS slots; ids = BD_ID_BASE + bucket * BD_CAPB + index
   uint64_t id_cap_ = 0;
   uint64_t n_buckets_ = 1;
-  DevBuf slots_, bucket_nkeys_, id_keys_, counters_, slot_rows_;
+  DevBuf slots_, bucket_nkeys_, id_keys_;
+  // bookkeeping the kernels report back, one contiguous buffer = one device->host copy per launch:
+  // [Counters | slot_rows[MAX_RING]].  slot_rows (on-time rows per ring slot) is cumulative; the host works with the
+  // difference between consecutive launches (no per-launch memset).
+  DevBuf book_;
+  static constexpr size_t BOOK_SLOT_OFF = (sizeof(Counters) + 15) / 16 * 16;
+  Counters* d_counters() const { return reinterpret_cast<Counters*>(book_.p); }
+  unsigned long long* d_slot_rows() const { return reinterpret_cast<unsigned long long*>((char*)book_.p + BOOK_SLOT_OFF); }
+  std::vector<unsigned long long> slot_rows_seen_;
   uint32_t n_keys_host_ = 1;       // ids in use = the id range the element-wise kernels walk (all of it: bucket ranges)
   uint32_t total_keys_host_ = 0;   // keys in the dictionary (statistics, growth policy)
   uint32_t dict_full_seen_ = 0;
   // two-pass ingest (ingest_two_pass.cuh)
-  DevBuf part_, part_cursor_;
+  DevBuf part_, part_cursor_;  // part_cursor_: two cursor sets; a launch's aggregation pass re-zeroes the other one
   uint32_t part_cap_ = 0;
+  int part_flip_ = 0;
   bool two_pass_attr_set_ = false;
   bool two_pass_enabled_ = true;
   uint64_t part_overflow_seen_ = 0;
@@ -942,7 +960,7 @@ class WindowAggOp final : public OpBase {
   PinnedBuf h_segs_[NLAUNCH];
   DevBuf d_segs_[NLAUNCH];
   LaunchRec launches_[NLAUNCH];
-  PinnedBuf h_counters_[NLAUNCH], h_slot_rows_[NLAUNCH];
+  PinnedBuf h_book_[NLAUNCH];
   int next_launch_ = 0;
   std::deque<int> in_flight_;
   std::deque<PendingRelease> releases_;
@@ -966,6 +984,7 @@ class WindowAggOp final : public OpBase {
   };
   std::vector<std::unique_ptr<OutSet>> out_sets_;
   DevBuf d_emit_panes_, d_out_count_;
+  unsigned int out_count_base_ = 0;
   PinnedBuf h_out_count_;
 
   ArroyoB200Stats st_{};
@@ -1119,12 +1138,13 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
   if (sliding_) sliding_planner_.reset(new SlidingPlanner(width_, slide_));
   else tumbling_.reset(new TumblingPlanner(width_));
 
-  counters_.alloc(sizeof(Counters));
-  slot_rows_.alloc(MAX_RING * sizeof(unsigned long long));
+  book_.alloc(BOOK_SLOT_OFF + MAX_RING * sizeof(unsigned long long));
+  AB_CUDA(cudaMemsetAsync(book_.p, 0, book_.bytes, stream_));
+  slot_rows_seen_.assign(MAX_RING, 0);
   Counters init{};
   init.max_q = 0;
   init.n_keys = 0;
-  AB_CUDA(cudaMemcpyAsync(counters_.p, &init, sizeof init, cudaMemcpyHostToDevice, stream_));
+  AB_CUDA(cudaMemcpyAsync(book_.p, &init, sizeof init, cudaMemcpyHostToDevice, stream_));
   last_counters_ = init;
 
   // one bucket per ~BD_MEAN expected keys (the bucket count doubles when a bucket runs out of ids)
@@ -1156,10 +1176,9 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
   for (int i = 0; i < NLAUNCH; ++i) {
     h_segs_[i].alloc(MAX_SEGS * sizeof(Segment));
     d_segs_[i].alloc(MAX_SEGS * sizeof(Segment));
-    h_counters_[i].alloc(sizeof(Counters));
-    h_slot_rows_[i].alloc(MAX_RING * sizeof(unsigned long long));
-    launches_[i].h_counters = h_counters_[i].as<Counters>();
-    launches_[i].h_slot_rows = h_slot_rows_[i].as<unsigned long long>();
+    h_book_[i].alloc(BOOK_SLOT_OFF + MAX_RING * sizeof(unsigned long long));
+    launches_[i].h_counters = h_book_[i].as<Counters>();
+    launches_[i].h_slot_rows = reinterpret_cast<unsigned long long*>((char*)h_book_[i].p + BOOK_SLOT_OFF);
     AB_CUDA(cudaEventCreateWithFlags(&launches_[i].done, cudaEventDisableTiming));
     if (profile_) {
       AB_CUDA(cudaEventCreate(&launches_[i].t0));
@@ -1170,6 +1189,7 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
   defer_cap_ = (uint64_t)chunk_rows_ * 2;
   d_emit_panes_.alloc(MAX_MERGE * sizeof(void*));
   d_out_count_.alloc(sizeof(unsigned int));
+  AB_CUDA(cudaMemsetAsync(d_out_count_.p, 0, sizeof(unsigned int), stream_));
   h_out_count_.alloc(sizeof(unsigned int));
   preallocate();
   AB_CUDA(cudaStreamSynchronize(stream_));
@@ -1260,7 +1280,7 @@ BDict WindowAggOp::dict_view() const {
   d.slots = slots_.as<BSlot>();
   d.nkeys = bucket_nkeys_.as<unsigned int>();
   d.id_keys = id_keys_.as<long long>();
-  d.n_total = (unsigned int*)((char*)counters_.p + offsetof(Counters, n_keys));
+  d.n_total = (unsigned int*)((char*)book_.p + offsetof(Counters, n_keys));
   d.n_buckets = (uint32_t)n_buckets_;
   return d;
 }
@@ -1343,7 +1363,7 @@ void WindowAggOp::grow_ids() {
   old_d.nkeys = old_nkeys.as<unsigned int>();
   old_d.id_keys = old_keys.as<long long>();
   const unsigned int zero = 0;
-  AB_CUDA(cudaMemcpyAsync((char*)counters_.p + offsetof(Counters, n_keys), &zero, sizeof zero, cudaMemcpyHostToDevice, stream_));
+  AB_CUDA(cudaMemcpyAsync((char*)book_.p + offsetof(Counters, n_keys), &zero, sizeof zero, cudaMemcpyHostToDevice, stream_));
   alloc_dictionary(n_buckets_ * 2);
   const uint64_t new_cap = id_cap_;
   DevBuf map((size_t)old_cap * sizeof(uint32_t));
@@ -1377,7 +1397,7 @@ void WindowAggOp::grow_ids() {
   }
   running_ = migrate(running_);
   Counters c{};
-  AB_CUDA(cudaMemcpyAsync(&c, counters_.p, sizeof c, cudaMemcpyDeviceToHost, stream_));
+  AB_CUDA(cudaMemcpyAsync(&c, book_.p, sizeof c, cudaMemcpyDeviceToHost, stream_));
   AB_CUDA(cudaStreamSynchronize(stream_));
   total_keys_host_ = c.n_keys;
   free_panes_.clear();
@@ -1790,11 +1810,14 @@ void WindowAggOp::launch_two_pass(IngestParams& p, uint64_t rows, long long tile
   if (part_cap_ != cap || !part_.p) {
     AB_CUDA(cudaStreamSynchronize(stream_));
     part_.alloc((size_t)n_regions * cap * sizeof(Rec));
-    part_cursor_.alloc((size_t)n_regions * sizeof(unsigned int));
+    part_cursor_.alloc((size_t)2 * n_regions * sizeof(unsigned int));
+    AB_CUDA(cudaMemsetAsync(part_cursor_.p, 0, (size_t)2 * n_regions * sizeof(unsigned int), stream_));
     part_cap_ = cap;
   }
   tp.part = part_.as<Rec>();
-  tp.cursor = part_cursor_.as<unsigned int>();
+  tp.cursor = part_cursor_.as<unsigned int>() + (size_t)part_flip_ * n_regions;
+  tp.cursor_next = part_cursor_.as<unsigned int>() + (size_t)(part_flip_ ^ 1) * n_regions;
+  part_flip_ ^= 1;
   tp.cap = cap;
   // blocks per region in pass 2: enough blocks to fill the GPU when there are few buckets
   const uint32_t want_blocks = (uint32_t)num_sms_ * 2;
@@ -1807,7 +1830,6 @@ void WindowAggOp::launch_two_pass(IngestParams& p, uint64_t rows, long long tile
     AB_CUDA(cudaFuncSetAttribute(agg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2_SMEM));
     two_pass_attr_set_ = true;
   }
-  AB_CUDA(cudaMemsetAsync(part_cursor_.p, 0, (size_t)n_regions * sizeof(unsigned int), stream_));
   const int grid1 = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)num_sms_ * P1_BLOCKS_PER_SM));
   const int grid2 = (int)std::max<uint32_t>(1, std::min<uint32_t>(n_regions * tp.slices, (uint32_t)num_sms_ * P2_BLOCKS_PER_SM));
   if (n_vals_ == 0) {
@@ -1850,7 +1872,6 @@ void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk
   }
   AB_CUDA(cudaMemcpyAsync(d_segs_[li].p, hs, segs_in.size() * sizeof(Segment), cudaMemcpyHostToDevice, stream_));
   if (ring_ > RING_INLINE) upload_ring();
-  AB_CUDA(cudaMemsetAsync(slot_rows_.p, 0, ring_ * sizeof(unsigned long long), stream_));
   if (!defer_[defer_cur_][0].p) {
     for (int c = 0; c < 2 + n_vals_; ++c) defer_[defer_cur_][c].alloc(defer_cap_ * 8);
   }
@@ -1883,8 +1904,8 @@ void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk
     p.acc_kind[a] = acc_kind_[a];
     p.acc_val[a] = acc_val_[a];
   }
-  p.counters = counters_.as<Counters>();
-  p.slot_rows = slot_rows_.as<unsigned long long>();
+  p.counters = d_counters();
+  p.slot_rows = d_slot_rows();
   p.d_key = defer_[defer_cur_][0].as<long long>();
   p.d_ts = defer_[defer_cur_][1].as<long long>();
   for (int v = 0; v < n_vals_; ++v) p.d_val[v] = defer_[defer_cur_][2 + v].as<long long>();
@@ -1929,8 +1950,8 @@ void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk
   if (profile_) AB_CUDA(cudaEventRecord(L.t1, stream_));
   ++st_.kernel_launches;
   ++st_.ingest_launches;
-  AB_CUDA(cudaMemcpyAsync(L.h_counters, counters_.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream_));
-  AB_CUDA(cudaMemcpyAsync(L.h_slot_rows, slot_rows_.p, ring_ * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+  AB_CUDA(cudaMemcpyAsync(L.h_counters, book_.p, BOOK_SLOT_OFF + ring_ * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                          stream_));
   AB_CUDA(cudaEventRecord(L.done, stream_));
   if (chunk >= 0) AB_CUDA(cudaEventRecord(chunk_free_[chunk], stream_));
   L.rows = rows;
@@ -1999,10 +2020,12 @@ void WindowAggOp::absorb(int li) {
   }
   if (c.max_q) max_bin_seen_ = std::max<int64_t>(max_bin_seen_, (int64_t)(c.max_q * (uint64_t)slide_));
   for (uint32_t s = 0; s < ring_; ++s) {
-    if (L.h_slot_rows[s]) {
+    const unsigned long long fresh = L.h_slot_rows[s] - slot_rows_seen_[s];  // cumulative on the device
+    slot_rows_seen_[s] = L.h_slot_rows[s];
+    if (fresh) {
       AB_REQUIRE(h_pane_bins_[s] != FREE_BIN, ARROYO_B200_RUNTIME, "touched a free ring slot");
       Pane& tp = panes_.at(h_pane_bins_[s]);
-      tp.rows += L.h_slot_rows[s];
+      tp.rows += fresh;
       if (tp.rows >= (1ull << 31)) need_promote_ = true;
       touch(h_pane_bins_[s]);
     }
@@ -2069,7 +2092,7 @@ void WindowAggOp::drain_deferred() {
     const int full = defer_cur_;
     defer_cur_ ^= 1;
     unsigned long long zero = 0;
-    AB_CUDA(cudaMemcpyAsync((char*)counters_.p + offsetof(Counters, deferred), &zero, sizeof zero,
+    AB_CUDA(cudaMemcpyAsync((char*)book_.p + offsetof(Counters, deferred), &zero, sizeof zero,
                             cudaMemcpyHostToDevice, stream_));
     Segment s{};
     s.key = defer_[full][0].as<long long>();
@@ -2154,10 +2177,13 @@ int64_t WindowAggOp::run_emit(const std::vector<const unsigned long long*>& bloc
                               bool partial, int64_t wstart, int64_t wend, int64_t ts, OutSet* os) {
   AB_REQUIRE(blocks.size() <= (size_t)MAX_MERGE, ARROYO_B200_RUNTIME, "too many panes in one window");
   const uint32_t n_ids = n_keys_host_;
-  if (!blocks.empty())
-    AB_CUDA(cudaMemcpyAsync(d_emit_panes_.p, blocks.data(), blocks.size() * sizeof(void*), cudaMemcpyHostToDevice, stream_));
-  AB_CUDA(cudaMemsetAsync(d_out_count_.p, 0, sizeof(unsigned int), stream_));
   EmitParams p{};
+  p.panes_inline = blocks.size() <= (size_t)EMIT_INLINE ? 1 : 0;
+  if (p.panes_inline) {
+    for (size_t i = 0; i < blocks.size(); ++i) p.inline_panes[i] = blocks[i];
+  } else {
+    AB_CUDA(cudaMemcpyAsync(d_emit_panes_.p, blocks.data(), blocks.size() * sizeof(void*), cudaMemcpyHostToDevice, stream_));
+  }
   p.panes = d_emit_panes_.as<const unsigned long long*>();
   p.n_panes = (int)blocks.size();
   p.n_acc = n_acc_;
@@ -2190,6 +2216,7 @@ int64_t WindowAggOp::run_emit(const std::vector<const unsigned long long*>& bloc
   p.wend = wend;
   p.ts = ts;
   p.out_count = d_out_count_.as<unsigned int>();
+  p.out_base = out_count_base_;
   p.running = use_running ? running_ : nullptr;
   p.n_add = n_add;
   p.partial = partial ? 1 : 0;
@@ -2238,7 +2265,9 @@ int64_t WindowAggOp::run_emit(const std::vector<const unsigned long long*>& bloc
   ++st_.emit_launches;
   AB_CUDA(cudaMemcpyAsync(h_out_count_.p, d_out_count_.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream_));
   AB_CUDA(cudaStreamSynchronize(stream_));
-  const int64_t n_out = (int64_t)*h_out_count_.as<unsigned int>();
+  const unsigned int out_now = *h_out_count_.as<unsigned int>();
+  const int64_t n_out = (int64_t)(unsigned int)(out_now - out_count_base_);
+  out_count_base_ = out_now;
   for (auto& d : dup_cols)
     if (n_out) AB_CUDA(cudaMemcpyAsync(d.second, d.first, (size_t)n_out * 8, cudaMemcpyDeviceToDevice, stream_));
   return n_out;
@@ -2676,13 +2705,13 @@ void WindowAggOp::on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, i
     pp.dict = dict_view();
     pp.pane = panes_.at(bin).frozen;
     pp.id_cap = id_cap_;
-    pp.counters = counters_.as<Counters>();
+    pp.counters = d_counters();
     int grid = (int)std::min<int64_t>((rows + 255) / 256, (int64_t)num_sms_ * 8);
     ingest_partial_kernel<<<std::max(grid, 1), 256, 0, stream_>>>(pp);
     AB_CUDA(cudaGetLastError());
     ++st_.kernel_launches;
     Counters c{};
-    AB_CUDA(cudaMemcpyAsync(&c, counters_.p, sizeof c, cudaMemcpyDeviceToHost, stream_));
+    AB_CUDA(cudaMemcpyAsync(&c, book_.p, sizeof c, cudaMemcpyDeviceToHost, stream_));
     AB_CUDA(cudaStreamSynchronize(stream_));
     AB_REQUIRE(c.lost == 0, ARROYO_B200_RUNTIME, "dictionary overflow during restore");
     total_keys_host_ = c.n_keys;

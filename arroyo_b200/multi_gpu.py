@@ -368,6 +368,9 @@ class LaggedCombiner:
         self.step = 0
         self.last_closed = None
         self.error = None
+        # where the host time of a step goes (seconds, accumulated; reset with reset_times())
+        self.times = {"feed": 0.0, "wait_round": 0.0, "wait_packed": 0.0, "local_close": 0.0, "pack": 0.0, "exchange": 0.0,
+                      "owner_ingest": 0.0, "owner_watermark": 0.0, "owner_idle": 0.0}
         self.th = threading.Thread(target=self._owner_loop, daemon=True)
         self.th.start()
 
@@ -376,23 +379,38 @@ class LaggedCombiner:
         """One step of the local stage: `feed()` enqueues the step's input on the local operator (asynchronously);
         then the panes that the effective watermark of round p - lag closes leave as partial rows.  Feeding first
         keeps the device busy with the ingest while this thread waits for the round and for the emission."""
+        import time
+        T = self.times
         p = self.step
         self.step += 1
+        t0 = time.perf_counter()
         feed()
+        t1 = time.perf_counter()
         eff = None
         with self.cv:
             if p - self.lag >= 0:
                 self.cv.wait_for(lambda: (p - self.lag) in self.eff_after or self.error is not None)
                 self._raise()
                 eff = self.eff_after.pop(p - self.lag)
+            t2 = time.perf_counter()
             # the previous step's partial rows must have been packed before the local stage overwrites them
             self.cv.wait_for(lambda: self.packed_upto >= p - 1 or self.error is not None)
             self._raise()
+        t3 = time.perf_counter()
         chunks, closing = [], None
         if eff is not None and eff != self.last_closed:
             chunks = self.local_close(eff)
             closing = self.last_closed = eff
+        t4 = time.perf_counter()
+        T["feed"] += t1 - t0
+        T["wait_round"] += t2 - t1
+        T["wait_packed"] += t3 - t2
+        T["local_close"] += t4 - t3
         self.q.put((p, closing, chunks, watermark))
+
+    def reset_times(self):
+        for k in self.times:
+            self.times[k] = 0.0
 
     def drain(self):
         """Waits until the owner stage has consumed everything queued so far."""
@@ -415,25 +433,35 @@ class LaggedCombiner:
         try:
             if self.thread_init:
                 self.thread_init()
+            import time
+            T = self.times
             while True:
+                t0 = time.perf_counter()
                 item = self.q.get()
+                T["owner_idle"] += time.perf_counter() - t0
                 if item is None:
                     self.q.task_done()
                     return
                 p, closing, chunks, wm = item
                 i = 0
                 while True:
+                    t0 = time.perf_counter()
                     if i < len(chunks):
                         packed, counts, m = self.pack(chunks[i])
                     else:
                         packed, counts, m = None, None, 0
                     i += 1
+                    t1 = time.perf_counter()
                     batches, _, any_more = self.ex.round_packed(packed, counts, m, wm if i == 1 else None,
                                                                 more=i < len(chunks))
+                    t2 = time.perf_counter()
                     if batches:
                         # the receive buffers come round again two rounds later: rows that no watermark is about to
                         # push through the owner must be consumed now
                         self.owner_ingest(batches, consume_now=any_more or closing is None)
+                    T["pack"] += t1 - t0
+                    T["exchange"] += t2 - t1
+                    T["owner_ingest"] += time.perf_counter() - t2
                     if not any_more:
                         break
                 with self.cv:
@@ -441,7 +469,9 @@ class LaggedCombiner:
                     self.eff_after[p] = self.ex.holder.last_present_watermark
                     self.cv.notify_all()
                 if closing is not None:
+                    t0 = time.perf_counter()
                     self.owner_watermark(closing)
+                    T["owner_watermark"] += time.perf_counter() - t0
                 self.q.task_done()
                 with self.cv:
                     self.cv.notify_all()
@@ -543,7 +573,7 @@ def _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, pane
     raw_schema = pa.schema([("key", pa.int64()), ("value", pa.int64()), ("_timestamp", pa.timestamp("ns"))])
     plan = part = ex = None
     if mode == "partials":
-        plan = PartialsPlan(torch, dist, B, ab, native, args, rank, world, local, device, flags, B.op_flags(args),
+        plan = PartialsPlan(torch, dist, B, ab, native, args, rank, world, local, device, flags, flags,
                             raw_schema=raw_schema)
         local_op, owner_op, ex = plan.local_op, plan.owner_op, plan.ex
     else:
@@ -630,6 +660,8 @@ def _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, pane
     dist.barrier()
     st0 = timed_op.stats()
     so0 = owner_op.stats()
+    if pipe is not None:
+        pipe.reset_times()
     rows_out_warm = rows_out
     rows_out = 0
     sent0 = ex.bytes_sent
@@ -658,6 +690,7 @@ def _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, pane
     tot = torch.tensor([launches, rows_out, d["rows_in"]], dtype=torch.int64, device=device)
     dist.all_reduce(tot)
     sent = ex.bytes_sent - sent0
+    host_ms = {k: round(1e3 * v / max(K, 1), 4) for k, v in pipe.times.items()} if pipe is not None else None
     if pipe is not None:
         pipe.close()
     if native_ex is not None:
@@ -669,7 +702,10 @@ def _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, pane
         part.close()
     torch.cuda.empty_cache()
     return {"ms": ms, "d": d, "launches": int(tot[0].item()), "rows_out": int(tot[1].item()), "sent": sent,
-            "clocks": clocks, "sums": sums, "pipelined": pipe is not None, "rows_out_warm": rows_out_warm}
+            "clocks": clocks, "sums": sums, "pipelined": pipe is not None, "rows_out_warm": rows_out_warm,
+            "host_ms_per_step": host_ms,
+            "owner_ms": {"ingest_ms": (so1["ingest_ms"] - so0["ingest_ms"]) / max(K, 1),
+                         "emit_ms": (so1["emit_ms"] - so0["emit_ms"]) / max(K, 1)} if local_op is not None else None}
 
 
 def _gather_window_sums(torch, dist, device, sums):
@@ -802,6 +838,8 @@ def bench(args, torch, dist, rank, world, local, all_cpus=None):
                                         if traffic and traffic.get("dram_bytes_per_row") else None),
                             "algorithmic_bytes_per_launch": 24.0 * d["ingest_rows_timed"] / max(d["ingest_launches"], 1),
                             "note": "rank 0's raw-row ingest kernel"},
+               "host_ms_per_step": res["host_ms_per_step"], "owner_stage_kernel_ms_per_step": res["owner_ms"],
+               "local_stage_kernel_ms_per_step": {"ingest_ms": d["ingest_ms"] / max(K, 1), "emit_ms": d["emit_ms"] / max(K, 1)},
                "e2e": e2e, "clocks": res["clocks"],
                "shuffle_bytes_sent_per_step_per_gpu": res["sent"] // max(K, 1)}
         if cpu is not None:

@@ -299,7 +299,9 @@ class _WindowAggregate(_NativeOperator):
 
     def handle_watermark_device(self, wm: int, max_out: int = 64):
         """Emission left on the device: list of (n_rows, [device pointers])."""
-        out = (ffi.DeviceBatch * max_out)()
+        out = getattr(self, "_dev_out", None)
+        if out is None or len(out) < max_out:
+            out = self._dev_out = (ffi.DeviceBatch * max_out)()  # reused: building it costs more than the call
         n = C.c_int64(0)
         st = self._lib.arroyo_b200_op_handle_watermark_device(self._h, clamp_watermark(wm), out, max_out, C.byref(n))
         _check(self._lib, self._h, st)
@@ -474,6 +476,92 @@ class SessionAggregatingWindowFunc(_NativeOperator):
         st = self._lib.arroyo_b200_op_handle_watermark_device(self._h, clamp_watermark(wm), out, max_out, C.byref(n))
         _check(self._lib, self._h, st)
         return [(out[i].n_rows, [out[i].cols[c] for c in range(out[i].n_cols)]) for i in range(n.value)]
+
+
+class UpdatingAggregatingFunc(_NativeOperator):
+    """arroyo-worker/src/arrow/incremental_aggregator.rs (`IncrementalAggregatingFunc`): the non-windowed GROUP BY.
+    Change rows leave on ticks (`tick_interval` = flush interval, :990-1004), at checkpoints (:951-961) and at end of
+    data (:1006-1018): [key cols..., aggregates..., _timestamp, _is_retract].  `config`: anything with `key_names`
+    and `aggs` (oracle.updating_oracle.UpdatingAggConfig has the shape).  Append-only inputs only."""
+    kind = ffi.UPDATING_AGGREGATE
+    IS_RETRACT = "_is_retract"
+
+    def __init__(self, config, input_schema: Optional[pa.Schema] = None, updating_input: bool = False, **kw):
+        super().__init__(**kw)
+        self.config = config
+        self.updating_input = updating_input
+        if input_schema is not None:
+            self._build(input_schema.names)
+
+    def name(self):
+        return "UpdatingAggregatingFunc"
+
+    def tables(self):
+        return {"a": 0, "b": 0}  # accumulator state / batch state (:963-988): restore is not implemented
+
+    def _build(self, names: List[str]):
+        c = self.config
+        cfg = ffi.OpConfig()
+        cfg.kind = self.kind
+        cfg.n_cols = len(names)
+        cfg.timestamp_col = names.index(TIMESTAMP)
+        if len(c.key_names) > 1:
+            raise ffi.UnsupportedPlan(ffi.UNSUPPORTED, "more than one group-by key column")
+        cfg.n_key_cols = len(c.key_names)
+        cfg.key_col = names.index(c.key_names[0]) if c.key_names else 0
+        cfg.n_aggs = len(c.aggs)
+        for i, a in enumerate(c.aggs):
+            if a.kind not in _AGG_KINDS:
+                raise ffi.UnsupportedPlan(ffi.UNSUPPORTED, f"aggregate {a.kind}")
+            cfg.aggs[i].kind = _AGG_KINDS[a.kind]
+            cfg.aggs[i].input_col = names.index(a.col) if a.col is not None else 0
+        if self.updating_input:
+            self._flags |= ffi.FLAG_UPDATING_INPUT
+        self._create(cfg)
+
+    def output_names(self) -> List[str]:
+        return list(self.config.key_names) + [a.name for a in self.config.aggs] + [TIMESTAMP, self.IS_RETRACT]
+
+    def process_batch(self, batch: pa.RecordBatch, ctx: OperatorContext, collector: Collector):
+        if not self.created:
+            self._build(batch.schema.names)
+        arr, sch = export_batch(batch)
+        st = self._lib.arroyo_b200_op_process_batch(self._h, 0, 1, C.byref(arr), C.byref(sch))
+        if st != ffi.OK and arr.release:
+            C.CFUNCTYPE(None, C.c_void_p)(arr.release)(C.addressof(arr))
+        if sch.release:
+            C.CFUNCTYPE(None, C.c_void_p)(sch.release)(C.addressof(sch))
+        _check(self._lib, self._h, st)
+
+    def handle_watermark(self, watermark, ctx: OperatorContext, collector: Collector):
+        return watermark
+
+    def _emit(self, out, collector: Collector):
+        names = self.output_names()
+        for b in import_batches(self._lib, out):
+            collector.collect(pa.RecordBatch.from_arrays(b.columns, names=names))
+
+    def handle_tick(self, tick, ctx: OperatorContext, collector: Collector):
+        if not self.created:
+            return
+        out = ffi.Batches()
+        _check(self._lib, self._h, self._lib.arroyo_b200_op_handle_tick(self._h, C.byref(out)))
+        self._emit(out, collector)
+
+    def handle_checkpoint(self, barrier, ctx: OperatorContext, collector: Collector):
+        if not self.created:
+            return
+        out = ffi.Batches()
+        _check(self._lib, self._h, self._lib.arroyo_b200_op_handle_checkpoint(self._h, ffi.INT64_MIN, C.byref(out)))
+        self._emit(out, collector)
+
+    def on_close(self, final_message, ctx: OperatorContext, collector: Collector):
+        if not self.created:
+            return
+        out = ffi.Batches()
+        _check(self._lib, self._h, self._lib.arroyo_b200_op_on_close(self._h, 1 if final_message == "end_of_data" else 0,
+                                                                      C.byref(out)))
+        self._emit(out, collector)
 
 
 _JOIN_TYPES = {"inner": ffi.JOIN_INNER, "left": ffi.JOIN_LEFT, "right": ffi.JOIN_RIGHT, "full": ffi.JOIN_FULL}

@@ -89,7 +89,11 @@ typedef enum ArroyoB200OpKind {
   ARROYO_B200_TUMBLING_AGGREGATE = 1, /* OperatorName::TumblingWindowAggregate */
   ARROYO_B200_SLIDING_AGGREGATE = 2,  /* OperatorName::SlidingWindowAggregate  */
   ARROYO_B200_SESSION_AGGREGATE = 3,  /* OperatorName::SessionWindowAggregate  */
-  ARROYO_B200_INSTANT_JOIN = 4        /* OperatorName::InstantJoin             */
+  ARROYO_B200_INSTANT_JOIN = 4,       /* OperatorName::InstantJoin             */
+  ARROYO_B200_UPDATING_AGGREGATE = 5  /* OperatorName::UpdatingAggregate: IncrementalAggregatingFunc,
+                                       * arroyo-worker/src/arrow/incremental_aggregator.rs (append-only inputs;
+                                       * COUNT(*) / SUM / AVG / MIN / MAX over Int64; emits on ticks, checkpoints and
+                                       * end of data: rows [key?, aggregates..., _timestamp, is_retract bool])      */
 } ArroyoB200OpKind;
 
 typedef enum ArroyoB200AggKind {
@@ -186,6 +190,8 @@ typedef struct ArroyoB200OpConfig {
 #define ARROYO_B200_FLAG_NO_TWO_PASS 128u /* always use the one-pass ingest kernel (probe + REDs per  */
                                           /* row) instead of partition + shared-memory aggregation     */
                                           /* (measurement knob; results are identical)                */
+#define ARROYO_B200_FLAG_UPDATING_INPUT 512u /* UPDATING_AGGREGATE: the input is itself an updating stream (rows carry
+                                          * `_updating_meta.is_retract`): refused, ARROYO_B200_UNSUPPORTED            */
 #define ARROYO_B200_FLAG_TWO_PASS_ALWAYS 256u /* two-pass ingest for every eligible launch, however small  */
                                           /* (by default launches under 2^19 rows use the one-pass kernel: */
                                           /* the per-bucket set-up does not pay for them; test knob)       */
@@ -305,6 +311,11 @@ int32_t arroyo_b200_op_handle_watermark(ArroyoB200Op* op, int64_t watermark_ns, 
  *          else `*ready` = 0.  The shim forwards the watermark after it has collected the batches
  *          (operator.rs:777-786).  `begin` with an uncollected emission outstanding is an error; the other
  *          entry points may be called in between (the copies overlap the next batches' host->device copies). */
+/* ArrowOperator::handle_tick(tick, ctx, collector) (operator.rs:1233-1241), for operators whose `tick_interval()` is
+ * set -- the updating aggregate flushes its change rows here (incremental_aggregator.rs:990-1004).  Other operators
+ * emit nothing. */
+int32_t arroyo_b200_op_handle_tick(ArroyoB200Op* op, ArroyoB200Batches* out);
+
 int32_t arroyo_b200_op_handle_watermark_begin(ArroyoB200Op* op, int64_t watermark_ns);
 int32_t arroyo_b200_op_handle_watermark_poll(ArroyoB200Op* op, int32_t block, ArroyoB200Batches* out, int32_t* ready);
 
