@@ -13,11 +13,12 @@
 //                         staged in shared memory in bucket order (write combining) and every bucket's run is appended
 //                         to the bucket's region of a partition buffer with ONE global atomic per (tile, bucket);
 //                         records are {key, value}, 16 bytes.
-//   pass 2  agg_kernel    one block per (pane, bucket): the bucket's dictionary slice (32 KB) is loaded into shared
-//                         memory, the region's records arrive through per-warp TMA rings (cp.async.bulk + mbarrier),
-//                         every row is one shared-memory probe and two or three 32-bit shared-memory atomics on the
-//                         bucket's accumulators, which are then added to the bucket's contiguous id range of the pane
-//                         block (coalesced; plain read-modify-write when the bucket has one block).
+//   pass 2  agg_kernel    one block per (pane, bucket): builds a lookup table of the bucket's keys in shared memory (from
+//                         the bucket's contiguous id range of id_keys), the region's records arrive through per-warp
+//                         TMA rings (cp.async.bulk + mbarrier), every row is one straight-line shared-memory lookup
+//                         and two or three 32-bit shared-memory atomics on the bucket's accumulators, which are then
+//                         added to the bucket's contiguous id range of the pane block (coalesced; plain
+//                         read-modify-write when the bucket has one block).
 //
 // Algorithmic bytes: 24 per input row (read once).  Traffic of the pair: 24 + 16 (partition write) + 16 (read back)
 // + the dictionary slices and the pane block once per launch.
@@ -64,8 +65,8 @@ struct TwoPassParams {
 };
 
 constexpr size_t P1_SMEM = (size_t)P1_TILE * 16 + (size_t)P1_TILE * 2 + (size_t)P1_NR * 12;
-constexpr size_t P2_SMEM = (size_t)BD_KS * 16 + (size_t)BD_CAPB * 12 + (size_t)P2_NW * P2_NST * P2_CH * 16 +
-                           (size_t)(P2_NW * P2_NST + 1) * 8;
+constexpr size_t P2_SMEM = (size_t)4096 * 10 + (size_t)BD_CAPB * 12 + (size_t)P2_NW * P2_NST * P2_CH * 16 +
+                           (size_t)(P2_NW * P2_NST + 1) * 8;  // 4096 = P2_HS (lookup table: 8-byte keys + 2-byte indices)
 
 // A row that left the fast path after window assignment: accumulate it directly (global lookup + REDs).  `q` is its
 // pane number; the pane block is `pane`, its ring slot `slot`.  Rows that cannot get an id are deferred with the pane's
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
                 // the sentinel key owns id 0, outside every bucket
                 direct_rec<NV>(p, fpane, fslot, q, k[j], NV > 0 ? __ldcs(vcol + i) : 0ll);
               } else {
-                r = bd_bucket(mix64((uint64_t)k[j]), NB);
+                r = bd_bucket(bd_hash(k[j]), NB);
                 r |= atomicAdd(&hist[r], 1u) << 16;
               }
             }
@@ -332,37 +333,60 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-// One block per (pane, bucket[, slice]).  The bucket's accumulators live ONCE in shared memory and take shared-memory
-// atomics: ATOMS.ADD.32 runs at ~3.5 SM-cycles per warp instruction on spread addresses, duplicates inside a warp
-// included.  The 64-bit wrapping SUM is kept as two 32-bit words: the low word takes every row's low half (the
-// returned old value tells whether it wrapped), the high word takes the high half plus that carry -- for the small
-// positive values of a bid stream a second atomic is rare.  (A 64-bit shared atomicAdd is a CAS loop: 19-30 cycles.)
-// The dictionary slice arrives with one 32 KB TMA bulk copy, the records through per-warp TMA rings.
+// One block per (pane, bucket[, slice]).
+//
+// The block builds its own lookup table of the bucket's keys in shared memory: P2_HS key slots in groups of eight
+// (one 64-byte line), filled from the bucket's id range of `id_keys` (8 KB for a full bucket; the dictionary's own
+// 32 KB slice is not read).  At a quarter load a group overflows once in ten thousand keys, so a row's lookup is four
+// LDS.128 and eight compares, straight-line: with a probe LOOP, every warp has some lane that needs another round, and
+// the loop was three quarters of the kernel's instructions (profiles/r02_two_pass_c / _d).
+// The bucket's accumulators live once in shared memory and take shared-memory atomics (ATOMS.ADD.32: ~3.5 SM-cycles
+// per warp instruction on spread addresses, duplicates inside a warp included).  The 64-bit wrapping SUM is two 32-bit
+// words: the low word takes every row's low half (the returned old value tells whether it wrapped), the high word the
+// high half plus that carry -- for the small positive values of a bid stream the second atomic is rare.
+// Records arrive through per-warp TMA rings (cp.async.bulk + mbarrier).
+constexpr int P2_HS = 4096;  // key slots of the block's lookup table
+constexpr int P2_HG = 8;     // slots per group
+__device__ __forceinline__ uint32_t p2_group(long long key) {
+  return (uint32_t)(((uint64_t)key * 0xD6E8FEB86659FD93ull) >> 55) * P2_HG;  // P2_HS / P2_HG = 512 groups
+}
+
+// Inserts `key -> idx` into the block's table (home group first, then the following groups).
+__device__ __forceinline__ void p2_insert(unsigned long long* hk, unsigned short* hidx, long long key, uint32_t idx) {
+  uint32_t s = p2_group(key);
+  for (int probe = 0; probe < P2_HS; ++probe) {
+    const unsigned long long old = atomicCAS(&hk[s], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+    if (old == (unsigned long long)EMPTY_KEY || old == (unsigned long long)key) {
+      hidx[s] = (unsigned short)idx;
+      return;
+    }
+    s = (s + 1) & (P2_HS - 1);
+  }
+}
+
 template <int NV>
 __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const __grid_constant__ IngestParams p,
                                                                            const __grid_constant__ TwoPassParams tp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  BSlot* ktab = reinterpret_cast<BSlot*>(smem_raw);                                    // BD_KS x 16
-  uint32_t* scnt = reinterpret_cast<uint32_t*>(smem_raw + (size_t)BD_KS * 16);          // [BD_CAPB] rows
+  unsigned long long* hk = reinterpret_cast<unsigned long long*>(smem_raw);             // [P2_HS] keys
+  unsigned short* hidx = reinterpret_cast<unsigned short*>(hk + P2_HS);                 // [P2_HS] index inside the bucket
+  uint32_t* scnt = reinterpret_cast<uint32_t*>(hidx + P2_HS);                           // [BD_CAPB] rows
   uint32_t* slo = scnt + BD_CAPB;                                                      // [BD_CAPB] sum, low word
   uint32_t* shi = slo + BD_CAPB;                                                       // [BD_CAPB] sum, high word
   Rec* ring = reinterpret_cast<Rec*>(shi + BD_CAPB);                                   // NW x NST x CH x 16
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + (size_t)P2_NW * P2_NST * P2_CH);  // NW x NST + 1
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + (size_t)P2_NW * P2_NST * P2_CH);  // NW x NST
   __shared__ unsigned long long s_rows;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t NB = p.dict.n_buckets;
   Rec* myring = ring + (size_t)w * P2_NST * P2_CH;
   const uint32_t bar0 = smem_u32(bars + (size_t)w * P2_NST);
-  const uint32_t kbar = smem_u32(bars + (size_t)P2_NW * P2_NST);  // the dictionary slice's barrier
   if (lane == 0)
     for (int s = 0; s < P2_NST; ++s) mbar_init(bar0 + 8 * s, 1);
-  if (tid == 0) mbar_init(kbar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   for (int i = tid; i < 3 * BD_CAPB; i += P2_NW * 32) scnt[i] = 0;
   if (tid == 0) s_rows = 0;
   __syncthreads();
   uint32_t phase = 0;  // bit s = parity of this warp's stage s
-  uint32_t kphase = 0;
 
   const uint32_t n_work = TP_NP * NB * tp.slices;
   for (uint32_t work = blockIdx.x; work < n_work; work += gridDim.x) {
@@ -382,15 +406,7 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
     unsigned long long* pane = tp.fast_ptr[psel];
     const uint64_t q = tp.fast_q[psel];
 
-    // the bucket's dictionary slice -> shared memory: one bulk copy (the previous bucket's readers are past the
-    // barrier that ends the loop body)
-    if (tid == 0) {
-      // the slice was written through the generic proxy (local inserts); the bulk copy writes through the async proxy
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(kbar, BD_KS * 16);
-      tma_load_1d(smem_u32(ktab), p.dict.slots + (size_t)b * BD_KS, BD_KS * 16, kbar);
-    }
-
+    // the first record chunks are requested before the table is built
     const unsigned n_chunks = (n + P2_CH - 1) / P2_CH;
     const unsigned my_chunks = n_chunks > (unsigned)w ? (n_chunks - w + P2_NW - 1) / P2_NW : 0;
     auto issue = [&](unsigned ci, int s) {
@@ -402,8 +418,23 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
       }
     };
     for (unsigned ci = 0; ci < (unsigned)P2_NST && ci < my_chunks; ++ci) issue(ci, (int)ci);
-    mbar_wait(kbar, kphase);
-    kphase ^= 1u;
+
+    // ---- build the bucket's lookup table ----
+    for (int i = tid; i < P2_HS / 2; i += P2_NW * 32)
+      reinterpret_cast<ulonglong2*>(hk)[i] = make_ulonglong2((unsigned long long)EMPTY_KEY, (unsigned long long)EMPTY_KEY);
+    // 0xFFFF = "key claimed, index not published yet": a lookup that sees it takes the insert path and waits there
+    for (int i = tid; i < P2_HS / 8; i += P2_NW * 32) reinterpret_cast<uint4*>(hidx)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    __syncthreads();
+    {
+      const unsigned nk = min(*(volatile const unsigned*)(p.dict.nkeys + b), (unsigned)BD_CAPB);
+      const long long* bkeys = p.dict.id_keys + bd_id(b, 0);
+      for (unsigned i = tid; i < nk; i += P2_NW * 32) {
+        const long long key = __ldcg(bkeys + i);
+        if (key != EMPTY_KEY) p2_insert(hk, hidx, key, i);  // EMPTY: an insert that has not published its key yet
+      }
+    }
+    __syncthreads();
+
     unsigned int my_rows = 0;
     for (unsigned ci = 0; ci < my_chunks; ++ci) {
       const int s = (int)(ci % P2_NST);
@@ -416,40 +447,43 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
         const unsigned ri = sub * 32 + lane;
         if (ri < nr) {
           const Rec rec = chunk[ri];
-          uint32_t sl = bd_slot0(rec.key);
-          uint32_t idx = ID_UNSET;
+          uint32_t g = p2_group(rec.key);
+          int pos = -1;
           {
-            // the key's home group: four slots, straight-line (a divergent probe loop here cost three quarters of the
-            // kernel's instructions: every warp has some lane that needs a second or third probe)
-            const ulonglong2* grp = reinterpret_cast<const ulonglong2*>(ktab + sl);
-            const ulonglong2 e0 = grp[0], e1 = grp[1], e2 = grp[2], e3 = grp[3];
-            idx = (long long)e0.x == rec.key ? (uint32_t)e0.y : idx;
-            idx = (long long)e1.x == rec.key ? (uint32_t)e1.y : idx;
-            idx = (long long)e2.x == rec.key ? (uint32_t)e2.y : idx;
-            idx = (long long)e3.x == rec.key ? (uint32_t)e3.y : idx;
+            const ulonglong2* kp = reinterpret_cast<const ulonglong2*>(hk + g);
+            const ulonglong2 a = kp[0], bq = kp[1], c = kp[2], d = kp[3];
+            const unsigned long long key = (unsigned long long)rec.key;
+            pos = a.x == key ? 0 : pos;
+            pos = a.y == key ? 1 : pos;
+            pos = bq.x == key ? 2 : pos;
+            pos = bq.y == key ? 3 : pos;
+            pos = c.x == key ? 4 : pos;
+            pos = c.y == key ? 5 : pos;
+            pos = d.x == key ? 6 : pos;
+            pos = d.y == key ? 7 : pos;
           }
-          if (idx >= ID_OVERFLOW) {
-            ulonglong2 e = *reinterpret_cast<const ulonglong2*>(ktab + sl);
+          uint32_t idx = pos >= 0 ? (uint32_t)hidx[g + pos] : 0xFFFFu;
+          if (idx == 0xFFFFu) {
+            // not in the home group: it spilled into the following groups, or the block has not seen the key yet
             idx = ID_UNSET;
+            uint32_t sl = (g + P2_HG) & (P2_HS - 1);
+            bool full = true;  // the home group holds no empty slot <=> the key may have spilled
+            for (int x = 0; x < P2_HG; ++x) full = full && hk[g + x] != (unsigned long long)EMPTY_KEY;
 #pragma unroll 1
-            for (int probe = 0; probe < BD_KS; ++probe) {
-              if ((long long)e.x == rec.key && (uint32_t)e.y < ID_OVERFLOW) {
-                idx = (uint32_t)e.y;
+            for (int probe = 0; full && probe < P2_HS; ++probe) {
+              const unsigned long long e = hk[sl];
+              if (e == (unsigned long long)rec.key) {
+                idx = hidx[sl] == 0xFFFFu ? ID_UNSET : (uint32_t)hidx[sl];
                 break;
               }
-              if ((long long)e.x == EMPTY_KEY || (long long)e.x == rec.key) {
-                // first sight in this slice: global insert (race-free across blocks), then publish it locally
-                const uint32_t id = bd_insert(p.dict, b, rec.key, bd_slot0(rec.key));
-                idx = id >= ID_OVERFLOW ? ID_OVERFLOW : id - bd_id(b, 0);
-                if ((long long)e.x == EMPTY_KEY && idx < ID_OVERFLOW) {
-                  const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&ktab[sl].key),
-                                                           (unsigned long long)EMPTY_KEY, (unsigned long long)rec.key);
-                  if (old == (unsigned long long)EMPTY_KEY) *(volatile uint32_t*)&ktab[sl].idx = idx;
-                }
-                break;
-              }
-              sl = (sl + 1) & (BD_KS - 1);
-              e = *reinterpret_cast<const ulonglong2*>(ktab + sl);
+              if (e == (unsigned long long)EMPTY_KEY) break;
+              sl = (sl + 1) & (P2_HS - 1);
+            }
+            if (idx == ID_UNSET) {
+              // first sight in this block: global insert (race-free across blocks), then remember it here
+              const uint32_t id = bd_insert(p.dict, b, rec.key, bd_slot0(rec.key));
+              idx = id >= ID_OVERFLOW ? ID_OVERFLOW : id - bd_id(b, 0);
+              if (idx < ID_OVERFLOW) p2_insert(hk, hidx, rec.key, idx);
             }
           }
           if (NV > 0 && p.guard_vals && big_one(rec.val)) {

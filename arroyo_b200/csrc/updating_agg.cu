@@ -202,6 +202,11 @@ class UpdatingAggOp final : public OpBase {
     AB_CUDA(cudaStreamSynchronize(stream_));
   }
   void stats(ArroyoB200Stats* out) override {
+    if (keyed_) {
+      AB_CUDA(cudaSetDevice(device_));
+      AB_CUDA(cudaMemcpyAsync(&total_keys_, n_total_.p, 4, cudaMemcpyDeviceToHost, stream_));
+      AB_CUDA(cudaStreamSynchronize(stream_));
+    }
     st_.n_keys = keyed_ ? total_keys_ : 0;
     *out = st_;
   }
@@ -352,8 +357,8 @@ void UpdatingAggOp::alloc_state(uint64_t n_buckets) {
   id_cap_ = bd_id_cap(n_buckets_);
   AB_REQUIRE(id_cap_ < (1ull << 31), ARROYO_B200_RUNTIME, "key dictionary too large");
   id_keys_.alloc(id_cap_ * 8);
-  const long long k0 = EMPTY_KEY;
-  AB_CUDA(cudaMemcpyAsync(id_keys_.p, &k0, 8, cudaMemcpyHostToDevice, stream_));
+  bd_fill_keys_kernel<<<num_sms_ * 4, 256, 0, stream_>>>(id_keys_.as<long long>(), id_cap_);
+  AB_CUDA(cudaGetLastError());
   bucket_nkeys_.alloc(n_buckets_ * 4);
   AB_CUDA(cudaMemsetAsync(bucket_nkeys_.p, 0, n_buckets_ * 4, stream_));
   if (keyed_) {

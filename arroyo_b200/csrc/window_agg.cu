@@ -250,7 +250,7 @@ __device__ __noinline__ void slow_row(const IngestParams& p, long long key, long
   uint32_t id = 0;
   bool ok = ring_bin(p, slot) == (long long)(q * (uint64_t)p.slide);
   if (ok && p.keyed) {
-    const uint64_t h = mix64((uint64_t)key);
+    const uint64_t h = bd_hash(key);
     const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(bd_home(p.dict, key, h));
     const ulonglong2 raw = __ldcg(hp), raw1 = __ldcg(hp + 1);
     id = bd_resolve(p.dict, key, h, raw.x, (uint32_t)raw.y, raw1.x, (uint32_t)raw1.y);
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(THREADS, AB_INGEST_MIN_BLOCKS) ingest_kernel(c
 #pragma unroll
       for (int x = 0; x < (NV > 0 ? NV : 1); ++x) v[x] = nv[x];
       ulonglong2 raw = {0, 0}, raw1 = {0, 0};
-      const uint64_t h = keyed ? mix64((uint64_t)key) : 0ull;
+      const uint64_t h = keyed ? bd_hash(key) : 0ull;
       if (valid && keyed) {
         const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(bd_home(p.dict, key, h));
         raw = __ldcg(hp);
@@ -1262,8 +1262,8 @@ void WindowAggOp::alloc_dictionary(uint64_t n_buckets) {
   AB_REQUIRE(id_cap_ < (1ull << 31), ARROYO_B200_RUNTIME, "key dictionary too large");
   n_keys_host_ = (uint32_t)(BD_ID_BASE + n_buckets_ * BD_CAPB);
   id_keys_.alloc(id_cap_ * sizeof(long long));
-  long long k0 = EMPTY_KEY;
-  AB_CUDA(cudaMemcpyAsync(id_keys_.p, &k0, sizeof k0, cudaMemcpyHostToDevice, stream_));
+  bd_fill_keys_kernel<<<num_sms_ * 4, 256, 0, stream_>>>(id_keys_.as<long long>(), id_cap_);
+  AB_CUDA(cudaGetLastError());
   bucket_nkeys_.alloc(n_buckets_ * sizeof(unsigned int));
   AB_CUDA(cudaMemsetAsync(bucket_nkeys_.p, 0, n_buckets_ * sizeof(unsigned int), stream_));
   if (keyed_) {
