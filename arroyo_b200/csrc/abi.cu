@@ -101,6 +101,9 @@ int32_t arroyo_b200_op_create(const ArroyoB200OpConfig* config, ArroyoB200Op** o
       case ARROYO_B200_UPDATING_AGGREGATE:
         impl = make_updating_agg_op(*config);
         break;
+      case ARROYO_B200_TTL_JOIN:
+        impl = make_ttl_join_op(*config);
+        break;
       default:
         set_err(err, err_len, "unknown operator kind");
         return ARROYO_B200_INVALID_ARGUMENT;
@@ -158,6 +161,26 @@ int32_t arroyo_b200_op_process_batch(ArroyoB200Op* op, uint32_t input_index, uin
   if (!op) return ARROYO_B200_INVALID_ARGUMENT;
   WallTimer wt(op->host_process_ms);
   return guarded(op, [&](OpBase* o) { o->process_batch(input_index, in_partitions, batch, schema); });
+}
+
+int32_t arroyo_b200_op_process_batch_emit(ArroyoB200Op* op, uint32_t input_index, uint32_t in_partitions,
+                                          struct ArrowArray* batch, const struct ArrowSchema* schema, ArroyoB200Batches* out) {
+  if (out) memset(out, 0, sizeof *out);
+  if (!op) return ARROYO_B200_INVALID_ARGUMENT;
+  WallTimer wt(op->host_process_ms);
+  return guarded(op, [&](OpBase* o) {
+    AB_REQUIRE(out != nullptr, ARROYO_B200_INVALID_ARGUMENT, "null out");
+    auto* priv = new BatchesPriv();
+    try {
+      o->process_batch_emit(input_index, in_partitions, batch, schema, priv);
+    } catch (...) {
+      ArroyoB200Batches tmp{};
+      batches_finish(priv, &tmp);
+      batches_release(&tmp);
+      throw;
+    }
+    batches_finish(priv, out);
+  });
 }
 
 int32_t arroyo_b200_op_process_device_batch(ArroyoB200Op* op, uint32_t input_index, uint32_t in_partitions,

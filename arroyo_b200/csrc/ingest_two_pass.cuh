@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
   uint32_t* toff = hist + P1_NR;                                                 // [P1_NR] start of the bucket's run in `reorder`
   uint32_t* gdelta = toff + P1_NR;                                               // [P1_NR] region position - tile position
   __shared__ uint32_t s_wsum[P1_NWARP];
-  __shared__ unsigned long long s_tile_q, s_late, s_maxq;  // s_tile_q: pane of the tile being processed
+  __shared__ unsigned long long s_tile_q[2], s_late, s_maxq;  // s_tile_q[parity]: pane of the tile being processed
   __shared__ unsigned int s_done;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t NB = p.dict.n_buckets;
@@ -117,8 +117,14 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
     s_maxq = 0;
     s_done = 0;
   }
+  for (int i = tid; i < P1_NR; i += P1_THREADS) hist[i] = 0;
 
-  for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+  // Where tile `tile` lives: segment, offset, rows.
+  struct TileRef {
+    const long long *kcol, *tcol, *vcol;
+    int cnt;
+  };
+  auto locate = [&](long long tile) {
     int lo = 0, hi = p.n_segs - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
@@ -127,95 +133,106 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
     const Segment* sg = p.segs + lo;
     const long long base = (tile - __ldg(&sg->tile_start)) * P1_TILE;
     const long long nrem = __ldg(&sg->n) - base;
-    const int cnt = nrem < P1_TILE ? (int)nrem : P1_TILE;
-    const long long* kcol = ldg_ptr(&sg->key) + base;
-    const long long* tcol = ldg_ptr(&sg->ts) + base;
-    const long long* vcol = NV > 0 ? ldg_ptr(&sg->val[0]) + base : nullptr;
-
-    for (int i = tid; i < P1_NR; i += P1_THREADS) hist[i] = 0;
-    // The tile's pane = the pane of its first row.  Tiles are contiguous in arrival order, so all but the tiles at a
-    // pane boundary hold one pane; rows of any other pane (and every row of a tile whose first row is late) take the
-    // direct path below.
+    TileRef r;
+    r.cnt = nrem < P1_TILE ? (int)nrem : P1_TILE;
+    r.kcol = ldg_ptr(&sg->key) + base;
+    r.tcol = ldg_ptr(&sg->ts) + base;
+    r.vcol = NV > 0 ? ldg_ptr(&sg->val[0]) + base : nullptr;
+    return r;
+  };
+  // The load phase of a tile: every key and timestamp of the thread's rows is requested before anything depends on
+  // one.  It runs during the previous tile's write-out (whose registers are free by then): the kernel is bound by the
+  // latency of these loads, not by their bandwidth.  The tile's pane = the pane of its first row (tiles are contiguous
+  // in arrival order: all but the tiles at a pane boundary hold one pane).
+  long long k[P1_RPT], t[P1_RPT];
+  auto prefetch = [&](const TileRef& tr, int parity) {
+#pragma unroll
+    for (int j = 0; j < P1_RPT; ++j) {
+      const int i = j * P1_THREADS + tid;
+      k[j] = 0;
+      t[j] = -1;
+      if (i < tr.cnt) {
+        k[j] = __ldcs(tr.kcol + i);
+        t[j] = __ldcs(tr.tcol + i);
+      }
+    }
     if (tid == 0) {
-      const long long t0 = __ldg(tcol);
       uint64_t q0 = ~0ull;
-      if (t0 >= 0) {
-        q0 = sd.div((uint64_t)t0);
+      if (t[0] >= 0) {
+        q0 = sd.div((uint64_t)t[0]);
         if (q0 < p.late_q) q0 = ~0ull;
       }
-      s_tile_q = q0;
+      s_tile_q[parity] = q0;
     }
-    __syncthreads();
-    const uint64_t tq = s_tile_q;
+  };
+
+  long long tile = blockIdx.x;
+  TileRef cur{};
+  int parity = 0;
+  if (tile < p.n_tiles) {
+    cur = locate(tile);
+    prefetch(cur, parity);
+  }
+  __syncthreads();
+
+  for (; tile < p.n_tiles; tile += gridDim.x, parity ^= 1) {
+    const uint64_t tq = s_tile_q[parity];
     int psel = -1;
 #pragma unroll
     for (int f = 0; f < TP_NP; ++f)
       if (tq == tp.fast_q[f] && tq != ~0ull) psel = f;
     unsigned long long* fpane = psel >= 0 ? tp.fast_ptr[psel] : nullptr;
     const uint32_t fslot = psel >= 0 ? tp.fast_slot[psel] : 0u;
+    const int cnt = cur.cnt;
 
-    // ---- load phase: every key and timestamp of the thread's 16 rows is requested before anything depends on one
-    // (the kernel is bound by the latency of these loads: 32 independent 8-byte loads per thread in flight) ----
-    long long k[P1_RPT], v[P1_RPT];
+    // ---- window-assign (K1), late filter (K7); bucket + rank on the fast path, or the direct path right here ----
     uint32_t rr[P1_RPT];  // bucket | rank inside the tile's bucket << 16
-    {
-      long long t[P1_RPT];
 #pragma unroll
-      for (int j = 0; j < P1_RPT; ++j) {
-        const int i = j * P1_THREADS + tid;
-        k[j] = 0;
-        t[j] = -1;
-        if (i < cnt) {
-          k[j] = __ldcs(kcol + i);
-          t[j] = __ldcs(tcol + i);
-        }
-      }
-      // ---- window-assign (K1), late filter (K7); bucket + rank on the fast path, or the direct path right here ----
-#pragma unroll
-      for (int j = 0; j < P1_RPT; ++j) {
-        const int i = j * P1_THREADS + tid;
-        uint32_t r = NO_REGION;
-        if (i < cnt) {
-          if (t[j] < 0) {
-            atomicAdd(&p.counters->neg_ts, 1ull);  // pre-epoch: reported, never aggregated
+    for (int j = 0; j < P1_RPT; ++j) {
+      const int i = j * P1_THREADS + tid;
+      uint32_t r = NO_REGION;
+      if (i < cnt) {
+        if (t[j] < 0) {
+          atomicAdd(&p.counters->neg_ts, 1ull);  // pre-epoch: reported, never aggregated
+        } else {
+          const uint64_t q = sd.div((uint64_t)t[j]);
+          if (q < p.late_q) {
+            ++late;
           } else {
-            const uint64_t q = sd.div((uint64_t)t[j]);
-            if (q < p.late_q) {
-              ++late;
+            maxq = max(maxq, q);
+            if (q != tq || psel < 0) {
+              // another pane than the tile's (pane boundary, disorder) or no fast pane: the direct path does everything
+              slow_row<NV, SIG>(p, k[j], t[j], q, NV > 0 ? __ldcs(cur.vcol + i) : 0ll, 0, 0, 0);
+            } else if (k[j] == EMPTY_KEY) {
+              // the sentinel key owns id 0, outside every bucket
+              direct_rec<NV>(p, fpane, fslot, q, k[j], NV > 0 ? __ldcs(cur.vcol + i) : 0ll);
             } else {
-              maxq = max(maxq, q);
-              if (q != tq || psel < 0) {
-                // another pane than the tile's (pane boundary, disorder) or no fast pane: the direct path does everything
-                slow_row<NV, SIG>(p, k[j], t[j], q, NV > 0 ? __ldcs(vcol + i) : 0ll, 0, 0, 0);
-              } else if (k[j] == EMPTY_KEY) {
-                // the sentinel key owns id 0, outside every bucket
-                direct_rec<NV>(p, fpane, fslot, q, k[j], NV > 0 ? __ldcs(vcol + i) : 0ll);
-              } else {
-                r = bd_bucket(bd_hash(k[j]), NB);
-                r |= atomicAdd(&hist[r], 1u) << 16;
-              }
+              r = bd_bucket(bd_hash(k[j]), NB);
+              r |= atomicAdd(&hist[r], 1u) << 16;
             }
           }
         }
-        rr[j] = r;
       }
+      rr[j] = r;
     }
-    // the values: requested now, consumed after the scan (in flight across the barrier)
+    // the values: requested now, consumed after the scan (in flight across the barriers)
+    long long v[P1_RPT];
 #pragma unroll
     for (int j = 0; j < P1_RPT; ++j) {
       const int i = j * P1_THREADS + tid;
       v[j] = 0;
-      if (NV > 0 && (rr[j] & 0xFFFFu) != NO_REGION) v[j] = __ldcs(vcol + i);
+      if (NV > 0 && (rr[j] & 0xFFFFu) != NO_REGION) v[j] = __ldcs(cur.vcol + i);
     }
     __syncthreads();
 
-    // ---- exclusive scan of the bucket counts (thread t owns buckets bpt*t ...), one region reservation per bucket ----
-    constexpr int BPT = P1_NR / P1_THREADS;  // buckets per thread
+    // ---- exclusive scan of the bucket counts (thread t owns BPT consecutive buckets); the histogram is left zeroed ----
+    constexpr int BPT = P1_NR / P1_THREADS;
     uint32_t c[BPT];
     uint32_t tsum = 0;
 #pragma unroll
     for (int x = 0; x < BPT; ++x) {
       c[x] = hist[BPT * tid + x];
+      hist[BPT * tid + x] = 0;
       tsum += c[x];
     }
     uint32_t incl = tsum;
@@ -233,22 +250,28 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
       if (ww < w) wbase += x;
       n_on += x;
     }
+    const uint32_t ex0 = wbase + incl - tsum;
     {
-      uint32_t ex = wbase + incl - tsum;
+      uint32_t ex = ex0;
+#pragma unroll
+      for (int x = 0; x < BPT; ++x) {
+        toff[BPT * tid + x] = ex;
+        ex += c[x];
+      }
+    }
+    // one region reservation per bucket: the atomics' round trip is hidden behind the scatter below
+    uint32_t g[BPT];
+    {
       const uint32_t rbase = (uint32_t)max(psel, 0) * NB;
 #pragma unroll
       for (int x = 0; x < BPT; ++x) {
-        const uint32_t b = BPT * tid + x;
-        toff[b] = ex;
-        uint32_t g = 0;
-        if (c[x]) g = atomicAdd(tp.cursor + rbase + b, c[x]);
-        gdelta[b] = g - ex;
-        ex += c[x];
+        g[x] = 0;
+        if (c[x]) g[x] = atomicAdd(tp.cursor + rbase + BPT * tid + x, c[x]);
       }
     }
     __syncthreads();
 
-    // ---- stage in bucket order (write combining), then append every bucket's run to its region ----
+    // ---- stage in bucket order (write combining) ----
 #pragma unroll
     for (int j = 0; j < P1_RPT; ++j) {
       const uint32_t r = rr[j] & 0xFFFFu;
@@ -258,7 +281,24 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
         rid[pos] = (uint16_t)r;
       }
     }
+    {
+      uint32_t ex = ex0;
+#pragma unroll
+      for (int x = 0; x < BPT; ++x) {
+        gdelta[BPT * tid + x] = g[x] - ex;
+        ex += c[x];
+      }
+    }
+    // ---- the next tile's loads go out now: this tile's rows have left the registers ----
+    const long long next = tile + gridDim.x;
+    TileRef nxt{};
+    if (next < p.n_tiles) {
+      nxt = locate(next);
+      prefetch(nxt, parity ^ 1);
+    }
     __syncthreads();
+
+    // ---- append every bucket's run to its region ----
     if (n_on) {
       Rec* out = tp.part + (size_t)max(psel, 0) * NB * tp.cap;
       for (uint32_t i = tid; i < n_on; i += P1_THREADS) {
@@ -275,6 +315,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
         }
       }
     }
+    cur = nxt;
     __syncthreads();
   }
 

@@ -19,6 +19,11 @@ class OpBase {
   virtual ~OpBase() {}
   virtual void on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, int64_t watermark, int64_t table_min) = 0;
   virtual void process_batch(uint32_t index, uint32_t in_partitions, ArrowArray* batch, const ArrowSchema* schema) = 0;
+  // process_batch for operators that emit from it (the TTL join); everything else emits nothing here
+  virtual void process_batch_emit(uint32_t index, uint32_t in_partitions, ArrowArray* batch, const ArrowSchema* schema,
+                                  BatchesPriv* /*out*/) {
+    process_batch(index, in_partitions, batch, schema);
+  }
   virtual void process_device_batch(uint32_t index, uint32_t in_partitions, const uint64_t* cols, int32_t n_cols,
                                     int64_t n_rows) = 0;
   // exactly one of out_host / out_dev is non-null
@@ -42,5 +47,6 @@ OpBase* make_window_agg_op(const ArroyoB200OpConfig& cfg);
 OpBase* make_instant_join_op(const ArroyoB200OpConfig& cfg);
 OpBase* make_session_op(const ArroyoB200OpConfig& cfg);
 OpBase* make_updating_agg_op(const ArroyoB200OpConfig& cfg);
+OpBase* make_ttl_join_op(const ArroyoB200OpConfig& cfg);
 
 }  // namespace ab

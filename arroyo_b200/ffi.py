@@ -12,7 +12,7 @@ MAX_AGGS = 8
 MAX_COLS = 16
 
 OK, INVALID_ARGUMENT, UNSUPPORTED, RUNTIME, FATAL, PANIC = 0, 1, 2, 3, 4, 5
-TUMBLING_AGGREGATE, SLIDING_AGGREGATE, SESSION_AGGREGATE, INSTANT_JOIN, UPDATING_AGGREGATE = 1, 2, 3, 4, 5
+TUMBLING_AGGREGATE, SLIDING_AGGREGATE, SESSION_AGGREGATE, INSTANT_JOIN, UPDATING_AGGREGATE, TTL_JOIN = 1, 2, 3, 4, 5, 6
 AGG_COUNT_STAR, AGG_SUM_I64, AGG_AVG_I64, AGG_MIN_I64, AGG_MAX_I64 = 1, 2, 3, 4, 5
 JOIN_INNER, JOIN_LEFT, JOIN_RIGHT, JOIN_FULL = 0, 1, 2, 3
 FLAG_PROFILE, FLAG_REMERGE_ONLY, FLAG_COMBINE, FLAG_AVG_F64, FLAG_NO_COMBINE, FLAG_ZERO_COPY = 1, 2, 4, 8, 16, 32
@@ -119,6 +119,8 @@ SYMBOLS = [
     ("arroyo_b200_op_handle_checkpoint", C.c_int32, [_VP, C.c_int64, C.POINTER(Batches)]),
     ("arroyo_b200_op_on_close", C.c_int32, [_VP, C.c_int32, C.POINTER(Batches)]),
     ("arroyo_b200_op_handle_tick", C.c_int32, [_VP, C.POINTER(Batches)]),
+    ("arroyo_b200_op_process_batch_emit", C.c_int32, [_VP, C.c_uint32, C.c_uint32, C.POINTER(ArrowArray), C.POINTER(ArrowSchema),
+                                                      C.POINTER(Batches)]),
     ("arroyo_b200_op_flush", C.c_int32, [_VP]),
     ("arroyo_b200_op_submit", C.c_int32, [_VP]),
     ("arroyo_b200_release_batches", None, [C.POINTER(Batches)]),

@@ -696,3 +696,54 @@ class InstantJoin(_NativeOperator):
         for b in import_batches(self._lib, out):
             collector.collect(pa.RecordBatch.from_arrays(b.columns, names=names))
         return wm
+
+
+class JoinWithExpiration(InstantJoin):
+    """arroyo-worker/src/arrow/join_with_expiration.rs: the non-windowed join (inner, append-only inputs).  Every
+    matching pair leaves once, from the `process_batch_index` call that brings its later row (:42-108)."""
+    kind = ffi.TTL_JOIN
+
+    def name(self):
+        return "JoinWithExpiration"
+
+    def tables(self):
+        return {"left": 0, "right": 0}  # key-time tables with retention = ttl (:228-262); restore is a replay
+
+    def on_start(self, ctx: OperatorContext):
+        raise ffi.UnsupportedPlan(ffi.UNSUPPORTED, "JoinWithExpiration restore: replay the key-time tables through process_batch_index")
+
+    def handle_checkpoint(self, barrier, ctx: OperatorContext, collector: Collector):
+        return
+
+    def _send(self, index, parts, batch, collector=None):
+        arr, sch = export_batch(batch)
+        out = ffi.Batches()
+        st = self._lib.arroyo_b200_op_process_batch_emit(self._h, index, parts, C.byref(arr), C.byref(sch), C.byref(out))
+        if st != ffi.OK and arr.release:
+            C.CFUNCTYPE(None, C.c_void_p)(arr.release)(C.addressof(arr))
+        if sch.release:
+            C.CFUNCTYPE(None, C.c_void_p)(sch.release)(C.addressof(sch))
+        _check(self._lib, self._h, st)
+        names = self.output_names()
+        for b in import_batches(self._lib, out):
+            if collector is not None:
+                collector.collect(pa.RecordBatch.from_arrays(b.columns, names=names))
+
+    def process_batch_index(self, index: int, in_partitions: int, batch: pa.RecordBatch, ctx: OperatorContext,
+                            collector: Collector):
+        side = index // (in_partitions // 2)
+        if self._schemas[side] is None:
+            self._schemas[side] = batch.schema
+        if not self.created:
+            if self._schemas[0] is not None and self._schemas[1] is not None:
+                self._build()
+                pending, self._buffered = self._buffered, []
+                for i, parts, b in pending:
+                    self._send(i, parts, b, collector)
+            else:
+                self._buffered.append((index, in_partitions, batch))
+                return
+        self._send(index, in_partitions, batch, collector)
+
+    def handle_watermark(self, watermark, ctx: OperatorContext, collector: Collector):
+        return watermark

@@ -90,10 +90,13 @@ typedef enum ArroyoB200OpKind {
   ARROYO_B200_SLIDING_AGGREGATE = 2,  /* OperatorName::SlidingWindowAggregate  */
   ARROYO_B200_SESSION_AGGREGATE = 3,  /* OperatorName::SessionWindowAggregate  */
   ARROYO_B200_INSTANT_JOIN = 4,       /* OperatorName::InstantJoin             */
-  ARROYO_B200_UPDATING_AGGREGATE = 5  /* OperatorName::UpdatingAggregate: IncrementalAggregatingFunc,
+  ARROYO_B200_UPDATING_AGGREGATE = 5, /* OperatorName::UpdatingAggregate: IncrementalAggregatingFunc,
                                        * arroyo-worker/src/arrow/incremental_aggregator.rs (append-only inputs;
                                        * COUNT(*) / SUM / AVG / MIN / MAX over Int64; emits on ticks, checkpoints and
                                        * end of data: rows [key?, aggregates..., _timestamp, is_retract bool])      */
+  ARROYO_B200_TTL_JOIN = 6            /* OperatorName::Join: JoinWithExpiration, arroyo-worker/src/arrow/
+                                       * join_with_expiration.rs (inner joins of append-only inputs; same column fields as
+                                       * INSTANT_JOIN; matches leave from arroyo_b200_op_process_batch_emit)            */
 } ArroyoB200OpKind;
 
 typedef enum ArroyoB200AggKind {
@@ -280,6 +283,12 @@ int32_t arroyo_b200_op_on_start(ArroyoB200Op* op, struct ArrowArray* state, stru
  * instant_join :109-172), so there is no collector argument. */
 int32_t arroyo_b200_op_process_batch(ArroyoB200Op* op, uint32_t input_index, uint32_t in_partitions,
                                      struct ArrowArray* batch, const struct ArrowSchema* schema);
+
+/* process_batch_index for operators that emit from it (operator.rs:1174-1188 hands them the collector): the TTL join
+ * emits the pairs an arriving batch completes (join_with_expiration.rs:42-130).  For every other operator this is
+ * arroyo_b200_op_process_batch with an empty `out`. */
+int32_t arroyo_b200_op_process_batch_emit(ArroyoB200Op* op, uint32_t input_index, uint32_t in_partitions,
+                                          struct ArrowArray* batch, const struct ArrowSchema* schema, ArroyoB200Batches* out);
 
 /* Same, for a batch already resident on the operator's device: `cols[i]` are device pointers
  * to n_rows 64-bit values each.  The buffers must stay valid until the next call that
