@@ -491,17 +491,19 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
           uint32_t g = p2_group(rec.key);
           int pos = -1;
           {
+            // Groups are 64-byte aligned: if every lane read chunk j of its group with the j-th load, the 32 addresses
+            // of one instruction would fall into two of the eight 16-byte bank groups (16-way conflicts: measured,
+            // profiles/r02_two_pass_e).  Each lane therefore starts at a different chunk of its group.
             const ulonglong2* kp = reinterpret_cast<const ulonglong2*>(hk + g);
-            const ulonglong2 a = kp[0], bq = kp[1], c = kp[2], d = kp[3];
             const unsigned long long key = (unsigned long long)rec.key;
-            pos = a.x == key ? 0 : pos;
-            pos = a.y == key ? 1 : pos;
-            pos = bq.x == key ? 2 : pos;
-            pos = bq.y == key ? 3 : pos;
-            pos = c.x == key ? 4 : pos;
-            pos = c.y == key ? 5 : pos;
-            pos = d.x == key ? 6 : pos;
-            pos = d.y == key ? 7 : pos;
+            const int rot = lane & 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c = (j + rot) & 3;
+              const ulonglong2 e = kp[c];
+              pos = e.x == key ? 2 * c : pos;
+              pos = e.y == key ? 2 * c + 1 : pos;
+            }
           }
           uint32_t idx = pos >= 0 ? (uint32_t)hidx[g + pos] : 0xFFFFu;
           if (idx == 0xFFFFu) {
