@@ -65,8 +65,8 @@ struct TwoPassParams {
 };
 
 constexpr size_t P1_SMEM = (size_t)P1_TILE * 16 + (size_t)P1_TILE * 2 + (size_t)P1_NR * 12;
-constexpr size_t P2_SMEM = (size_t)4096 * 10 + (size_t)BD_CAPB * 12 + (size_t)P2_NW * P2_NST * P2_CH * 16 +
-                           (size_t)(P2_NW * P2_NST + 1) * 8;  // 4096 = P2_HS (lookup table: 8-byte keys + 2-byte indices)
+constexpr size_t P2_SMEM = (size_t)4096 * 12 + (size_t)BD_CAPB * 12 + (size_t)P2_NW * P2_NST * P2_CH * 16 +
+                           (size_t)(P2_NW * P2_NST + 1) * 8;  // 4096 = P2_HS (lookup table: key 8 + tag 2 + index 2 bytes per slot)
 
 // A row that left the fast path after window assignment: accumulate it directly (global lookup + REDs).  `q` is its
 // pane number; the pane block is `pane`, its ring slot `slot`.  Rows that cannot get an id are deferred with the pane's
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
   uint32_t* toff = hist + P1_NR;                                                 // [P1_NR] start of the bucket's run in `reorder`
   uint32_t* gdelta = toff + P1_NR;                                               // [P1_NR] region position - tile position
   __shared__ uint32_t s_wsum[P1_NWARP];
-  __shared__ unsigned long long s_tile_q[2], s_late, s_maxq;  // s_tile_q[parity]: pane of the tile being processed
+  __shared__ unsigned long long s_tile_q, s_late, s_maxq;  // s_tile_q: pane of the tile being processed
   __shared__ unsigned int s_done;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t NB = p.dict.n_buckets;
@@ -117,14 +117,8 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
     s_maxq = 0;
     s_done = 0;
   }
-  for (int i = tid; i < P1_NR; i += P1_THREADS) hist[i] = 0;
 
-  // Where tile `tile` lives: segment, offset, rows.
-  struct TileRef {
-    const long long *kcol, *tcol, *vcol;
-    int cnt;
-  };
-  auto locate = [&](long long tile) {
+  for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     int lo = 0, hi = p.n_segs - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
@@ -133,106 +127,95 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
     const Segment* sg = p.segs + lo;
     const long long base = (tile - __ldg(&sg->tile_start)) * P1_TILE;
     const long long nrem = __ldg(&sg->n) - base;
-    TileRef r;
-    r.cnt = nrem < P1_TILE ? (int)nrem : P1_TILE;
-    r.kcol = ldg_ptr(&sg->key) + base;
-    r.tcol = ldg_ptr(&sg->ts) + base;
-    r.vcol = NV > 0 ? ldg_ptr(&sg->val[0]) + base : nullptr;
-    return r;
-  };
-  // The load phase of a tile: every key and timestamp of the thread's rows is requested before anything depends on
-  // one.  It runs during the previous tile's write-out (whose registers are free by then): the kernel is bound by the
-  // latency of these loads, not by their bandwidth.  The tile's pane = the pane of its first row (tiles are contiguous
-  // in arrival order: all but the tiles at a pane boundary hold one pane).
-  long long k[P1_RPT], t[P1_RPT];
-  auto prefetch = [&](const TileRef& tr, int parity) {
-#pragma unroll
-    for (int j = 0; j < P1_RPT; ++j) {
-      const int i = j * P1_THREADS + tid;
-      k[j] = 0;
-      t[j] = -1;
-      if (i < tr.cnt) {
-        k[j] = __ldcs(tr.kcol + i);
-        t[j] = __ldcs(tr.tcol + i);
-      }
-    }
+    const int cnt = nrem < P1_TILE ? (int)nrem : P1_TILE;
+    const long long* kcol = ldg_ptr(&sg->key) + base;
+    const long long* tcol = ldg_ptr(&sg->ts) + base;
+    const long long* vcol = NV > 0 ? ldg_ptr(&sg->val[0]) + base : nullptr;
+
+    for (int i = tid; i < P1_NR; i += P1_THREADS) hist[i] = 0;
+    // The tile's pane = the pane of its first row.  Tiles are contiguous in arrival order, so all but the tiles at a
+    // pane boundary hold one pane; rows of any other pane (and every row of a tile whose first row is late) take the
+    // direct path below.
     if (tid == 0) {
+      const long long t0 = __ldg(tcol);
       uint64_t q0 = ~0ull;
-      if (t[0] >= 0) {
-        q0 = sd.div((uint64_t)t[0]);
+      if (t0 >= 0) {
+        q0 = sd.div((uint64_t)t0);
         if (q0 < p.late_q) q0 = ~0ull;
       }
-      s_tile_q[parity] = q0;
+      s_tile_q = q0;
     }
-  };
-
-  long long tile = blockIdx.x;
-  TileRef cur{};
-  int parity = 0;
-  if (tile < p.n_tiles) {
-    cur = locate(tile);
-    prefetch(cur, parity);
-  }
-  __syncthreads();
-
-  for (; tile < p.n_tiles; tile += gridDim.x, parity ^= 1) {
-    const uint64_t tq = s_tile_q[parity];
+    __syncthreads();
+    const uint64_t tq = s_tile_q;
     int psel = -1;
 #pragma unroll
     for (int f = 0; f < TP_NP; ++f)
       if (tq == tp.fast_q[f] && tq != ~0ull) psel = f;
     unsigned long long* fpane = psel >= 0 ? tp.fast_ptr[psel] : nullptr;
     const uint32_t fslot = psel >= 0 ? tp.fast_slot[psel] : 0u;
-    const int cnt = cur.cnt;
 
-    // ---- window-assign (K1), late filter (K7); bucket + rank on the fast path, or the direct path right here ----
+    // ---- load phase: every key and timestamp of the thread's 16 rows is requested before anything depends on one
+    // (the kernel is bound by the latency of these loads: 32 independent 8-byte loads per thread in flight) ----
+    long long k[P1_RPT], v[P1_RPT];
     uint32_t rr[P1_RPT];  // bucket | rank inside the tile's bucket << 16
+    {
+      long long t[P1_RPT];
 #pragma unroll
-    for (int j = 0; j < P1_RPT; ++j) {
-      const int i = j * P1_THREADS + tid;
-      uint32_t r = NO_REGION;
-      if (i < cnt) {
-        if (t[j] < 0) {
-          atomicAdd(&p.counters->neg_ts, 1ull);  // pre-epoch: reported, never aggregated
-        } else {
-          const uint64_t q = sd.div((uint64_t)t[j]);
-          if (q < p.late_q) {
-            ++late;
+      for (int j = 0; j < P1_RPT; ++j) {
+        const int i = j * P1_THREADS + tid;
+        k[j] = 0;
+        t[j] = -1;
+        if (i < cnt) {
+          k[j] = __ldcs(kcol + i);
+          t[j] = __ldcs(tcol + i);
+        }
+      }
+      // ---- window-assign (K1), late filter (K7); bucket + rank on the fast path, or the direct path right here ----
+#pragma unroll
+      for (int j = 0; j < P1_RPT; ++j) {
+        const int i = j * P1_THREADS + tid;
+        uint32_t r = NO_REGION;
+        if (i < cnt) {
+          if (t[j] < 0) {
+            atomicAdd(&p.counters->neg_ts, 1ull);  // pre-epoch: reported, never aggregated
           } else {
-            maxq = max(maxq, q);
-            if (q != tq || psel < 0) {
-              // another pane than the tile's (pane boundary, disorder) or no fast pane: the direct path does everything
-              slow_row<NV, SIG>(p, k[j], t[j], q, NV > 0 ? __ldcs(cur.vcol + i) : 0ll, 0, 0, 0);
-            } else if (k[j] == EMPTY_KEY) {
-              // the sentinel key owns id 0, outside every bucket
-              direct_rec<NV>(p, fpane, fslot, q, k[j], NV > 0 ? __ldcs(cur.vcol + i) : 0ll);
+            const uint64_t q = sd.div((uint64_t)t[j]);
+            if (q < p.late_q) {
+              ++late;
             } else {
-              r = bd_bucket(bd_hash(k[j]), NB);
-              r |= atomicAdd(&hist[r], 1u) << 16;
+              maxq = max(maxq, q);
+              if (q != tq || psel < 0) {
+                // another pane than the tile's (pane boundary, disorder) or no fast pane: the direct path does everything
+                slow_row<NV, SIG>(p, k[j], t[j], q, NV > 0 ? __ldcs(vcol + i) : 0ll, 0, 0, 0);
+              } else if (k[j] == EMPTY_KEY) {
+                // the sentinel key owns id 0, outside every bucket
+                direct_rec<NV>(p, fpane, fslot, q, k[j], NV > 0 ? __ldcs(vcol + i) : 0ll);
+              } else {
+                r = bd_bucket(bd_hash(k[j]), NB);
+                r |= atomicAdd(&hist[r], 1u) << 16;
+              }
             }
           }
         }
+        rr[j] = r;
       }
-      rr[j] = r;
     }
-    // the values: requested now, consumed after the scan (in flight across the barriers)
-    long long v[P1_RPT];
+    // the values: requested now, consumed after the scan (in flight across the barrier)
 #pragma unroll
     for (int j = 0; j < P1_RPT; ++j) {
       const int i = j * P1_THREADS + tid;
       v[j] = 0;
-      if (NV > 0 && (rr[j] & 0xFFFFu) != NO_REGION) v[j] = __ldcs(cur.vcol + i);
+      if (NV > 0 && (rr[j] & 0xFFFFu) != NO_REGION) v[j] = __ldcs(vcol + i);
     }
     __syncthreads();
 
-    // ---- exclusive scan of the bucket counts (thread t owns BPT consecutive buckets); the histogram is left zeroed ----
-    constexpr int BPT = P1_NR / P1_THREADS;
+    // ---- exclusive scan of the bucket counts (thread t owns buckets bpt*t ...), one region reservation per bucket ----
+    constexpr int BPT = P1_NR / P1_THREADS;  // buckets per thread
     uint32_t c[BPT];
     uint32_t tsum = 0;
 #pragma unroll
     for (int x = 0; x < BPT; ++x) {
       c[x] = hist[BPT * tid + x];
-      hist[BPT * tid + x] = 0;
       tsum += c[x];
     }
     uint32_t incl = tsum;
@@ -251,27 +234,22 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
       n_on += x;
     }
     const uint32_t ex0 = wbase + incl - tsum;
+    uint32_t g[BPT];  // one region reservation per bucket: the atomics' round trip is hidden behind the scatter below
     {
       uint32_t ex = ex0;
-#pragma unroll
-      for (int x = 0; x < BPT; ++x) {
-        toff[BPT * tid + x] = ex;
-        ex += c[x];
-      }
-    }
-    // one region reservation per bucket: the atomics' round trip is hidden behind the scatter below
-    uint32_t g[BPT];
-    {
       const uint32_t rbase = (uint32_t)max(psel, 0) * NB;
 #pragma unroll
       for (int x = 0; x < BPT; ++x) {
+        const uint32_t b = BPT * tid + x;
+        toff[b] = ex;
         g[x] = 0;
-        if (c[x]) g[x] = atomicAdd(tp.cursor + rbase + BPT * tid + x, c[x]);
+        if (c[x]) g[x] = atomicAdd(tp.cursor + rbase + b, c[x]);
+        ex += c[x];
       }
     }
     __syncthreads();
 
-    // ---- stage in bucket order (write combining) ----
+    // ---- stage in bucket order (write combining), then append every bucket's run to its region ----
 #pragma unroll
     for (int j = 0; j < P1_RPT; ++j) {
       const uint32_t r = rr[j] & 0xFFFFu;
@@ -289,16 +267,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
         ex += c[x];
       }
     }
-    // ---- the next tile's loads go out now: this tile's rows have left the registers ----
-    const long long next = tile + gridDim.x;
-    TileRef nxt{};
-    if (next < p.n_tiles) {
-      nxt = locate(next);
-      prefetch(nxt, parity ^ 1);
-    }
     __syncthreads();
-
-    // ---- append every bucket's run to its region ----
     if (n_on) {
       Rec* out = tp.part + (size_t)max(psel, 0) * NB * tp.cap;
       for (uint32_t i = tid; i < n_on; i += P1_THREADS) {
@@ -315,7 +284,6 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
         }
       }
     }
-    cur = nxt;
     __syncthreads();
   }
 
@@ -376,29 +344,39 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 // One block per (pane, bucket[, slice]).
 //
-// The block builds its own lookup table of the bucket's keys in shared memory: P2_HS key slots in groups of eight
-// (one 64-byte line), filled from the bucket's id range of `id_keys` (8 KB for a full bucket; the dictionary's own
-// 32 KB slice is not read).  At a quarter load a group overflows once in ten thousand keys, so a row's lookup is four
-// LDS.128 and eight compares, straight-line: with a probe LOOP, every warp has some lane that needs another round, and
-// the loop was three quarters of the kernel's instructions (profiles/r02_two_pass_c / _d).
+// The block builds its own lookup table of the bucket's keys in shared memory, from the bucket's id range of
+// `id_keys` (8 KB for a full bucket; the dictionary's own 32 KB slice is not read): P2_HS slots in groups of eight, and
+// per slot a 16-bit TAG (hash bits of the key), the key itself and its index inside the bucket.  A row's lookup is ONE
+// 16-byte load (the eight tags of its home group), a SIMD compare, and -- for the slot whose tag matches -- one 8-byte
+// load to confirm the key and one 2-byte load for the index: straight-line, ~25 instructions.  (With a probe loop every
+// warp has some lane that needs another round -- it was three quarters of the kernel's instructions -- and comparing
+// eight full keys costs four 16-byte loads and sixteen compares per row: profiles/r02_two_pass_c .. _f.)  At a
+// quarter load a group overflows once in ten thousand keys; those and first sightings take the slow path.
 // The bucket's accumulators live once in shared memory and take shared-memory atomics (ATOMS.ADD.32: ~3.5 SM-cycles
 // per warp instruction on spread addresses, duplicates inside a warp included).  The 64-bit wrapping SUM is two 32-bit
 // words: the low word takes every row's low half (the returned old value tells whether it wrapped), the high word the
 // high half plus that carry -- for the small positive values of a bid stream the second atomic is rare.
 // Records arrive through per-warp TMA rings (cp.async.bulk + mbarrier).
-constexpr int P2_HS = 4096;  // key slots of the block's lookup table
-constexpr int P2_HG = 8;     // slots per group
-__device__ __forceinline__ uint32_t p2_group(long long key) {
-  return (uint32_t)(((uint64_t)key * 0xD6E8FEB86659FD93ull) >> 55) * P2_HG;  // P2_HS / P2_HG = 512 groups
+constexpr int P2_HS = 4096;  // slots of the block's lookup table
+constexpr int P2_HG = 8;     // slots per group (their tags = one 16-byte load)
+__device__ __forceinline__ uint32_t p2_hash(long long key) { return (uint32_t)(((uint64_t)key * 0xD6E8FEB86659FD93ull) >> 32); }
+__device__ __forceinline__ uint32_t p2_group(uint32_t h) { return (h >> 23) * P2_HG; }  // top 9 bits: 512 groups
+__device__ __forceinline__ uint32_t p2_tag(uint32_t h) {                               // 16 other bits; 0 = empty slot
+  const uint32_t t = (h >> 4) & 0xFFFFu;
+  return t ? t : 1u;
 }
 
-// Inserts `key -> idx` into the block's table (home group first, then the following groups).
-__device__ __forceinline__ void p2_insert(unsigned long long* hk, unsigned short* hidx, long long key, uint32_t idx) {
-  uint32_t s = p2_group(key);
+// Inserts `key -> idx` into the block's table (home group first, then the following slots).
+__device__ __forceinline__ void p2_insert(unsigned long long* hk, unsigned short* htag, unsigned short* hidx, long long key,
+                                          uint32_t idx) {
+  const uint32_t h = p2_hash(key);
+  uint32_t s = p2_group(h);
   for (int probe = 0; probe < P2_HS; ++probe) {
     const unsigned long long old = atomicCAS(&hk[s], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
     if (old == (unsigned long long)EMPTY_KEY || old == (unsigned long long)key) {
       hidx[s] = (unsigned short)idx;
+      __threadfence_block();
+      htag[s] = (unsigned short)p2_tag(h);  // published last: a lookup that matches the tag finds key and index in place
       return;
     }
     s = (s + 1) & (P2_HS - 1);
@@ -410,7 +388,8 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
                                                                            const __grid_constant__ TwoPassParams tp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned long long* hk = reinterpret_cast<unsigned long long*>(smem_raw);             // [P2_HS] keys
-  unsigned short* hidx = reinterpret_cast<unsigned short*>(hk + P2_HS);                 // [P2_HS] index inside the bucket
+  unsigned short* htag = reinterpret_cast<unsigned short*>(hk + P2_HS);                 // [P2_HS] tags
+  unsigned short* hidx = htag + P2_HS;                                                  // [P2_HS] index inside the bucket
   uint32_t* scnt = reinterpret_cast<uint32_t*>(hidx + P2_HS);                           // [BD_CAPB] rows
   uint32_t* slo = scnt + BD_CAPB;                                                      // [BD_CAPB] sum, low word
   uint32_t* shi = slo + BD_CAPB;                                                       // [BD_CAPB] sum, high word
@@ -428,6 +407,7 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
   if (tid == 0) s_rows = 0;
   __syncthreads();
   uint32_t phase = 0;  // bit s = parity of this warp's stage s
+  const bool guard = NV > 0 && p.guard_vals != 0;
 
   const uint32_t n_work = TP_NP * NB * tp.slices;
   for (uint32_t work = blockIdx.x; work < n_work; work += gridDim.x) {
@@ -463,15 +443,14 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
     // ---- build the bucket's lookup table ----
     for (int i = tid; i < P2_HS / 2; i += P2_NW * 32)
       reinterpret_cast<ulonglong2*>(hk)[i] = make_ulonglong2((unsigned long long)EMPTY_KEY, (unsigned long long)EMPTY_KEY);
-    // 0xFFFF = "key claimed, index not published yet": a lookup that sees it takes the insert path and waits there
-    for (int i = tid; i < P2_HS / 8; i += P2_NW * 32) reinterpret_cast<uint4*>(hidx)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    for (int i = tid; i < P2_HS / 8; i += P2_NW * 32) reinterpret_cast<uint4*>(htag)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     {
       const unsigned nk = min(*(volatile const unsigned*)(p.dict.nkeys + b), (unsigned)BD_CAPB);
       const long long* bkeys = p.dict.id_keys + bd_id(b, 0);
       for (unsigned i = tid; i < nk; i += P2_NW * 32) {
         const long long key = __ldcg(bkeys + i);
-        if (key != EMPTY_KEY) p2_insert(hk, hidx, key, i);  // EMPTY: an insert that has not published its key yet
+        if (key != EMPTY_KEY) p2_insert(hk, htag, hidx, key, i);  // EMPTY: an insert that has not published its key yet
       }
     }
     __syncthreads();
@@ -488,35 +467,34 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
         const unsigned ri = sub * 32 + lane;
         if (ri < nr) {
           const Rec rec = chunk[ri];
-          uint32_t g = p2_group(rec.key);
-          int pos = -1;
-          {
-            // Groups are 64-byte aligned: if every lane read chunk j of its group with the j-th load, the 32 addresses
-            // of one instruction would fall into two of the eight 16-byte bank groups (16-way conflicts: measured,
-            // profiles/r02_two_pass_e).  Each lane therefore starts at a different chunk of its group.
-            const ulonglong2* kp = reinterpret_cast<const ulonglong2*>(hk + g);
-            const unsigned long long key = (unsigned long long)rec.key;
-            const int rot = lane & 3;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int c = (j + rot) & 3;
-              const ulonglong2 e = kp[c];
-              pos = e.x == key ? 2 * c : pos;
-              pos = e.y == key ? 2 * c + 1 : pos;
+          const uint32_t h = p2_hash(rec.key);
+          const uint32_t g = p2_group(h);
+          const uint32_t tag2 = p2_tag(h) * 0x10001u;  // the tag in both halves
+          // the eight tags of the home group: one 16-byte load, four 2 x 16-bit compares
+          const uint4 tg = *reinterpret_cast<const uint4*>(htag + g);
+          uint32_t m = (__vcmpeq2(tg.x, tag2) & 0x00010100u) | ((__vcmpeq2(tg.y, tag2) & 0x00010100u) << 2) |
+                       ((__vcmpeq2(tg.z, tag2) & 0x00010100u) << 4) | ((__vcmpeq2(tg.w, tag2) & 0x00010100u) << 6);
+          // bit 8 + 2j: low half of word j matches (slot 2j); bit 16 + 2j: high half (slot 2j + 1)
+          uint32_t idx = ID_UNSET;
+          while (m) {  // almost always one candidate; a second one is a 16-bit tag collision inside the group
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            const int slot = bit >= 16 ? 2 * ((bit - 16) >> 1) + 1 : 2 * ((bit - 8) >> 1);
+            if (hk[g + slot] == (unsigned long long)rec.key) {
+              idx = hidx[g + slot];
+              break;
             }
           }
-          uint32_t idx = pos >= 0 ? (uint32_t)hidx[g + pos] : 0xFFFFu;
-          if (idx == 0xFFFFu) {
-            // not in the home group: it spilled into the following groups, or the block has not seen the key yet
-            idx = ID_UNSET;
+          if (idx == ID_UNSET) {
+            // not in the home group: it spilled into the following slots, or the block has not seen the key yet
+            bool full = true;  // only a group without an empty slot can have spilled
+            for (int x = 0; x < P2_HG; ++x) full = full && htag[g + x] != 0;
             uint32_t sl = (g + P2_HG) & (P2_HS - 1);
-            bool full = true;  // the home group holds no empty slot <=> the key may have spilled
-            for (int x = 0; x < P2_HG; ++x) full = full && hk[g + x] != (unsigned long long)EMPTY_KEY;
 #pragma unroll 1
             for (int probe = 0; full && probe < P2_HS; ++probe) {
               const unsigned long long e = hk[sl];
-              if (e == (unsigned long long)rec.key) {
-                idx = hidx[sl] == 0xFFFFu ? ID_UNSET : (uint32_t)hidx[sl];
+              if (e == (unsigned long long)rec.key && htag[sl] != 0) {
+                idx = hidx[sl];
                 break;
               }
               if (e == (unsigned long long)EMPTY_KEY) break;
@@ -526,10 +504,10 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
               // first sight in this block: global insert (race-free across blocks), then remember it here
               const uint32_t id = bd_insert(p.dict, b, rec.key, bd_slot0(rec.key));
               idx = id >= ID_OVERFLOW ? ID_OVERFLOW : id - bd_id(b, 0);
-              if (idx < ID_OVERFLOW) p2_insert(hk, hidx, rec.key, idx);
+              if (idx < ID_OVERFLOW) p2_insert(hk, htag, hidx, rec.key, idx);
             }
           }
-          if (NV > 0 && p.guard_vals && big_one(rec.val)) {
+          if (guard && big_one(rec.val)) {
             // exact-AVG guard (the partition pass does not look at values): park the row for the host's promotion
             atomicAdd(&p.counters->big_vals, 1ull);
             defer_row(p, rec.key, (long long)(q * (uint64_t)p.slide), rec.val, 0, 0, 0);

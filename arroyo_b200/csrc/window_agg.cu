@@ -945,7 +945,7 @@ class WindowAggOp final : public OpBase {
   // staging
   static constexpr int NCHUNK = 3;
   static constexpr int NLAUNCH = 3;
-  int64_t chunk_rows_ = 1 << 23;
+  int64_t chunk_rows_ = 1 << 24;  // rows per ingest launch: one headline pane; fixed per-launch costs (table builds, tails) halve vs 2^23
   DevBuf chunk_[NCHUNK];
   cudaEvent_t chunk_free_[NCHUNK] = {nullptr, nullptr, nullptr};
   // host batches are staged by the copy engine on their own stream, so the link never waits for an ingest kernel:
