@@ -90,6 +90,25 @@ __device__ __noinline__ void direct_rec(const IngestParams& p, unsigned long lon
   if (NV > 0) red_add_u64(pane + p.id_cap + id, (unsigned long long)val);
 }
 
+// Everything the partition kernel does not keep on its fast path, out of line: pre-epoch timestamps, late rows, rows of
+// another pane than the tile's (pane boundary, disorder, no fast pane at all), the sentinel key.
+template <int NV, int SIG>
+__device__ __noinline__ void off_path_row(const IngestParams& p, long long key, long long ts, long long val, uint64_t tile_q,
+                                          unsigned long long* fpane, uint32_t fslot, uint32_t& late, uint64_t& maxq) {
+  if (ts < 0) {
+    atomicAdd(&p.counters->neg_ts, 1ull);  // pre-epoch: reported, never aggregated
+    return;
+  }
+  const uint64_t q = p.slide_div.div((uint64_t)ts);
+  if (q < p.late_q) {
+    ++late;
+    return;
+  }
+  maxq = max(maxq, q);
+  if (q == tile_q) direct_rec<NV>(p, fpane, fslot, q, key, val);  // the sentinel key: id 0, outside every bucket
+  else slow_row<NV, SIG>(p, key, ts, q, val, 0, 0, 0);            // the one-pass path does everything
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // pass 1
 // ---------------------------------------------------------------------------------------------------------------
@@ -170,35 +189,25 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
           t[j] = __ldcs(tcol + i);
         }
       }
-      // ---- window-assign (K1), late filter (K7); bucket + rank on the fast path, or the direct path right here ----
+      // ---- window-assign (K1) + late filter (K7) as ONE range test against the tile's pane: a row is on the fast
+      // path iff its timestamp lies in [pane start, pane start + slide) -- that excludes late rows (the tile's pane
+      // is not late), pre-epoch rows and rows of other panes, which all go through `off_path_row` ----
+      const unsigned long long plo = tq * (unsigned long long)p.slide;
 #pragma unroll
       for (int j = 0; j < P1_RPT; ++j) {
         const int i = j * P1_THREADS + tid;
         uint32_t r = NO_REGION;
         if (i < cnt) {
-          if (t[j] < 0) {
-            atomicAdd(&p.counters->neg_ts, 1ull);  // pre-epoch: reported, never aggregated
+          if (psel >= 0 && (unsigned long long)t[j] - plo < (unsigned long long)p.slide && k[j] != EMPTY_KEY) {
+            r = bd_bucket(bd_hash(k[j]), NB);
+            r |= atomicAdd(&hist[r], 1u) << 16;
           } else {
-            const uint64_t q = sd.div((uint64_t)t[j]);
-            if (q < p.late_q) {
-              ++late;
-            } else {
-              maxq = max(maxq, q);
-              if (q != tq || psel < 0) {
-                // another pane than the tile's (pane boundary, disorder) or no fast pane: the direct path does everything
-                slow_row<NV, SIG>(p, k[j], t[j], q, NV > 0 ? __ldcs(vcol + i) : 0ll, 0, 0, 0);
-              } else if (k[j] == EMPTY_KEY) {
-                // the sentinel key owns id 0, outside every bucket
-                direct_rec<NV>(p, fpane, fslot, q, k[j], NV > 0 ? __ldcs(vcol + i) : 0ll);
-              } else {
-                r = bd_bucket(bd_hash(k[j]), NB);
-                r |= atomicAdd(&hist[r], 1u) << 16;
-              }
-            }
+            off_path_row<NV, SIG>(p, k[j], t[j], NV > 0 ? __ldcs(vcol + i) : 0ll, psel >= 0 ? tq : ~0ull, fpane, fslot, late, maxq);
           }
         }
         rr[j] = r;
       }
+      if (psel >= 0) maxq = max(maxq, tq);
     }
     // the values: requested now, consumed after the scan (in flight across the barrier)
 #pragma unroll
@@ -470,16 +479,19 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
           const uint32_t h = p2_hash(rec.key);
           const uint32_t g = p2_group(h);
           const uint32_t tag2 = p2_tag(h) * 0x10001u;  // the tag in both halves
-          // the eight tags of the home group: one 16-byte load, four 2 x 16-bit compares
+          // the eight tags of the home group: one 16-byte load.  A half-word of (tags ^ tag2) is zero where the tag
+          // matches; (x - 0x00010001) & ~x & 0x80008000 flags zero half-words (a flagged half-word above a matching one
+          // can be a false positive: every candidate is confirmed against the key anyway).
           const uint4 tg = *reinterpret_cast<const uint4*>(htag + g);
-          uint32_t m = (__vcmpeq2(tg.x, tag2) & 0x00010100u) | ((__vcmpeq2(tg.y, tag2) & 0x00010100u) << 2) |
-                       ((__vcmpeq2(tg.z, tag2) & 0x00010100u) << 4) | ((__vcmpeq2(tg.w, tag2) & 0x00010100u) << 6);
-          // bit 8 + 2j: low half of word j matches (slot 2j); bit 16 + 2j: high half (slot 2j + 1)
+          const uint32_t x0 = tg.x ^ tag2, x1 = tg.y ^ tag2, x2 = tg.z ^ tag2, x3 = tg.w ^ tag2;
+          uint32_t m = (((x0 - 0x00010001u) & ~x0 & 0x80008000u) >> 15) | (((x1 - 0x00010001u) & ~x1 & 0x80008000u) >> 14) |
+                       (((x2 - 0x00010001u) & ~x2 & 0x80008000u) >> 13) | (((x3 - 0x00010001u) & ~x3 & 0x80008000u) >> 12);
+          // bit j: slot 2j (low half of word j); bit 16 + j: slot 2j + 1
           uint32_t idx = ID_UNSET;
           while (m) {  // almost always one candidate; a second one is a 16-bit tag collision inside the group
             const int bit = __ffs(m) - 1;
             m &= m - 1;
-            const int slot = bit >= 16 ? 2 * ((bit - 16) >> 1) + 1 : 2 * ((bit - 8) >> 1);
+            const int slot = bit >= 16 ? 2 * (bit - 16) + 1 : 2 * bit;
             if (hk[g + slot] == (unsigned long long)rec.key) {
               idx = hidx[g + slot];
               break;

@@ -1185,7 +1185,7 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
       AB_CUDA(cudaEventCreate(&launches_[i].t1));
     }
   }
-  if (c.reserved >= 16 && c.reserved <= 26) chunk_rows_ = 1ll << c.reserved;  // rows per ingest launch (default 2^23)
+  if (c.reserved >= 16 && c.reserved <= 26) chunk_rows_ = 1ll << c.reserved;  // rows per ingest launch (default 2^24)
   defer_cap_ = (uint64_t)chunk_rows_ * 2;
   d_emit_panes_.alloc(MAX_MERGE * sizeof(void*));
   d_out_count_.alloc(sizeof(unsigned int));

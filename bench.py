@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--no-combine", action="store_true", help="measurement knob: no warp-combining of equal keys")
     ap.add_argument("--avg-f64", action="store_true", help="measurement knob: AVG with its own f64 accumulator")
-    ap.add_argument("--chunk-log2", type=int, default=0, help="rows per ingest launch = 2^n (default 23)")
+    ap.add_argument("--chunk-log2", type=int, default=0, help="rows per ingest launch = 2^n (default 24)")
     ap.add_argument("--keyspace", default="scattered", choices=["scattered", "dense"],
                     help="scattered: key ids multiplied by an odd 64-bit constant (every key is hashed); "
                          "dense: Nexmark-shaped ids 1000 + n (the operator maps the range straight onto dense ids)")

@@ -174,7 +174,7 @@ typedef struct ArroyoB200OpConfig {
 
   uint64_t expected_keys;   /* capacity hint for the key dictionary (0 = default)         */
   uint32_t flags;           /* ARROYO_B200_FLAG_*                                         */
-  uint32_t reserved;        /* 0, or log2(rows per ingest launch) in [16, 26] (default 23)     */
+  uint32_t reserved;        /* 0, or log2(rows per ingest launch) in [16, 26] (default 24)     */
 } ArroyoB200OpConfig;
 
 #define ARROYO_B200_FLAG_PROFILE 1u       /* time kernels with CUDA events (op_stats)      */
