@@ -946,6 +946,10 @@ class WindowAggOp final : public OpBase {
   static constexpr int NCHUNK = 3;
   static constexpr int NLAUNCH = 3;
   int64_t chunk_rows_ = 1 << 24;  // rows per ingest launch: one headline pane; fixed per-launch costs (table builds, tails) halve vs 2^23
+  // device-resident batches are only pointers: they may pile up a little past one chunk before a launch is forced, so a
+  // stream whose watermarks arrive every chunk_rows_ rows or so gets one launch per watermark instead of a chunk-sized
+  // launch plus a fragment
+  int64_t launch_rows_ = (1 << 24) + (1 << 22);
   DevBuf chunk_[NCHUNK];
   cudaEvent_t chunk_free_[NCHUNK] = {nullptr, nullptr, nullptr};
   // host batches are staged by the copy engine on their own stream, so the link never waits for an ingest kernel:
@@ -1186,7 +1190,8 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
     }
   }
   if (c.reserved >= 16 && c.reserved <= 26) chunk_rows_ = 1ll << c.reserved;  // rows per ingest launch (default 2^24)
-  defer_cap_ = (uint64_t)chunk_rows_ * 2;
+  launch_rows_ = chunk_rows_ + chunk_rows_ / 4;
+  defer_cap_ = (uint64_t)launch_rows_ * 2;
   d_emit_panes_.alloc(MAX_MERGE * sizeof(void*));
   d_out_count_.alloc(sizeof(unsigned int));
   AB_CUDA(cudaMemsetAsync(d_out_count_.p, 0, sizeof(unsigned int), stream_));
@@ -1695,18 +1700,18 @@ void WindowAggOp::process_batch(uint32_t, uint32_t, ArrowArray* batch, const Arr
     if (pinned) {
       int64_t done = 0;
       while (done < n) {
-        int64_t take = std::min<int64_t>(n - done, chunk_rows_ - pending_rows_);
+        int64_t take = std::min<int64_t>(n - done, launch_rows_ - pending_rows_);
         const long long* vals[MAX_VALS];
         for (int v = 0; v < n_vals_; ++v) vals[v] = (const long long*)devp[val_cols_[v]] + done;
         add_segment(keyed_ ? (const long long*)devp[key_col_] + done : nullptr, (const long long*)devp[ts_col_] + done,
                     vals, take);
         done += take;
-        if (done < n && pending_rows_ >= chunk_rows_) launch_pending();
+        if (done < n && pending_rows_ >= launch_rows_) launch_pending();
       }
       st_.h2d_bytes += (uint64_t)n * 8 * (uint64_t)((keyed_ ? 1 : 0) + 1 + n_vals_);
       zero_copy_inputs_.push_back(*batch);
       batch->release = nullptr;
-      if (pending_rows_ >= chunk_rows_) launch_pending();
+      if (pending_rows_ >= launch_rows_) launch_pending();
       return;
     }
   }
@@ -1755,13 +1760,13 @@ void WindowAggOp::process_device_batch(uint32_t, uint32_t, const uint64_t* cols,
   st_.rows_in += (uint64_t)n_rows;
   int64_t done = 0;
   while (done < n_rows) {
-    int64_t take = std::min<int64_t>(n_rows - done, chunk_rows_ - pending_rows_);
+    int64_t take = std::min<int64_t>(n_rows - done, launch_rows_ - pending_rows_);
     const long long* vals[MAX_VALS];
     for (int v = 0; v < n_vals_; ++v) vals[v] = (const long long*)cols[val_cols_[v]] + done;
     add_segment(keyed_ ? (const long long*)cols[key_col_] + done : nullptr, (const long long*)cols[ts_col_] + done, vals,
                 take);
     done += take;
-    if (pending_rows_ >= chunk_rows_) launch_pending();
+    if (pending_rows_ >= launch_rows_) launch_pending();
   }
 }
 
@@ -1805,7 +1810,7 @@ void WindowAggOp::launch_two_pass(IngestParams& p, uint64_t rows, long long tile
   }
   const uint32_t n_regions = (uint32_t)(TP_NP * n_buckets_);
   // a region holds a bucket's share of one pane's rows: mean rows / buckets, plus slack for the spread
-  const uint64_t mean = (uint64_t)chunk_rows_ / n_buckets_ + 1;
+  const uint64_t mean = (uint64_t)launch_rows_ / n_buckets_ + 1;
   const uint32_t cap = (uint32_t)std::min<uint64_t>(((mean + mean / 4 + 2048 + 63) / 64) * 64, 1u << 30);
   if (part_cap_ != cap || !part_.p) {
     AB_CUDA(cudaStreamSynchronize(stream_));
@@ -1845,8 +1850,8 @@ void WindowAggOp::launch_two_pass(IngestParams& p, uint64_t rows, long long tile
 }
 
 void WindowAggOp::launch_segments(const std::vector<Segment>& segs_in, int chunk) {
-  // At most two launches (each <= chunk_rows_ rows) are ever in flight, so the deferred buffer
-  // (2 * chunk_rows_ rows) cannot overflow; as soon as a finished launch reports deferrals they are
+  // At most two launches (each <= launch_rows_ rows) are ever in flight, so the deferred buffer
+  // (2 * launch_rows_ rows) cannot overflow; as soon as a finished launch reports deferrals they are
   // drained before anything else is queued.
   while (in_flight_.size() >= 2) absorb(in_flight_.front());
   if (!draining_ && have_counters_ && last_counters_.deferred > 0) {
