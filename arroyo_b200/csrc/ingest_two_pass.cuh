@@ -13,12 +13,12 @@
 //                         staged in shared memory in bucket order (write combining) and every bucket's run is appended
 //                         to the bucket's region of a partition buffer with ONE global atomic per (tile, bucket);
 //                         records are {key, value}, 16 bytes.
-//   pass 2  agg_kernel    one block per (pane, bucket): builds a lookup table of the bucket's keys in shared memory (from
-//                         the bucket's contiguous id range of id_keys), the region's records arrive through per-warp
-//                         TMA rings (cp.async.bulk + mbarrier), every row is one straight-line shared-memory lookup
-//                         and two or three 32-bit shared-memory atomics on the bucket's accumulators, which are then
-//                         added to the bucket's contiguous id range of the pane block (coalesced; plain
-//                         read-modify-write when the bucket has one block).
+//   pass 2  agg_kernel    one block per bucket: builds a lookup table of the bucket's keys in shared memory (from the
+//                         bucket's contiguous id range of id_keys) once for the bucket's regions of both fast panes;
+//                         a region's records arrive through per-warp TMA rings (cp.async.bulk + mbarrier), every row
+//                         is one straight-line shared-memory lookup and one or two 32-bit shared-memory atomics on
+//                         the bucket's accumulators, which are then added to the bucket's contiguous id range of the
+//                         pane block (coalesced; plain read-modify-write when the bucket has one block).
 //
 // Algorithmic bytes: 24 per input row (read once).  Traffic of the pair: 24 + 16 (partition write) + 16 (read back)
 // + the dictionary slices and the pane block once per launch.
@@ -351,7 +351,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-// One block per (pane, bucket[, slice]).
+// One block per (bucket[, slice]); the bucket's regions of the launch's fast panes one after the other.
 //
 // The block builds its own lookup table of the bucket's keys in shared memory, from the bucket's id range of
 // `id_keys` (8 KB for a full bucket; the dictionary's own 32 KB slice is not read): P2_HS slots in groups of eight, and
@@ -362,9 +362,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // eight full keys costs four 16-byte loads and sixteen compares per row: profiles/r02_two_pass_c .. _f.)  At a
 // quarter load a group overflows once in ten thousand keys; those and first sightings take the slow path.
 // The bucket's accumulators live once in shared memory and take shared-memory atomics (ATOMS.ADD.32: ~3.5 SM-cycles
-// per warp instruction on spread addresses, duplicates inside a warp included).  The 64-bit wrapping SUM is two 32-bit
-// words: the low word takes every row's low half (the returned old value tells whether it wrapped), the high word the
-// high half plus that carry -- for the small positive values of a bid stream the second atomic is rare.
+// per warp instruction on spread addresses, duplicates inside a warp included).  The shared-memory data pipe is what
+// bounds this kernel (72 % busy in profiles/r02_two_pass_h), so a row costs two atomics, not three: the 64-bit wrapping
+// SUM's low word takes every row's low half (the returned old value tells whether it wrapped); that carry -- minus one
+// for a negative row, whose high word is all ones -- rides in the high 16 bits of the key's row-count word, which is
+// flushed before either half can reach 2^15.  Only values that are not sign-extended 32-bit numbers add their high
+// word with a third atomic.
 // Records arrive through per-warp TMA rings (cp.async.bulk + mbarrier).
 constexpr int P2_HS = 4096;  // slots of the block's lookup table
 constexpr int P2_HG = 8;     // slots per group (their tags = one 16-byte load)
@@ -392,6 +395,65 @@ __device__ __forceinline__ void p2_insert(unsigned long long* hk, unsigned short
   }
 }
 
+// shared-memory accesses of the aggregation loop by 32-bit shared address (the generic form re-derives the block's
+// shared window for every access)
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned long long lds64(uint32_t a) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void reds_add(uint32_t a, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+// A key the home group's tags did not yield: it spilled into the following slots, or the block has not seen it yet
+// (out of line: rare, and its probe loops would sit in the middle of the hot loop).
+__device__ __noinline__ uint32_t agg_slow_lookup(const IngestParams& p, unsigned long long* hk, unsigned short* htag,
+                                                 unsigned short* hidx, uint32_t b, long long key, uint32_t g) {
+  bool full = true;  // only a group without an empty slot can have spilled
+  for (int x = 0; x < P2_HG; ++x) full = full && htag[g + x] != 0;
+  uint32_t sl = (g + P2_HG) & (P2_HS - 1);
+#pragma unroll 1
+  for (int probe = 0; full && probe < P2_HS; ++probe) {
+    const unsigned long long e = hk[sl];
+    if (e == (unsigned long long)key && htag[sl] != 0) return hidx[sl];
+    if (e == (unsigned long long)EMPTY_KEY) break;
+    sl = (sl + 1) & (P2_HS - 1);
+  }
+  // first sight in this block: global insert (race-free across blocks), then remember it here
+  const uint32_t id = bd_insert(p.dict, b, key, bd_slot0(key));
+  if (id >= ID_OVERFLOW) return ID_OVERFLOW;
+  const uint32_t idx = id - bd_id(b, 0);
+  p2_insert(hk, htag, hidx, key, idx);
+  return idx;
+}
+
+// rows the aggregation pass hands back to the host (out of line: keeps their address arithmetic off the hot path)
+__device__ __noinline__ void agg_defer(const IngestParams& p, long long key, long long ts, long long val, int why) {
+  if (why == 0) atomicAdd(&p.counters->big_vals, 1ull);  // exact-AVG guard: the host promotes the operator
+  else atomicAdd(&p.counters->dict_full, 1u);            // bucket out of ids: the host grows the dictionary
+  defer_row(p, key, ts, val, 0, 0, 0);
+}
+
+// rows per block between two flushes of the shared accumulators: the row count and the high-word carries of a key
+// share one 32-bit word (16 bits each), so neither may reach 2^15
+constexpr unsigned P2_FLUSH_ITERS = 31;  // x P2_NW warps x P2_CH rows = 31744 rows
+
 template <int NV>
 __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const __grid_constant__ IngestParams p,
                                                                            const __grid_constant__ TwoPassParams tp) {
@@ -399,9 +461,9 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
   unsigned long long* hk = reinterpret_cast<unsigned long long*>(smem_raw);             // [P2_HS] keys
   unsigned short* htag = reinterpret_cast<unsigned short*>(hk + P2_HS);                 // [P2_HS] tags
   unsigned short* hidx = htag + P2_HS;                                                  // [P2_HS] index inside the bucket
-  uint32_t* scnt = reinterpret_cast<uint32_t*>(hidx + P2_HS);                           // [BD_CAPB] rows
-  uint32_t* slo = scnt + BD_CAPB;                                                      // [BD_CAPB] sum, low word
-  uint32_t* shi = slo + BD_CAPB;                                                       // [BD_CAPB] sum, high word
+  uint32_t* scw = reinterpret_cast<uint32_t*>(hidx + P2_HS);  // [BD_CAPB] rows (low 16 bits) + signed high-word delta (high 16)
+  uint32_t* slo = scw + BD_CAPB;                                                       // [BD_CAPB] sum, low word
+  uint32_t* shi = slo + BD_CAPB;                                                       // [BD_CAPB] sum, high word (wide values only)
   Rec* ring = reinterpret_cast<Rec*>(shi + BD_CAPB);                                   // NW x NST x CH x 16
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + (size_t)P2_NW * P2_NST * P2_CH);  // NW x NST
   __shared__ unsigned long long s_rows;
@@ -409,44 +471,55 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
   const uint32_t NB = p.dict.n_buckets;
   Rec* myring = ring + (size_t)w * P2_NST * P2_CH;
   const uint32_t bar0 = smem_u32(bars + (size_t)w * P2_NST);
+  const uint32_t a_hk = smem_u32(hk), a_tag = smem_u32(htag), a_idx = smem_u32(hidx), a_cw = smem_u32(scw),
+                 a_lo = smem_u32(slo), a_hi = smem_u32(shi), a_ring = smem_u32(myring);
   if (lane == 0)
     for (int s = 0; s < P2_NST; ++s) mbar_init(bar0 + 8 * s, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  for (int i = tid; i < 3 * BD_CAPB; i += P2_NW * 32) scnt[i] = 0;
+  for (int i = tid; i < 3 * BD_CAPB; i += P2_NW * 32) scw[i] = 0;
   if (tid == 0) s_rows = 0;
   __syncthreads();
   uint32_t phase = 0;  // bit s = parity of this warp's stage s
   const bool guard = NV > 0 && p.guard_vals != 0;
 
-  const uint32_t n_work = TP_NP * NB * tp.slices;
+  // work item = (bucket, slice): the bucket's lookup table is built once and serves the bucket's regions of all the
+  // launch's fast panes
+  const uint32_t n_work = NB * tp.slices;
   for (uint32_t work = blockIdx.x; work < n_work; work += gridDim.x) {
-    const uint32_t region = work / tp.slices, slice = work % tp.slices;
-    const uint32_t psel = region / NB, b = region % NB;
-    if (tid == 0) tp.cursor_next[region] = 0;  // nobody else touches the other cursor set during this launch
-    const unsigned n_all = min(tp.cursor[region], tp.cap);
-    if (n_all == 0 || tp.fast_ptr[psel] == nullptr) continue;  // block-uniform
-    // this block's share of the region, in whole ring chunks
-    const unsigned chunks_all = (n_all + P2_CH - 1) / P2_CH;
-    const unsigned c_lo = (unsigned)((unsigned long long)chunks_all * slice / tp.slices);
-    const unsigned c_hi = (unsigned)((unsigned long long)chunks_all * (slice + 1) / tp.slices);
-    if (c_lo == c_hi) continue;
-    const unsigned r_lo = c_lo * P2_CH, r_hi = min(c_hi * P2_CH, n_all);
-    const Rec* rows = tp.part + (size_t)region * tp.cap + r_lo;
-    const unsigned n = r_hi - r_lo;
-    unsigned long long* pane = tp.fast_ptr[psel];
-    const uint64_t q = tp.fast_q[psel];
+    const uint32_t b = work / tp.slices, slice = work % tp.slices;
+    unsigned n_reg[TP_NP];
+    unsigned n_any = 0;
+#pragma unroll
+    for (int f = 0; f < TP_NP; ++f) {
+      n_reg[f] = tp.fast_ptr[f] ? min(tp.cursor[f * NB + b], tp.cap) : 0u;
+      n_any |= n_reg[f];
+      if (tid == 0) tp.cursor_next[f * NB + b] = 0;  // nobody else touches the other cursor set during this launch
+    }
+    if (n_any == 0) continue;  // block-uniform
 
-    // the first record chunks are requested before the table is built
-    const unsigned n_chunks = (n + P2_CH - 1) / P2_CH;
-    const unsigned my_chunks = n_chunks > (unsigned)w ? (n_chunks - w + P2_NW - 1) / P2_NW : 0;
+    // this block's rows of one region, in whole ring chunks
+    const Rec* rows = nullptr;
+    unsigned n = 0, my_chunks = 0;
+    auto select = [&](int f) {
+      const unsigned chunks_all = (n_reg[f] + P2_CH - 1) / P2_CH;
+      const unsigned c_lo = (unsigned)((unsigned long long)chunks_all * slice / tp.slices);
+      const unsigned c_hi = (unsigned)((unsigned long long)chunks_all * (slice + 1) / tp.slices);
+      const unsigned r_lo = c_lo * P2_CH, r_hi = min(c_hi * P2_CH, n_reg[f]);
+      rows = tp.part + (size_t)(f * NB + b) * tp.cap + r_lo;
+      n = r_hi > r_lo ? r_hi - r_lo : 0u;
+      const unsigned n_chunks = (n + P2_CH - 1) / P2_CH;
+      my_chunks = n_chunks > (unsigned)w ? (n_chunks - w + P2_NW - 1) / P2_NW : 0;
+    };
     auto issue = [&](unsigned ci, int s) {
       const unsigned r0 = (w + ci * P2_NW) * P2_CH;
       const unsigned nr = min((unsigned)P2_CH, n - r0);
       if (lane == 0) {
         mbar_expect_tx(bar0 + 8 * s, nr * 16);
-        tma_load_1d(smem_u32(myring + (size_t)s * P2_CH), rows + r0, nr * 16, bar0 + 8 * s);
+        tma_load_1d(a_ring + (uint32_t)s * P2_CH * 16, rows + r0, nr * 16, bar0 + 8 * s);
       }
     };
+    // the first record chunks of the first pane are requested before the table is built
+    select(0);
     for (unsigned ci = 0; ci < (unsigned)P2_NST && ci < my_chunks; ++ci) issue(ci, (int)ci);
 
     // ---- build the bucket's lookup table ----
@@ -464,109 +537,115 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
     }
     __syncthreads();
 
-    unsigned int my_rows = 0;
-    for (unsigned ci = 0; ci < my_chunks; ++ci) {
-      const int s = (int)(ci % P2_NST);
-      mbar_wait(bar0 + 8 * s, (phase >> s) & 1u);
-      phase ^= 1u << s;
-      const unsigned nr = min((unsigned)P2_CH, n - (w + ci * P2_NW) * P2_CH);
-      const Rec* chunk = myring + (size_t)s * P2_CH;
-#pragma unroll
-      for (int sub = 0; sub < P2_CH / 32; ++sub) {
-        const unsigned ri = sub * 32 + lane;
-        if (ri < nr) {
-          const Rec rec = chunk[ri];
-          const uint32_t h = p2_hash(rec.key);
-          const uint32_t g = p2_group(h);
-          const uint32_t tag2 = p2_tag(h) * 0x10001u;  // the tag in both halves
-          // the eight tags of the home group: one 16-byte load.  A half-word of (tags ^ tag2) is zero where the tag
-          // matches; (x - 0x00010001) & ~x & 0x80008000 flags zero half-words (a flagged half-word above a matching one
-          // can be a false positive: every candidate is confirmed against the key anyway).
-          const uint4 tg = *reinterpret_cast<const uint4*>(htag + g);
-          const uint32_t x0 = tg.x ^ tag2, x1 = tg.y ^ tag2, x2 = tg.z ^ tag2, x3 = tg.w ^ tag2;
-          uint32_t m = (((x0 - 0x00010001u) & ~x0 & 0x80008000u) >> 15) | (((x1 - 0x00010001u) & ~x1 & 0x80008000u) >> 14) |
-                       (((x2 - 0x00010001u) & ~x2 & 0x80008000u) >> 13) | (((x3 - 0x00010001u) & ~x3 & 0x80008000u) >> 12);
-          // bit j: slot 2j (low half of word j); bit 16 + j: slot 2j + 1
-          uint32_t idx = ID_UNSET;
-          while (m) {  // almost always one candidate; a second one is a 16-bit tag collision inside the group
-            const int bit = __ffs(m) - 1;
-            m &= m - 1;
-            const int slot = bit >= 16 ? 2 * (bit - 16) + 1 : 2 * bit;
-            if (hk[g + slot] == (unsigned long long)rec.key) {
-              idx = hidx[g + slot];
-              break;
+#pragma unroll 1
+    for (int f = 0; f < TP_NP; ++f) {
+      if (f > 0) {
+        select(f);
+        for (unsigned ci = 0; ci < (unsigned)P2_NST && ci < my_chunks; ++ci) issue(ci, (int)ci);
+      }
+      if (n == 0) continue;  // block-uniform
+      unsigned long long* pane = tp.fast_ptr[f];
+      const long long pane_ts = (long long)(tp.fast_q[f] * (uint64_t)p.slide);
+      unsigned long long* prow = pane + bd_id(b, 0);
+      unsigned long long* psum = pane + p.id_cap + bd_id(b, 0);
+      unsigned int flushed = 0;
+      // adds the bucket's accumulators to its id range of the pane block and leaves them zeroed
+      auto flush = [&]() {
+        for (unsigned i = tid; i < (unsigned)BD_CAPB; i += P2_NW * 32) {
+          const uint32_t cw = scw[i];
+          if (cw) {
+            const uint32_t c = cw & 0xFFFFu;
+            const uint32_t dh = (uint32_t)((int32_t)(cw - c) >> 16);  // carries minus negative rows, sign-extended
+            const unsigned long long sum = ((unsigned long long)(shi[i] + dh) << 32) + (unsigned long long)slo[i];
+            scw[i] = 0;
+            slo[i] = 0;
+            shi[i] = 0;
+            flushed += c;
+            if (tp.slices == 1) {  // the block owns the bucket's ids of this pane for the whole launch
+              prow[i] += c;
+              if (NV > 0) psum[i] += sum;
+            } else {
+              red_add_u64(prow + i, c);
+              if (NV > 0) red_add_u64(psum + i, sum);
             }
           }
-          if (idx == ID_UNSET) {
-            // not in the home group: it spilled into the following slots, or the block has not seen the key yet
-            bool full = true;  // only a group without an empty slot can have spilled
-            for (int x = 0; x < P2_HG; ++x) full = full && htag[g + x] != 0;
-            uint32_t sl = (g + P2_HG) & (P2_HS - 1);
+        }
+      };
+      const unsigned iters = ((n + P2_CH - 1) / P2_CH + P2_NW - 1) / P2_NW;  // block-uniform bound of my_chunks
 #pragma unroll 1
-            for (int probe = 0; full && probe < P2_HS; ++probe) {
-              const unsigned long long e = hk[sl];
-              if (e == (unsigned long long)rec.key && htag[sl] != 0) {
-                idx = hidx[sl];
+      for (unsigned ci = 0; ci < iters; ++ci) {
+        if (ci && ci % P2_FLUSH_ITERS == 0) {
+          __syncthreads();
+          flush();
+          __syncthreads();
+        }
+        if (ci >= my_chunks) continue;
+        const int s = (int)(ci % P2_NST);
+        mbar_wait(bar0 + 8 * s, (phase >> s) & 1u);
+        phase ^= 1u << s;
+        const unsigned nr = min((unsigned)P2_CH, n - (w + ci * P2_NW) * P2_CH);
+        const uint32_t a_chunk = a_ring + (uint32_t)s * P2_CH * 16;
+#pragma unroll
+        for (int sub = 0; sub < P2_CH / 32; ++sub) {
+          const unsigned ri = sub * 32 + lane;
+          if (ri < nr) {
+            const uint4 rr = lds128(a_chunk + ri * 16);
+            const long long key = (long long)(((unsigned long long)rr.y << 32) | rr.x);
+            const uint32_t h = p2_hash(key);
+            const uint32_t g = p2_group(h);
+            const uint32_t tag2 = p2_tag(h) * 0x10001u;  // the tag in both halves
+            // the eight tags of the home group: one 16-byte load.  A half-word of (tags ^ tag2) is zero where the tag
+            // matches; (x - 0x00010001) & ~x & 0x80008000 flags zero half-words (a flagged half-word above a matching one
+            // can be a false positive: every candidate is confirmed against the key anyway).
+            const uint4 tg = lds128(a_tag + g * 2);
+            const uint32_t x0 = tg.x ^ tag2, x1 = tg.y ^ tag2, x2 = tg.z ^ tag2, x3 = tg.w ^ tag2;
+            uint32_t m = (((x0 - 0x00010001u) & ~x0 & 0x80008000u) >> 15) | (((x1 - 0x00010001u) & ~x1 & 0x80008000u) >> 14) |
+                         (((x2 - 0x00010001u) & ~x2 & 0x80008000u) >> 13) | (((x3 - 0x00010001u) & ~x3 & 0x80008000u) >> 12);
+            // bit j: slot 2j (low half of word j); bit 16 + j: slot 2j + 1
+            uint32_t idx = ID_UNSET;
+            while (m) {  // almost always one candidate; a second one is a 16-bit tag collision inside the group
+              const uint32_t bit = (uint32_t)__ffs(m) - 1u;
+              m &= m - 1;
+              const uint32_t sl = g + (((bit & 15u) << 1) | (bit >> 4));
+              if (lds64(a_hk + sl * 8) == (unsigned long long)key) {
+                idx = lds16(a_idx + sl * 2);
                 break;
               }
-              if (e == (unsigned long long)EMPTY_KEY) break;
-              sl = (sl + 1) & (P2_HS - 1);
             }
-            if (idx == ID_UNSET) {
-              // first sight in this block: global insert (race-free across blocks), then remember it here
-              const uint32_t id = bd_insert(p.dict, b, rec.key, bd_slot0(rec.key));
-              idx = id >= ID_OVERFLOW ? ID_OVERFLOW : id - bd_id(b, 0);
-              if (idx < ID_OVERFLOW) p2_insert(hk, htag, hidx, rec.key, idx);
+            if (idx == ID_UNSET) idx = agg_slow_lookup(p, hk, htag, hidx, b, key, g);
+            const uint32_t vl = rr.z, vh = rr.w;
+            const bool narrow = NV == 0 || (uint32_t)((int32_t)vl >> 31) == vh;  // the value is a sign-extended 32-bit number
+            if (idx >= (uint32_t)BD_CAPB) {
+              agg_defer(p, key, pane_ts, (long long)(((unsigned long long)vh << 32) | vl), 1);
+            } else if (NV > 0 && guard && !narrow) {
+              // exact-AVG guard (the partition pass does not look at values): park the row for the host's promotion
+              agg_defer(p, key, pane_ts, (long long)(((unsigned long long)vh << 32) | vl), 0);
+            } else if (NV == 0) {
+              reds_add(a_cw + idx * 4, 1u);
+            } else {
+              // low word: every row; its carry, minus one for a negative row (whose high word is all ones), rides in
+              // the high half of the row-count word.  Wide values add their high word separately (rare).
+              const uint32_t old = atoms_add(a_lo + idx * 4, vl);
+              uint32_t d = (old + vl) < vl ? 1u : 0u;
+              if (narrow) d -= vl >> 31;
+              else reds_add(a_hi + idx * 4, vh);
+              reds_add(a_cw + idx * 4, 1u + (d << 16));
             }
           }
-          if (guard && big_one(rec.val)) {
-            // exact-AVG guard (the partition pass does not look at values): park the row for the host's promotion
-            atomicAdd(&p.counters->big_vals, 1ull);
-            defer_row(p, rec.key, (long long)(q * (uint64_t)p.slide), rec.val, 0, 0, 0);
-          } else if (idx < (uint32_t)BD_CAPB) {
-            atomicAdd(&scnt[idx], 1u);
-            if (NV > 0) {
-              const uint32_t vl = (uint32_t)(unsigned long long)rec.val;
-              const uint32_t old = atomicAdd(&slo[idx], vl);
-              const uint32_t vh = (uint32_t)((unsigned long long)rec.val >> 32) + ((old + vl) < vl ? 1u : 0u);
-              if (vh) atomicAdd(&shi[idx], vh);
-            }
-            ++my_rows;
-          } else {
-            atomicAdd(&p.counters->dict_full, 1u);  // bucket out of ids: the row waits for the host to grow the dictionary
-            defer_row(p, rec.key, (long long)(q * (uint64_t)p.slide), rec.val, 0, 0, 0);
-          }
         }
+        __syncwarp();
+        if (ci + P2_NST < my_chunks) issue(ci + P2_NST, s);
       }
-      __syncwarp();
-      if (ci + P2_NST < my_chunks) issue(ci + P2_NST, s);
-    }
-    // rows this block aggregated into the pane (the host's per-pane on-time row counts)
-    my_rows = __reduce_add_sync(0xffffffffu, my_rows);
-    if (lane == 0 && my_rows) atomicAdd(&s_rows, (unsigned long long)my_rows);
-    __syncthreads();
-    // add the bucket's accumulators to its id range of the pane block and leave them zeroed for the next bucket
-    unsigned long long* prow = pane + bd_id(b, 0);
-    unsigned long long* psum = pane + p.id_cap + bd_id(b, 0);
-    for (unsigned i = tid; i < (unsigned)BD_CAPB; i += P2_NW * 32) {
-      const uint32_t c = scnt[i];
-      if (c) {
-        const unsigned long long sum = ((unsigned long long)shi[i] << 32) + (unsigned long long)slo[i];
-        scnt[i] = 0;
-        slo[i] = 0;
-        shi[i] = 0;
-        if (tp.slices == 1) {  // the block owns the bucket's ids of this pane for the whole launch
-          prow[i] += c;
-          if (NV > 0) psum[i] += sum;
-        } else {
-          red_add_u64(prow + i, c);
-          if (NV > 0) red_add_u64(psum + i, sum);
-        }
+      __syncthreads();
+      flush();
+      // rows this block aggregated into the pane (the host's per-pane on-time row counts)
+      flushed = __reduce_add_sync(0xffffffffu, flushed);
+      if (lane == 0 && flushed) atomicAdd(&s_rows, (unsigned long long)flushed);
+      __syncthreads();
+      if (tid == 0) {
+        if (s_rows) atomicAdd(p.slot_rows + tp.fast_slot[f], s_rows);
+        s_rows = 0;
       }
-    }
-    if (tid == 0) {
-      if (s_rows) atomicAdd(p.slot_rows + tp.fast_slot[psel], s_rows);
-      s_rows = 0;
     }
     __syncthreads();
   }

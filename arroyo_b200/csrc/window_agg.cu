@@ -1836,7 +1836,7 @@ void WindowAggOp::launch_two_pass(IngestParams& p, uint64_t rows, long long tile
     two_pass_attr_set_ = true;
   }
   const int grid1 = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)num_sms_ * P1_BLOCKS_PER_SM));
-  const int grid2 = (int)std::max<uint32_t>(1, std::min<uint32_t>(n_regions * tp.slices, (uint32_t)num_sms_ * P2_BLOCKS_PER_SM));
+  const int grid2 = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)n_buckets_ * tp.slices, (uint32_t)num_sms_ * P2_BLOCKS_PER_SM));
   if (n_vals_ == 0) {
     part_kernel<0, 0><<<grid1, P1_THREADS, P1_SMEM, stream_>>>(p, tp);
     AB_CUDA(cudaGetLastError());

@@ -822,6 +822,10 @@ def bench(args, torch, dist, rank, world, local, all_cpus=None):
                "config": B.workload_config(args, world),
                "impl": {"shuffle": ("partial aggregates per pane (partial -> shuffle -> final)" if mode == "partials"
                                     else "raw rows (reference plan shape)"),
+                        "exchange": (None if mode != "partials" or args.sync_plan else
+                                     "one C call per round: device partition + ncclAllGather of the control records + grouped "
+                                     "ncclSend / ncclRecv (csrc/exchange.cu)" if getattr(args, "native_exchange", False) else
+                                     "torch.distributed all_gather + all_to_all_single"),
                         "numa": getattr(args, "numa", None),
                         "warmup_note": "warm-up = max(--warmup, width/slide + 5) panes: the timed steps see the steady state"},
                "plan": (None if mode != "partials" else

@@ -76,15 +76,20 @@ def parse():
     ap.add_argument("--local-chunk-log2", type=int, default=23,
                     help="N>1, partials: rows per ingest launch of the local stage = 2^n; short launches let the owner "
                          "stage's kernels in between")
-    ap.add_argument("--native-exchange", action="store_true",
-                    help="N>1, partials: the shuffle round as one C call with NCCL from C++ (csrc/exchange.cu); "
-                         "experimental, not the measured default")
+    ap.add_argument("--python-exchange", action="store_true",
+                    help="N>1, partials: the shuffle round through torch.distributed (device partitioner + all_gather + "
+                         "all_to_all_single from Python) instead of the library's own round (csrc/exchange.cu: partition + "
+                         "control all-gather + grouped ncclSend / ncclRecv in one C call), which is the default: "
+                         "47.7 vs 32.7 G rows/s at N = 2 (profiles/r02_bench_n2_*.json)")
+    ap.add_argument("--native-exchange", action="store_true", help="accepted and ignored (it is the default since round 2)")
     ap.add_argument("--sync-plan", action="store_true",
                     help="N>1, partials: run the local stage, the shuffle and the owner stage in sequence on one host "
                          "thread instead of as a two-stage pipeline")
     ap.add_argument("--shuffle", default="partials", choices=["partials", "rows"],
                     help="N>1: what crosses the all-to-all (per-pane partial aggregates, or raw rows)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    args.native_exchange = not args.python_exchange
+    return args
 
 
 # ------------------------------------------------------------------------------------------------

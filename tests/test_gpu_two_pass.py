@@ -120,3 +120,59 @@ def test_two_pass_survives_a_checkpoint_and_restore(G):
     ctx.watermarks.set(0, ab.FINAL_WATERMARK)
     op.handle_watermark(ab.FINAL_WATERMARK, ctx, out)
     assert_same(want, [from_arrow(b) for b in out.batches], float_cols=("avg",))
+
+
+def test_one_large_launch_with_wide_and_negative_values_against_a_group_by(G):
+    """One 2^24-row launch over 100 000 keys, SUM + COUNT (no AVG, so no value guard): 128 buckets x 3 blocks, i.e.
+    ~44 000 rows per aggregation block -- more than the packed row-count / carry word holds between two flushes -- and
+    values that are full-range, negative, or just around the 32-bit boundaries (the wide-value path, carries, borrows).
+    Checked row by row against an independent group-by (torch.unique + index_add, which wraps like i64 SUM)."""
+    import pyarrow as pa
+    import torch
+
+    import arroyo_b200 as ab
+    from arroyo_b200 import ffi, operators as native
+    from arroyo_b200.multi_gpu import _Ptr
+
+    device = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    torch.cuda.set_stream(torch.cuda.Stream(device=device))
+    g = torch.Generator(device=device)
+    g.manual_seed(5)
+    n, n_keys = 1 << 24, 100_000
+    ids = torch.randint(0, n_keys, (n,), generator=g, device=device, dtype=torch.int64)
+    key = ids * 0x1E3779B97F4A7C15 % (1 << 62) - (1 << 61)  # scattered (the product wraps), some negative
+    val = torch.randint(-(1 << 62), 1 << 62, (n,), generator=g, device=device, dtype=torch.int64) * 2
+    kind = torch.randint(0, 4, (n,), generator=g, device=device)
+    small = torch.randint(-(1 << 31), 1 << 31, (n,), generator=g, device=device, dtype=torch.int64)
+    edge = torch.tensor([-1, -(1 << 31), (1 << 31) - 1, 1 << 31, -(1 << 31) - 1, (1 << 32) - 1, -(1 << 32), 0],
+                        device=device)[torch.randint(0, 8, (n,), generator=g, device=device)]
+    val = torch.where(kind == 0, val, torch.where(kind == 1, edge, small))
+    ts = T0 + torch.randint(0, S, (n,), generator=g, device=device, dtype=torch.int64)
+    cfg = ab.WindowAggConfig(width=S, key_names=["key"], aggs=[ab.Agg("sum", "value", "sum"), ab.Agg("count", None, "n")],
+                             window_index=1)
+    schema = pa.schema([("key", pa.int64()), ("value", pa.int64()), ("_timestamp", pa.timestamp("ns"))])
+    op = native.TumblingAggregatingWindowFunc(cfg, input_schema=schema, device=0,
+                                              stream=torch.cuda.current_stream().cuda_stream,
+                                              flags=ffi.FLAG_TWO_PASS_ALWAYS, expected_keys=n_keys)
+    # a first small batch tells the operator where the stream is (the two passes need a known newest pane)
+    op.process_device_batch([key.data_ptr(), val.data_ptr(), ts.data_ptr()], 4096)
+    op.flush()
+    op.process_device_batch([key.data_ptr() + 8 * 4096, val.data_ptr() + 8 * 4096, ts.data_ptr() + 8 * 4096], n - 4096)
+    got = None
+    for rows, ptrs in op.handle_watermark_device(T0 + 2 * S):
+        assert got is None
+        got = [torch.as_tensor(_Ptr(c, rows), device=device).clone() for c in ptrs]
+    st = op.stats()
+    op.close()
+    assert got is not None
+    uk, inv = torch.unique(key, return_inverse=True)
+    want_sum = torch.zeros(uk.numel(), dtype=torch.int64, device=device).index_add_(0, inv, val)
+    want_cnt = torch.zeros(uk.numel(), dtype=torch.int64, device=device).index_add_(0, inv, torch.ones_like(val))
+    k_out, ws, we, s_out, n_out = got[0], got[1], got[2], got[3], got[4]  # device layout: window = two i64 columns
+    order = torch.argsort(k_out)
+    assert torch.equal(k_out[order], uk)
+    assert torch.equal(n_out[order], want_cnt)
+    assert torch.equal(s_out[order], want_sum)
+    assert bool((ws == T0).all()) and bool((we == T0 + S).all())
+    assert st["rows_deferred"] == 0
