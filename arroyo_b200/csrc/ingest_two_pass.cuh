@@ -61,7 +61,9 @@ struct TwoPassParams {
   unsigned int* cursor;                // [TP_NP * n_buckets], zero when the partition pass starts
   unsigned int* cursor_next;           // the NEXT launch's cursors: the aggregation pass zeroes them
   uint32_t cap;                        // records per region
-  uint32_t slices;                     // pass-2 blocks per region
+  uint32_t slices;                     // pass-2 blocks per bucket (buckets below tail_first)
+  uint32_t tail_first;                 // buckets from here on are cut into tail_slices slices each: the last round of
+  uint32_t tail_slices;                // work items is made of part-buckets, so that it is short instead of ragged
 };
 
 constexpr size_t P1_SMEM = (size_t)P1_TILE * 16 + (size_t)P1_TILE * 2 + (size_t)P1_NR * 12;
@@ -137,12 +139,13 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
     s_done = 0;
   }
 
+  for (int i = tid; i < P1_NR; i += P1_THREADS) hist[i] = 0;  // afterwards every bucket's owner re-zeroes it in the scan
   for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    int lo = 0, hi = p.n_segs - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (__ldg(&p.segs[mid].tile_start) <= tile) lo = mid; else hi = mid - 1;
-    }
+    // the tile's segment: batches are mostly equal-sized, so an interpolated guess is right or off by one (a binary
+    // search is eight dependent loads before the tile's first row can be requested)
+    int lo = (int)((unsigned long long)tile * (unsigned)p.n_segs / (unsigned long long)p.n_tiles);
+    while (lo > 0 && __ldg(&p.segs[lo].tile_start) > tile) --lo;
+    while (lo + 1 < p.n_segs && __ldg(&p.segs[lo + 1].tile_start) <= tile) ++lo;
     const Segment* sg = p.segs + lo;
     const long long base = (tile - __ldg(&sg->tile_start)) * P1_TILE;
     const long long nrem = __ldg(&sg->n) - base;
@@ -151,12 +154,26 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
     const long long* tcol = ldg_ptr(&sg->ts) + base;
     const long long* vcol = NV > 0 ? ldg_ptr(&sg->val[0]) + base : nullptr;
 
-    for (int i = tid; i < P1_NR; i += P1_THREADS) hist[i] = 0;
-    // The tile's pane = the pane of its first row.  Tiles are contiguous in arrival order, so all but the tiles at a
-    // pane boundary hold one pane; rows of any other pane (and every row of a tile whose first row is late) take the
-    // direct path below.
+    // ---- load phase: every key and timestamp of the thread's rows is requested before anything depends on one
+    // (the kernel is bound by the latency of these loads) ----
+    long long k[P1_RPT], v[P1_RPT];
+    uint32_t rr[P1_RPT];  // bucket | rank inside the tile's bucket << 16
+    long long t[P1_RPT];
+#pragma unroll
+    for (int j = 0; j < P1_RPT; ++j) {
+      const int i = j * P1_THREADS + tid;
+      k[j] = 0;
+      t[j] = -1;
+      if (i < cnt) {
+        k[j] = __ldcs(kcol + i);
+        t[j] = __ldcs(tcol + i);
+      }
+    }
+    // The tile's pane = the pane of its first row (thread 0's first load: no separate round trip).  Tiles are contiguous
+    // in arrival order, so all but the tiles at a pane boundary hold one pane; rows of any other pane (and every row of
+    // a tile whose first row is late) take the direct path below.
     if (tid == 0) {
-      const long long t0 = __ldg(tcol);
+      const long long t0 = t[0];
       uint64_t q0 = ~0ull;
       if (t0 >= 0) {
         q0 = sd.div((uint64_t)t0);
@@ -164,7 +181,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
       }
       s_tile_q = q0;
     }
-    __syncthreads();
+    __syncthreads();  // also: everybody has left the previous tile's write-out (reorder / rid / gdelta are free)
     const uint64_t tq = s_tile_q;
     int psel = -1;
 #pragma unroll
@@ -172,23 +189,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
       if (tq == tp.fast_q[f] && tq != ~0ull) psel = f;
     unsigned long long* fpane = psel >= 0 ? tp.fast_ptr[psel] : nullptr;
     const uint32_t fslot = psel >= 0 ? tp.fast_slot[psel] : 0u;
-
-    // ---- load phase: every key and timestamp of the thread's 16 rows is requested before anything depends on one
-    // (the kernel is bound by the latency of these loads: 32 independent 8-byte loads per thread in flight) ----
-    long long k[P1_RPT], v[P1_RPT];
-    uint32_t rr[P1_RPT];  // bucket | rank inside the tile's bucket << 16
     {
-      long long t[P1_RPT];
-#pragma unroll
-      for (int j = 0; j < P1_RPT; ++j) {
-        const int i = j * P1_THREADS + tid;
-        k[j] = 0;
-        t[j] = -1;
-        if (i < cnt) {
-          k[j] = __ldcs(kcol + i);
-          t[j] = __ldcs(tcol + i);
-        }
-      }
       // ---- window-assign (K1) + late filter (K7) as ONE range test against the tile's pane: a row is on the fast
       // path iff its timestamp lies in [pane start, pane start + slide) -- that excludes late rows (the tile's pane
       // is not late), pre-epoch rows and rows of other panes, which all go through `off_path_row` ----
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
 #pragma unroll
     for (int x = 0; x < BPT; ++x) {
       c[x] = hist[BPT * tid + x];
+      hist[BPT * tid + x] = 0;  // for the next tile (its ranking starts two barriers from here)
       tsum += c[x];
     }
     uint32_t incl = tsum;
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
         }
       }
     }
-    __syncthreads();
+    // (no barrier here: the next tile's first barrier comes before anything of this tile's staging is overwritten)
   }
 
   // bookkeeping counters: warp reduce -> shared -> the last warp of the block publishes
@@ -484,9 +486,13 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
 
   // work item = (bucket, slice): the bucket's lookup table is built once and serves the bucket's regions of all the
   // launch's fast panes
-  const uint32_t n_work = NB * tp.slices;
+  const uint32_t head_work = tp.tail_first * tp.slices;
+  const uint32_t n_work = head_work + (NB - tp.tail_first) * tp.tail_slices;
   for (uint32_t work = blockIdx.x; work < n_work; work += gridDim.x) {
-    const uint32_t b = work / tp.slices, slice = work % tp.slices;
+    const bool tail = work >= head_work;
+    const uint32_t n_slices = tail ? tp.tail_slices : tp.slices;
+    const uint32_t b = tail ? tp.tail_first + (work - head_work) / n_slices : work / n_slices;
+    const uint32_t slice = tail ? (work - head_work) % n_slices : work % n_slices;
     unsigned n_reg[TP_NP];
     unsigned n_any = 0;
 #pragma unroll
@@ -502,8 +508,8 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
     unsigned n = 0, my_chunks = 0;
     auto select = [&](int f) {
       const unsigned chunks_all = (n_reg[f] + P2_CH - 1) / P2_CH;
-      const unsigned c_lo = (unsigned)((unsigned long long)chunks_all * slice / tp.slices);
-      const unsigned c_hi = (unsigned)((unsigned long long)chunks_all * (slice + 1) / tp.slices);
+      const unsigned c_lo = (unsigned)((unsigned long long)chunks_all * slice / n_slices);
+      const unsigned c_hi = (unsigned)((unsigned long long)chunks_all * (slice + 1) / n_slices);
       const unsigned r_lo = c_lo * P2_CH, r_hi = min(c_hi * P2_CH, n_reg[f]);
       rows = tp.part + (size_t)(f * NB + b) * tp.cap + r_lo;
       n = r_hi > r_lo ? r_hi - r_lo : 0u;
@@ -561,7 +567,7 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
             slo[i] = 0;
             shi[i] = 0;
             flushed += c;
-            if (tp.slices == 1) {  // the block owns the bucket's ids of this pane for the whole launch
+            if (n_slices == 1) {  // the block owns the bucket's ids of this pane for the whole launch
               prow[i] += c;
               if (NV > 0) psum[i] += sum;
             } else {

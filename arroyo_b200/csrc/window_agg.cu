@@ -1836,7 +1836,21 @@ void WindowAggOp::launch_two_pass(IngestParams& p, uint64_t rows, long long tile
     two_pass_attr_set_ = true;
   }
   const int grid1 = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)num_sms_ * P1_BLOCKS_PER_SM));
-  const int grid2 = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)n_buckets_ * tp.slices, (uint32_t)num_sms_ * P2_BLOCKS_PER_SM));
+  // Blocks take work items round-robin.  With one item per bucket the last round is ragged (1024 buckets over 296
+  // blocks: the fourth round keeps 136 blocks busy and 160 idle for a whole bucket); cutting the buckets of that round
+  // into slices turns it into a short round of part-buckets (each slice builds the bucket's table again).
+  const uint32_t max_blocks = (uint32_t)num_sms_ * P2_BLOCKS_PER_SM;
+  tp.tail_first = (uint32_t)n_buckets_;
+  tp.tail_slices = 1;
+  if (tp.slices == 1 && n_buckets_ > max_blocks && rows / n_buckets_ >= 2048) {
+    const uint32_t rest = (uint32_t)(n_buckets_ % max_blocks);
+    if (rest && max_blocks / rest >= 2) {
+      tp.tail_first = (uint32_t)n_buckets_ - rest;
+      tp.tail_slices = std::min<uint32_t>(max_blocks / rest, 4);
+    }
+  }
+  const uint32_t n_work = tp.tail_first * tp.slices + ((uint32_t)n_buckets_ - tp.tail_first) * tp.tail_slices;
+  const int grid2 = (int)std::max<uint32_t>(1, std::min<uint32_t>(n_work, max_blocks));
   if (n_vals_ == 0) {
     part_kernel<0, 0><<<grid1, P1_THREADS, P1_SMEM, stream_>>>(p, tp);
     AB_CUDA(cudaGetLastError());

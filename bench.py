@@ -73,9 +73,10 @@ def parse():
     ap.add_argument("--no-direct", action="store_true", help="accepted and ignored (every key is hashed since round 2)")
     ap.add_argument("--one-pass", action="store_true",
                     help="measurement knob: the one-pass ingest kernel (probe + REDs per row) instead of the two-pass ingest")
-    ap.add_argument("--local-chunk-log2", type=int, default=23,
-                    help="N>1, partials: rows per ingest launch of the local stage = 2^n; short launches let the owner "
-                         "stage's kernels in between")
+    ap.add_argument("--local-chunk-log2", type=int, default=24,
+                    help="N>1, partials: rows per ingest launch of the local stage = 2^n (one pane per launch: the two-pass "
+                         "ingest pays its per-launch table builds once; 2^23 measured 0.73 vs 0.53 ms per step, "
+                         "profiles/r02_partials_n1_c2*.json)")
     ap.add_argument("--python-exchange", action="store_true",
                     help="N>1, partials: the shuffle round through torch.distributed (device partitioner + all_gather + "
                          "all_to_all_single from Python) instead of the library's own round (csrc/exchange.cu: partition + "
