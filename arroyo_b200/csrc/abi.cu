@@ -354,6 +354,27 @@ int32_t arroyo_b200_op_handle_watermark_device(ArroyoB200Op* op, int64_t waterma
   });
 }
 
+int32_t arroyo_b200_op_handle_watermark_device_begin(ArroyoB200Op* op, int64_t watermark_ns) {
+  if (!op) return ARROYO_B200_INVALID_ARGUMENT;
+  WallTimer wt(op->host_watermark_ms);
+  return guarded(op, [&](OpBase* o) { o->begin_watermark_device(watermark_ns); });
+}
+
+int32_t arroyo_b200_op_handle_watermark_device_poll(ArroyoB200Op* op, ArroyoB200DeviceBatch* out, int64_t max_out,
+                                                    int64_t* n_out) {
+  if (n_out) *n_out = 0;
+  if (!op) return ARROYO_B200_INVALID_ARGUMENT;
+  WallTimer wt(op->host_watermark_ms);
+  return guarded(op, [&](OpBase* o) {
+    AB_REQUIRE(n_out != nullptr && (out != nullptr || max_out == 0), ARROYO_B200_INVALID_ARGUMENT, "null out");
+    std::vector<ArroyoB200DeviceBatch> v;
+    o->poll_watermark_device(&v);
+    AB_REQUIRE((int64_t)v.size() <= max_out, ARROYO_B200_RUNTIME, "more windows emitted than max_out");
+    for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
+    *n_out = (int64_t)v.size();
+  });
+}
+
 int32_t arroyo_b200_op_handle_checkpoint(ArroyoB200Op* op, int64_t watermark_ns, ArroyoB200Batches* state_out) {
   if (state_out) memset(state_out, 0, sizeof *state_out);
   return guarded(op, [&](OpBase* o) {

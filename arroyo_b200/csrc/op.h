@@ -40,6 +40,18 @@ class OpBase {
   BatchesPriv* pending_out = nullptr;
   virtual void begin_watermark(int64_t watermark) { handle_watermark(watermark, pending_out, nullptr); }
   virtual bool poll_watermark(bool /*block*/) { return true; }
+  // handle_watermark with device-resident output, split the same way: `begin` enqueues the emission and returns
+  // without waiting for the windows' row counts; `poll` waits for them and hands the windows out.  Operators without
+  // their own implementation emit in `begin`.
+  std::vector<ArroyoB200DeviceBatch> pending_dev;
+  virtual void begin_watermark_device(int64_t watermark) {
+    pending_dev.clear();
+    handle_watermark(watermark, nullptr, &pending_dev);
+  }
+  virtual void poll_watermark_device(std::vector<ArroyoB200DeviceBatch>* out) {
+    out->swap(pending_dev);
+    pending_dev.clear();
+  }
   virtual void stats(ArroyoB200Stats* out) = 0;
 };
 

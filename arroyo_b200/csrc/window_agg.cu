@@ -844,6 +844,8 @@ class WindowAggOp final : public OpBase {
   void submit() override;
   void begin_watermark(int64_t wm) override;
   bool poll_watermark(bool block) override;
+  void begin_watermark_device(int64_t wm) override;
+  void poll_watermark_device(std::vector<ArroyoB200DeviceBatch>* out) override;
   void stats(ArroyoB200Stats* out) override;
 
  private:
@@ -990,6 +992,16 @@ class WindowAggOp final : public OpBase {
   DevBuf d_emit_panes_, d_out_count_;
   unsigned int out_count_base_ = 0;
   PinnedBuf h_out_count_;
+  // deferred row counts (begin_watermark_device / poll_watermark_device): the emission is enqueued without waiting
+  // for its windows' row counts, which travel to these pinned slots; `pending_dev[i].n_rows` = -(slot + 1) until
+  // resolve_deferred() has read them
+  static constexpr int COUNT_SLOTS = 64;
+  PinnedBuf h_out_counts_;
+  bool defer_counts_ = false;
+  int count_slots_used_ = 0;
+  bool counts_pending_ = false;
+  cudaEvent_t counts_done_ = nullptr;
+  void resolve_deferred();
 
   ArroyoB200Stats st_{};
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> emit_events_;  // pooled: [0, emit_events_used_) are recorded
@@ -1196,6 +1208,7 @@ WindowAggOp::WindowAggOp(const ArroyoB200OpConfig& c) {
   d_out_count_.alloc(sizeof(unsigned int));
   AB_CUDA(cudaMemsetAsync(d_out_count_.p, 0, sizeof(unsigned int), stream_));
   h_out_count_.alloc(sizeof(unsigned int));
+  h_out_counts_.alloc(COUNT_SLOTS * sizeof(unsigned int));
   preallocate();
   AB_CUDA(cudaStreamSynchronize(stream_));
 }
@@ -1222,6 +1235,7 @@ void WindowAggOp::preallocate() {
 
 WindowAggOp::~WindowAggOp() {
   cudaSetDevice(device_);
+  if (counts_done_) cudaEventDestroy(counts_done_);
   // nothing may still be reading the input batches or writing output buffers when they are handed back
   if (copy_stream_) cudaStreamSynchronize(copy_stream_);
   if (out_stream_) cudaStreamSynchronize(out_stream_);
@@ -1407,7 +1421,7 @@ void WindowAggOp::grow_ids() {
   total_keys_host_ = c.n_keys;
   free_panes_.clear();
   pane_storage_ = std::move(new_storage);
-  out_sets_.clear();  // sized by id_cap_
+  // (output sets stay: a caller may still hold the last emission's device pointers; out_set() grows them on demand)
   part_cap_ = 0;      // the partition buffer is sized by the bucket count
   ring_dirty_ = true;
 }
@@ -2127,6 +2141,7 @@ void WindowAggOp::drain_deferred() {
 
 void WindowAggOp::flush() {
   set_device();
+  resolve_deferred();
   launch_pending();
   sync_all();
   poll_releases(true);
@@ -2235,6 +2250,12 @@ int64_t WindowAggOp::run_emit(const std::vector<const unsigned long long*>& bloc
   p.wend = wend;
   p.ts = ts;
   p.out_count = d_out_count_.as<unsigned int>();
+  const bool deferred = defer_counts_ && count_slots_used_ < COUNT_SLOTS;
+  if (defer_counts_) {
+    // nobody on the host knows the counter's value before the previous window's count has come back: restart it
+    AB_CUDA(cudaMemsetAsync(d_out_count_.p, 0, sizeof(unsigned int), stream_));
+    out_count_base_ = 0;
+  }
   p.out_base = out_count_base_;
   p.running = use_running ? running_ : nullptr;
   p.n_add = n_add;
@@ -2282,6 +2303,15 @@ int64_t WindowAggOp::run_emit(const std::vector<const unsigned long long*>& bloc
   }
   ++st_.kernel_launches;
   ++st_.emit_launches;
+  if (deferred) {
+    const int slot = count_slots_used_++;
+    AB_CUDA(cudaMemcpyAsync(h_out_counts_.as<unsigned int>() + slot, d_out_count_.p, sizeof(unsigned int),
+                            cudaMemcpyDeviceToHost, stream_));
+    counts_pending_ = true;
+    for (auto& d : dup_cols)  // row count unknown here: every id's worth
+      if (n_ids) AB_CUDA(cudaMemcpyAsync(d.second, d.first, (size_t)n_ids * 8, cudaMemcpyDeviceToDevice, stream_));
+    return -(int64_t)(slot + 1);
+  }
   AB_CUDA(cudaMemcpyAsync(h_out_count_.p, d_out_count_.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream_));
   AB_CUDA(cudaStreamSynchronize(stream_));
   const unsigned int out_now = *h_out_count_.as<unsigned int>();
@@ -2461,8 +2491,10 @@ void WindowAggOp::emit_window(int64_t a, int64_t b, size_t out_index, BatchesPri
   }
   zombies_.clear();
   if (n == 0) return;
-  st_.rows_out += (uint64_t)n;
-  ++st_.windows_out;
+  if (n > 0) {  // (a deferred count is accounted for when it is resolved)
+    st_.rows_out += (uint64_t)n;
+    ++st_.windows_out;
+  }
   if (out_host) {
     export_window(os, n, out_host);
   } else {
@@ -2486,6 +2518,7 @@ void WindowAggOp::emit_window(int64_t a, int64_t b, size_t out_index, BatchesPri
 
 void WindowAggOp::handle_watermark(int64_t wm, BatchesPriv* out_host, std::vector<ArroyoB200DeviceBatch>* out_dev) {
   set_device();
+  if (!defer_counts_) resolve_deferred();
   wait_outputs();
   launch_pending();
   sync_all();
@@ -2561,7 +2594,63 @@ void WindowAggOp::handle_watermark(int64_t wm, BatchesPriv* out_host, std::vecto
       if (h_pane_bins_[slot] == FREE_BIN && late_bin_ <= max_bin_seen_ + 2 * slide_) ensure_pane(late_bin_);
     }
   }
+  if (!defer_counts_) collect_emit_times();
+}
+
+// handle_watermark for device-resident output without its last host wait: the emit kernels, the counter resets and the
+// copies of the windows' row counts are enqueued and the call returns; poll_watermark_device (or any later entry
+// point that needs the operator's state settled) reads the counts.  What the caller does in between -- typically
+// handing over and submitting the next batches -- runs while the emission executes.
+void WindowAggOp::begin_watermark_device(int64_t wm) {
+  set_device();
+  resolve_deferred();
+  AB_REQUIRE(pending_dev.empty(), ARROYO_B200_INVALID_ARGUMENT,
+             "the previous emission has not been collected (handle_watermark_device_poll)");
+  if (!counts_done_) AB_CUDA(cudaEventCreateWithFlags(&counts_done_, cudaEventDisableTiming));
+  struct Flag {
+    bool& f;
+    explicit Flag(bool& x) : f(x) { f = true; }
+    ~Flag() { f = false; }
+  } flag(defer_counts_);
+  count_slots_used_ = 0;
+  try {
+    handle_watermark(wm, nullptr, &pending_dev);
+  } catch (...) {
+    if (counts_pending_) cudaEventRecord(counts_done_, stream_);
+    throw;
+  }
+  if (counts_pending_) AB_CUDA(cudaEventRecord(counts_done_, stream_));
+}
+
+// Reads the row counts of a deferred emission (idempotent); empty windows are dropped like the blocking path drops them.
+void WindowAggOp::resolve_deferred() {
+  if (!counts_pending_) return;
+  AB_CUDA(cudaEventSynchronize(counts_done_));
+  counts_pending_ = false;
+  const unsigned int* h = h_out_counts_.as<unsigned int>();
+  std::vector<ArroyoB200DeviceBatch> kept;
+  for (ArroyoB200DeviceBatch& d : pending_dev) {
+    if (d.n_rows < 0) {
+      const int slot = (int)(-d.n_rows - 1);
+      d.n_rows = (int64_t)h[slot];
+      if (d.n_rows) {
+        st_.rows_out += (uint64_t)d.n_rows;
+        ++st_.windows_out;
+      }
+    }
+    if (d.n_rows) kept.push_back(d);
+  }
+  pending_dev.swap(kept);
+  if (count_slots_used_ > 0) out_count_base_ = h[count_slots_used_ - 1];  // the counter's value after its last restart
+  count_slots_used_ = 0;
   collect_emit_times();
+}
+
+void WindowAggOp::poll_watermark_device(std::vector<ArroyoB200DeviceBatch>* out) {
+  set_device();
+  resolve_deferred();
+  out->swap(pending_dev);
+  pending_dev.clear();
 }
 
 // Adds up the emit kernels' CUDA-event times (FLAG_PROFILE); the events go back to the pool.
@@ -2578,6 +2667,7 @@ void WindowAggOp::collect_emit_times() {
 
 void WindowAggOp::handle_checkpoint(int64_t wm, BatchesPriv* out) {
   set_device();
+  resolve_deferred();
   wait_outputs();
   launch_pending();
   sync_all();
@@ -2743,6 +2833,8 @@ void WindowAggOp::on_start(ArrowArray* state, ArrowSchema* schemas, int64_t n, i
 }
 
 void WindowAggOp::stats(ArroyoB200Stats* out) {
+  set_device();
+  resolve_deferred();  // an outstanding emission's windows are counted once their row counts are in
   st_.n_keys = keyed_ ? total_keys_host_ : 0;
   st_.rows_late = last_counters_.late_rows;
   *out = st_;

@@ -116,6 +116,9 @@ SYMBOLS = [
                                                C.POINTER(Batches), C.POINTER(C.c_int64)]),
     ("arroyo_b200_op_handle_watermark_device", C.c_int32, [_VP, C.c_int64, C.POINTER(DeviceBatch), C.c_int64,
                                                            C.POINTER(C.c_int64)]),
+    ("arroyo_b200_op_handle_watermark_device_begin", C.c_int32, [_VP, C.c_int64]),
+    ("arroyo_b200_op_handle_watermark_device_poll", C.c_int32, [_VP, C.POINTER(DeviceBatch), C.c_int64,
+                                                                C.POINTER(C.c_int64)]),
     ("arroyo_b200_op_handle_checkpoint", C.c_int32, [_VP, C.c_int64, C.POINTER(Batches)]),
     ("arroyo_b200_op_on_close", C.c_int32, [_VP, C.c_int32, C.POINTER(Batches)]),
     ("arroyo_b200_op_handle_tick", C.c_int32, [_VP, C.POINTER(Batches)]),

@@ -307,6 +307,19 @@ class _WindowAggregate(_NativeOperator):
         _check(self._lib, self._h, st)
         return [(out[i].n_rows, [out[i].cols[c] for c in range(out[i].n_cols)]) for i in range(n.value)]
 
+    def handle_watermark_device_begin(self, wm: int):
+        """First half of handle_watermark_device: the emission is enqueued, its row counts are not awaited."""
+        _check(self._lib, self._h, self._lib.arroyo_b200_op_handle_watermark_device_begin(self._h, clamp_watermark(wm)))
+
+    def handle_watermark_device_poll(self, max_out: int = 64):
+        """Second half: the windows of the outstanding emission, list of (n_rows, [device pointers])."""
+        out = getattr(self, "_dev_out", None)
+        if out is None or len(out) < max_out:
+            out = self._dev_out = (ffi.DeviceBatch * max_out)()
+        n = C.c_int64(0)
+        _check(self._lib, self._h, self._lib.arroyo_b200_op_handle_watermark_device_poll(self._h, out, max_out, C.byref(n)))
+        return [(out[i].n_rows, [out[i].cols[c] for c in range(out[i].n_cols)]) for i in range(n.value)]
+
     def handle_checkpoint(self, barrier, ctx: OperatorContext, collector: Collector):
         if not self.created:
             return

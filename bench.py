@@ -467,23 +467,46 @@ def device_resident(args, torch, native, ffi, local, panes, W, K, rows, collect=
     rows_out = 0
     sums = {}
 
+    outstanding = False
+
+    def gather():
+        # the windows of the outstanding emission (arroyo_b200_op_handle_watermark_device_poll)
+        nonlocal rows_out, outstanding
+        if not outstanding:
+            return
+        outstanding = False
+        emitted = op.handle_watermark_device_poll()
+        for n, _ in emitted:
+            rows_out += n
+        if collect:
+            for ws, we, n, cnt, sm, av in window_checksums(torch, device, emitted):
+                sums[ws] = (we, n, cnt, sm, av)
+
     def step(p):
-        nonlocal rows_out
+        # handle_watermark as the begin / poll pair: the emission is enqueued, the next batches are handed over and
+        # submitted behind it, and only then are the emitted windows' row counts read -- the device never idles while
+        # the host goes round (with `--sync-emit`: the blocking call, one round trip more per step)
+        nonlocal rows_out, outstanding
         for cols, nrows, wm in plans[p]:
             op.process_device_batches(cols, nrows, 3)
-            if wm is not None:
-                emitted = op.handle_watermark_device(wm)
-                for n, _ in emitted:
-                    rows_out += n
-                if collect:
-                    for ws, we, n, cnt, sm, av in window_checksums(torch, device, emitted):
-                        sums[ws] = (we, n, cnt, sm, av)
+            if wm is None:
+                continue
+            if args.sync_emit:
+                outstanding = True
+                op.handle_watermark_device_begin(wm)
+                gather()
+                continue
+            op.submit()
+            gather()
+            op.handle_watermark_device_begin(wm)
+            outstanding = True
 
     sampler = ClockSampler(local)
     if not collect:
         sampler.start()
     for p in range(W):
         step(p)
+    gather()
     op.flush()
     torch.cuda.synchronize()
     st0 = op.stats()
@@ -493,6 +516,7 @@ def device_resident(args, torch, native, ffi, local, panes, W, K, rows, collect=
     e0.record()
     for p in range(W, W + K):
         step(p)
+    gather()
     op.flush()
     e1.record()
     torch.cuda.synchronize()

@@ -294,9 +294,12 @@ def test_checkpoint_restore_round_trip(G):
     assert_same(want, got, float_cols=("avg",))
 
 
-def test_device_resident_batches_and_device_output(G):
+@pytest.mark.parametrize("split", [False, True])
+def test_device_resident_batches_and_device_output(G, split):
     """process_device_batch / handle_watermark_device (the chaining + benchmark path) give the same
-    windows as the host path."""
+    windows as the host path -- with the blocking call, and with the begin / poll pair (row counts read one
+    emission late, the next batches handed over and submitted in between; the final watermark emits several
+    windows in one emission)."""
     import torch
     import arroyo_b200 as ab
     from arroyo_b200 import operators as native
@@ -330,9 +333,22 @@ def test_device_resident_batches_and_device_output(G):
         op.process_device_batch([t.data_ptr() for t in dev], b.num_rows)
         wm = gen.on_batch(int(b[O.TIMESTAMP].min()), int(b[O.TIMESTAMP].max()))
         if wm is not None:
-            collect(op.handle_watermark_device(wm))
-    collect(op.handle_watermark_device(ab.FINAL_WATERMARK))
+            if split:
+                op.submit()
+                collect(op.handle_watermark_device_poll())  # the previous emission (nothing the first time)
+                op.handle_watermark_device_begin(wm)
+            else:
+                collect(op.handle_watermark_device(wm))
+    if split:
+        collect(op.handle_watermark_device_poll())
+        op.handle_watermark_device_begin(ab.FINAL_WATERMARK)
+        st = op.stats()  # settles the outstanding emission without consuming it
+        collect(op.handle_watermark_device_poll())
+        assert collect(op.handle_watermark_device_poll()) is None and st["rows_out"] >= 0
+    else:
+        collect(op.handle_watermark_device(ab.FINAL_WATERMARK))
     assert_same(want, got, float_cols=("avg",))
+    assert op.stats()["rows_out"] == sum(b.num_rows for b in got)
 
 
 @pytest.mark.parametrize("join_type", ["inner", "left", "right", "full"])
