@@ -588,14 +588,28 @@ def _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, pane
     rows_out = 0
     sums = {}
 
-    def emit(eff):
-        nonlocal rows_out
-        emitted = owner_op.handle_watermark_device(eff)
+    outstanding = False
+
+    def gather():
+        # the owner stage's outstanding emission (arroyo_b200_op_handle_watermark_device_poll)
+        nonlocal rows_out, outstanding
+        if not outstanding:
+            return
+        outstanding = False
+        emitted = owner_op.handle_watermark_device_poll()
         for n, _ in emitted:
             rows_out += n
         if collect:
             for ws, we, n, cnt, sm, av in B.window_checksums(torch, device, emitted):
                 sums[ws] = (we, n, cnt, sm, av)
+
+    def emit(eff):
+        # begin / poll: the owner's emission is enqueued and its row counts are read one emission late, so the thread
+        # that runs the shuffle edge goes straight on to the next round
+        nonlocal outstanding
+        gather()
+        owner_op.handle_watermark_device_begin(eff)
+        outstanding = True
 
     native_ex = None
     if plan is not None and not args.sync_plan and getattr(args, "native_exchange", False):
@@ -655,6 +669,7 @@ def _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, pane
         step(p)
     if pipe is not None:
         pipe.drain()
+    gather()
     owner_op.flush()
     torch.cuda.synchronize()
     dist.barrier()
@@ -672,6 +687,7 @@ def _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, pane
         step(p)
     if pipe is not None:
         pipe.drain()
+    gather()
     owner_op.flush()
     if local_op is not None:
         local_op.flush()
