@@ -86,6 +86,14 @@ def parse():
     ap.add_argument("--sync-plan", action="store_true",
                     help="N>1, partials: run the local stage, the shuffle and the owner stage in sequence on one host "
                          "thread instead of as a two-stage pipeline")
+    ap.add_argument("--workload", default="sliding", choices=["sliding", "join", "session"],
+                    help="sliding = the headline (BASELINE configs[2]); join = configs[3] (q8-shaped windowed hash join "
+                         "behind two key-hash shuffles); session = configs[4] (session windows behind a key-hash shuffle): "
+                         "bench_workloads.py")
+    ap.add_argument("--join-persons-log2", type=int, default=21, help="--workload join: persons per GPU and window = 2^n")
+    ap.add_argument("--join-auctions-log2", type=int, default=23, help="--workload join: auctions per GPU and window = 2^n")
+    ap.add_argument("--session-keys", type=int, default=10_000_000, help="--workload session: keys per GPU")
+    ap.add_argument("--session-rows-log2", type=int, default=22, help="--workload session: rows per GPU and step = 2^n")
     ap.add_argument("--shuffle", default="partials", choices=["partials", "rows"],
                     help="N>1: what crosses the all-to-all (per-pane partial aggregates, or raw rows)")
     args = ap.parse_args()
@@ -806,9 +814,35 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_reference_workload(args):
+    """--impl reference --workload join | session: the C restatement of the operator on the host cores (rank 0)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import bench_workloads as BW
+    world = max(1, args.gpus)
+    if args.workload == "join":
+        v, cores, sample = BW.cpu_join(1 << args.join_persons_log2, 1 << args.join_auctions_log2, world, budget_s=60.0)
+        metric = "input rows/sec windowed hash-join (Nexmark q8 shape)"
+    else:
+        v, cores, sample = BW.cpu_session(args.session_keys, 1 << args.session_rows_log2, world, budget_s=60.0)
+        metric = "rows/sec session-window aggregate (5 s gap)"
+    print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "rows/s", "n_gpus": args.gpus,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+                      "config": {"workload": args.workload, "n_gpus": world},
+                      "cpu_baseline": {"value": v, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
+                      "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}), flush=True)
+
+
 def main():
     args = parse()
-    if args.impl == "reference":
+    if args.workload != "sliding":
+        if args.impl == "reference":
+            run_reference_workload(args)
+        else:
+            import bench_workloads
+            bench_workloads.run(args, sys.modules[__name__])
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
