@@ -331,10 +331,10 @@ def _run_session(torch, dist, rank, world, local, device, n_keys, srows, warm, s
 
 
 def verify_session(torch, dist, rank, world, local, device, seed=11):
-    """The N-GPU plan on 14 one-second steps of 4096 rows per GPU (2000 keys per GPU) plus the end-of-data watermark,
+    """The N-GPU plan on 14 one-second steps of 4096 rows per GPU (20 000 keys per GPU) plus the end-of-data watermark,
     against a single-process simulation of the same world x world topology with the numpy oracle's session operator
     (every sender's block is its own batch, senders in rank order, watermarks min-merged per owner)."""
-    n_keys, srows, n_steps = 2000, 4096, 14
+    n_keys, srows, n_steps = 20_000, 4096, 14  # a key sees a row every ~5 steps: gaps on both sides of the 5-s session gap
     _, _, sums, _ = _run_session(torch, dist, rank, world, local, device, n_keys, srows, n_steps, 0, seed, collect=True,
                                  final=True)
     t = torch.tensor([sum(n for n, _ in sums), 0], dtype=torch.int64, device=device)

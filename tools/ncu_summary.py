@@ -3,6 +3,8 @@
 
   python tools/ncu_summary.py launches gpurun_out/launches.csv  > profiles/<name>_launches.txt
   python tools/ncu_summary.py full gpurun_out/prof.ncu-rep [kernel-regex] > profiles/<name>_full.json
+  python tools/ncu_summary.py traffic gpurun_out/prof.ncu-rep <rows per launch> "<source note>" > profiles/ingest_traffic.json
+      (DRAM bytes per input row over every kernel of the capture = one ingest launch: part_kernel + agg_kernel)
 """
 import csv
 import io
@@ -52,6 +54,14 @@ KEYS = [
     "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "l1tex__throughput.avg.pct_of_peak_sustained_active", "sm__cycles_active.avg", "sm__cycles_elapsed.avg",
+    "smsp__inst_executed_op_shared_atom.sum", "launch__shared_mem_per_block_dynamic",
 ]
 
 
@@ -72,8 +82,32 @@ def full(path, pattern=None):
     print(json.dumps(out, indent=1))
 
 
+def traffic(path, rows_per_launch, source):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    kernels, total, us = [], 0.0, 0.0
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        b = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            b += float(d[k].replace(",", "")) * scale[units[hdr.index(k)]]
+        t = float(d["gpu__time_duration.sum"].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}[units[hdr.index("gpu__time_duration.sum")]]
+        name = re.sub(r"\(.*", "", d["Kernel Name"]).replace("void ", "")
+        kernels.append({"kernel": name, "dram_bytes": b, "us_under_ncu": round(t, 1)})
+        total += b
+        us += t
+    print(json.dumps({"kernel": "ingest = " + " + ".join(k["kernel"].split("::")[-1].split("<")[0] for k in kernels),
+                      "dram_bytes_per_row": total / rows_per_launch, "dram_bytes_per_launch": total,
+                      "rows_per_launch": rows_per_launch, "algorithmic_bytes_per_launch": 24 * rows_per_launch,
+                      "kernels": kernels, "kernel_us_under_ncu": round(us, 1), "source": source}, indent=1))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2], int(sys.argv[3]), sys.argv[4])
     else:
         full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
