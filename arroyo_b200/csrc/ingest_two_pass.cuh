@@ -66,9 +66,9 @@ struct TwoPassParams {
   uint32_t tail_slices;                // work items is made of part-buckets, so that it is short instead of ragged
 };
 
-constexpr size_t P1_SMEM = (size_t)P1_TILE * 16 + (size_t)P1_TILE * 2 + (size_t)P1_NR * 12;
-constexpr size_t P2_SMEM = (size_t)4096 * 12 + (size_t)BD_CAPB * 12 + (size_t)P2_NW * P2_NST * P2_CH * 16 +
-                           (size_t)(P2_NW * P2_NST + 1) * 8;  // 4096 = P2_HS (lookup table: key 8 + tag 2 + index 2 bytes per slot)
+constexpr size_t P1_SMEM = (size_t)P1_TILE * 16 + (size_t)P1_NR * 12;
+constexpr size_t P2_SMEM = (size_t)4096 * 11 + (size_t)BD_CAPB * 12 + (size_t)P2_NW * P2_NST * P2_CH * 16 +
+                           (size_t)(P2_NW * P2_NST + 1) * 8;  // 4096 = P2_HS (lookup table: key 8 + tag 1 + index 2 bytes per slot)
 
 // A row that left the fast path after window assignment: accumulate it directly (global lookup + REDs).  `q` is its
 // pane number; the pane block is `pane`, its ring slot `slot`.  Rows that cannot get an id are deferred with the pane's
@@ -121,8 +121,9 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
                                                                             const __grid_constant__ TwoPassParams tp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Rec* reorder = reinterpret_cast<Rec*>(smem_raw);                               // [P1_TILE]
-  uint16_t* rid = reinterpret_cast<uint16_t*>(smem_raw + (size_t)P1_TILE * 16);  // [P1_TILE] bucket of each staged record
-  uint32_t* hist = reinterpret_cast<uint32_t*>(rid + P1_TILE);                   // [P1_NR] rows per bucket in the tile
+  // (a staged record's bucket is re-derived from its key at write-out: two multiplies instead of a 2-byte shared store
+  // and load per row -- shared-memory wavefronts are what this kernel runs out of)
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)P1_TILE * 16);  // [P1_NR] rows per bucket in the tile
   uint32_t* toff = hist + P1_NR;                                                 // [P1_NR] start of the bucket's run in `reorder`
   uint32_t* gdelta = toff + P1_NR;                                               // [P1_NR] region position - tile position
   __shared__ uint32_t s_wsum[P1_NWARP];
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
       }
       s_tile_q = q0;
     }
-    __syncthreads();  // also: everybody has left the previous tile's write-out (reorder / rid / gdelta are free)
+    __syncthreads();  // also: everybody has left the previous tile's write-out (reorder / gdelta are free)
     const uint64_t tq = s_tile_q;
     int psel = -1;
 #pragma unroll
@@ -267,7 +268,6 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
       if (r != NO_REGION) {
         const uint32_t pos = toff[r] + (rr[j] >> 16);
         reorder[pos] = Rec{k[j], v[j]};
-        rid[pos] = (uint16_t)r;
       }
     }
     {
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(P1_THREADS, P1_BLOCKS_PER_SM) part_kernel(cons
       Rec* out = tp.part + (size_t)max(psel, 0) * NB * tp.cap;
       for (uint32_t i = tid; i < n_on; i += P1_THREADS) {
         const Rec rec = reorder[i];
-        const uint32_t r = rid[i];
+        const uint32_t r = bd_bucket(bd_hash(rec.key), NB);
         const uint32_t dst = gdelta[r] + i;
         if (dst < tp.cap) {
           out[(size_t)r * tp.cap + dst] = rec;
@@ -357,8 +357,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 //
 // The block builds its own lookup table of the bucket's keys in shared memory, from the bucket's id range of
 // `id_keys` (8 KB for a full bucket; the dictionary's own 32 KB slice is not read): P2_HS slots in groups of eight, and
-// per slot a 16-bit TAG (hash bits of the key), the key itself and its index inside the bucket.  A row's lookup is ONE
-// 16-byte load (the eight tags of its home group), a SIMD compare, and -- for the slot whose tag matches -- one 8-byte
+// per slot an 8-bit TAG (hash bits of the key), the key itself and its index inside the bucket.  A row's lookup is ONE
+// 8-byte load (the eight tags of its home group), a SIMD compare, and -- for the slot whose tag matches -- one 8-byte
 // load to confirm the key and one 2-byte load for the index: straight-line, ~25 instructions.  (With a probe loop every
 // warp has some lane that needs another round -- it was three quarters of the kernel's instructions -- and comparing
 // eight full keys costs four 16-byte loads and sixteen compares per row: profiles/r02_two_pass_c .. _f.)  At a
@@ -372,16 +372,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // word with a third atomic.
 // Records arrive through per-warp TMA rings (cp.async.bulk + mbarrier).
 constexpr int P2_HS = 4096;  // slots of the block's lookup table
-constexpr int P2_HG = 8;     // slots per group (their tags = one 16-byte load)
+constexpr int P2_HG = 8;     // slots per group (their tags = one 8-byte load)
 __device__ __forceinline__ uint32_t p2_hash(long long key) { return (uint32_t)(((uint64_t)key * 0xD6E8FEB86659FD93ull) >> 32); }
 __device__ __forceinline__ uint32_t p2_group(uint32_t h) { return (h >> 23) * P2_HG; }  // top 9 bits: 512 groups
-__device__ __forceinline__ uint32_t p2_tag(uint32_t h) {                               // 16 other bits; 0 = empty slot
-  const uint32_t t = (h >> 4) & 0xFFFFu;
+__device__ __forceinline__ uint32_t p2_tag(uint32_t h) {                               // 8 other bits; 0 = empty slot
+  const uint32_t t = (h >> 4) & 0xFFu;
   return t ? t : 1u;
 }
 
 // Inserts `key -> idx` into the block's table (home group first, then the following slots).
-__device__ __forceinline__ void p2_insert(unsigned long long* hk, unsigned short* htag, unsigned short* hidx, long long key,
+__device__ __forceinline__ void p2_insert(unsigned long long* hk, unsigned char* htag, unsigned short* hidx, long long key,
                                           uint32_t idx) {
   const uint32_t h = p2_hash(key);
   uint32_t s = p2_group(h);
@@ -390,7 +390,7 @@ __device__ __forceinline__ void p2_insert(unsigned long long* hk, unsigned short
     if (old == (unsigned long long)EMPTY_KEY || old == (unsigned long long)key) {
       hidx[s] = (unsigned short)idx;
       __threadfence_block();
-      htag[s] = (unsigned short)p2_tag(h);  // published last: a lookup that matches the tag finds key and index in place
+      htag[s] = (unsigned char)p2_tag(h);  // published last: a lookup that matches the tag finds key and index in place
       return;
     }
     s = (s + 1) & (P2_HS - 1);
@@ -425,7 +425,7 @@ __device__ __forceinline__ void reds_add(uint32_t a, uint32_t v) {
 
 // A key the home group's tags did not yield: it spilled into the following slots, or the block has not seen it yet
 // (out of line: rare, and its probe loops would sit in the middle of the hot loop).
-__device__ __noinline__ uint32_t agg_slow_lookup(const IngestParams& p, unsigned long long* hk, unsigned short* htag,
+__device__ __noinline__ uint32_t agg_slow_lookup(const IngestParams& p, unsigned long long* hk, unsigned char* htag,
                                                  unsigned short* hidx, uint32_t b, long long key, uint32_t g) {
   bool full = true;  // only a group without an empty slot can have spilled
   for (int x = 0; x < P2_HG; ++x) full = full && htag[g + x] != 0;
@@ -461,8 +461,8 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
                                                                            const __grid_constant__ TwoPassParams tp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned long long* hk = reinterpret_cast<unsigned long long*>(smem_raw);             // [P2_HS] keys
-  unsigned short* htag = reinterpret_cast<unsigned short*>(hk + P2_HS);                 // [P2_HS] tags
-  unsigned short* hidx = htag + P2_HS;                                                  // [P2_HS] index inside the bucket
+  unsigned char* htag = reinterpret_cast<unsigned char*>(hk + P2_HS);                   // [P2_HS] tags
+  unsigned short* hidx = reinterpret_cast<unsigned short*>(htag + P2_HS);               // [P2_HS] index inside the bucket
   uint32_t* scw = reinterpret_cast<uint32_t*>(hidx + P2_HS);  // [BD_CAPB] rows (low 16 bits) + signed high-word delta (high 16)
   uint32_t* slo = scw + BD_CAPB;                                                       // [BD_CAPB] sum, low word
   uint32_t* shi = slo + BD_CAPB;                                                       // [BD_CAPB] sum, high word (wide values only)
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
     // ---- build the bucket's lookup table ----
     for (int i = tid; i < P2_HS / 2; i += P2_NW * 32)
       reinterpret_cast<ulonglong2*>(hk)[i] = make_ulonglong2((unsigned long long)EMPTY_KEY, (unsigned long long)EMPTY_KEY);
-    for (int i = tid; i < P2_HS / 8; i += P2_NW * 32) reinterpret_cast<uint4*>(htag)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < P2_HS / 16; i += P2_NW * 32) reinterpret_cast<uint4*>(htag)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     {
       const unsigned nk = min(*(volatile const unsigned*)(p.dict.nkeys + b), (unsigned)BD_CAPB);
@@ -599,20 +599,19 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
             const long long key = (long long)(((unsigned long long)rr.y << 32) | rr.x);
             const uint32_t h = p2_hash(key);
             const uint32_t g = p2_group(h);
-            const uint32_t tag2 = p2_tag(h) * 0x10001u;  // the tag in both halves
-            // the eight tags of the home group: one 16-byte load.  A half-word of (tags ^ tag2) is zero where the tag
-            // matches; (x - 0x00010001) & ~x & 0x80008000 flags zero half-words (a flagged half-word above a matching one
-            // can be a false positive: every candidate is confirmed against the key anyway).
-            const uint4 tg = lds128(a_tag + g * 2);
-            const uint32_t x0 = tg.x ^ tag2, x1 = tg.y ^ tag2, x2 = tg.z ^ tag2, x3 = tg.w ^ tag2;
-            uint32_t m = (((x0 - 0x00010001u) & ~x0 & 0x80008000u) >> 15) | (((x1 - 0x00010001u) & ~x1 & 0x80008000u) >> 14) |
-                         (((x2 - 0x00010001u) & ~x2 & 0x80008000u) >> 13) | (((x3 - 0x00010001u) & ~x3 & 0x80008000u) >> 12);
-            // bit j: slot 2j (low half of word j); bit 16 + j: slot 2j + 1
+            const uint32_t tag4 = p2_tag(h) * 0x01010101u;  // the tag in all four bytes
+            // the eight tags of the home group: one 8-byte load.  A byte of (tags ^ tag4) is zero where the tag matches;
+            // (x - 0x01010101) & ~x & 0x80808080 flags zero bytes (a flagged byte above a matching one can be a false
+            // positive, and two keys in 255 share a tag: every candidate is confirmed against the key)
+            const unsigned long long tg = lds64(a_tag + g);
+            const uint32_t x0 = (uint32_t)tg ^ tag4, x1 = (uint32_t)(tg >> 32) ^ tag4;
+            uint32_t m = (((x0 - 0x01010101u) & ~x0 & 0x80808080u) >> 7) | (((x1 - 0x01010101u) & ~x1 & 0x80808080u) >> 3);
+            // bit 8j: slot j; bit 8j + 4: slot 4 + j
             uint32_t idx = ID_UNSET;
-            while (m) {  // almost always one candidate; a second one is a 16-bit tag collision inside the group
+            while (m) {  // almost always one candidate
               const uint32_t bit = (uint32_t)__ffs(m) - 1u;
               m &= m - 1;
-              const uint32_t sl = g + (((bit & 15u) << 1) | (bit >> 4));
+              const uint32_t sl = g + (bit >> 3) + (bit & 4u);
               if (lds64(a_hk + sl * 8) == (unsigned long long)key) {
                 idx = lds16(a_idx + sl * 2);
                 break;

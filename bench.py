@@ -94,6 +94,9 @@ def parse():
     ap.add_argument("--join-auctions-log2", type=int, default=23, help="--workload join: auctions per GPU and window = 2^n")
     ap.add_argument("--session-keys", type=int, default=10_000_000, help="--workload session: keys per GPU")
     ap.add_argument("--session-rows-log2", type=int, default=22, help="--workload session: rows per GPU and step = 2^n")
+    ap.add_argument("--session-split", type=int, default=1,
+                    help="--workload session, N = 1, measurement knob: hand every step over as this many batches that cover "
+                         "the same second, i.e. what an owner behind that many senders receives")
     ap.add_argument("--shuffle", default="partials", choices=["partials", "rows"],
                     help="N>1: what crosses the all-to-all (per-pane partial aggregates, or raw rows)")
     args = ap.parse_args()

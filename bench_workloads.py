@@ -276,7 +276,8 @@ def _session_cfg(mod):
                              window_index=1)
 
 
-def _run_session(torch, dist, rank, world, local, device, n_keys, srows, warm, steps, seed, collect=False, final=False):
+def _run_session(torch, dist, rank, world, local, device, n_keys, srows, warm, steps, seed, collect=False, final=False,
+                 split=1):
     import pyarrow as pa
 
     import arroyo_b200 as ab
@@ -290,6 +291,7 @@ def _run_session(torch, dist, rank, world, local, device, n_keys, srows, warm, s
     tsb = [torch.empty(srows, device=device, dtype=torch.int64) for _ in range(2)]
     rows_out = 0
     sums = []
+    keep = []
 
     def emit(wm):
         nonlocal rows_out
@@ -302,6 +304,13 @@ def _run_session(torch, dist, rank, world, local, device, n_keys, srows, warm, s
         ts = tsb[p & 1]
         torch.add(offs, T0 + p * S, out=ts)
         got, eff = edge.round([keys[p].data_ptr(), val.data_ptr(), ts.data_ptr()], srows, T0 + p * S - S)
+        if split > 1 and world == 1:
+            # measurement knob: what an owner behind `split` senders sees -- `split` batches per step that cover the same
+            # second (rows j, j + split, j + 2 split, ... of the step)
+            parts = [(keys[p][j::split].contiguous(), val[j::split].contiguous(), ts[j::split].contiguous()) for j in range(split)]
+            keep.append(parts)
+            del keep[:-2]
+            got = [([k.data_ptr(), v.data_ptr(), t.data_ptr()], k.numel()) for k, v, t in parts]
         for cols, n in got:  # one batch per sender, in sender order
             sop.process_device_batch(cols, n)
         if eff is not None:
@@ -466,7 +475,8 @@ def run(args, B):
     else:
         n_keys, srows, warm = args.session_keys, 1 << args.session_rows_log2, 14
         sampler.begin()
-        ms, rows_out, _, launches = _run_session(torch, dist, rank, world, local, device, n_keys, srows, warm, steps, 1)
+        ms, rows_out, _, launches = _run_session(torch, dist, rank, world, local, device, n_keys, srows, warm, steps, 1,
+                                                 split=args.session_split)
         sampler.end()
         rows_step = srows
         verify = verify_session(torch, dist, rank, world, local, device)
