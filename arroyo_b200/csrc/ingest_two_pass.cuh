@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
             const uint32_t tag4 = p2_tag(h) * 0x01010101u;  // the tag in all four bytes
             // the eight tags of the home group: one 8-byte load.  A byte of (tags ^ tag4) is zero where the tag matches;
             // (x - 0x01010101) & ~x & 0x80808080 flags zero bytes (a flagged byte above a matching one can be a false
-            // positive, and two keys in 255 share a tag: every candidate is confirmed against the key)
+            // positive: candidates are re-checked exactly; two keys in 255 share a tag: the key confirms)
             const unsigned long long tg = lds64(a_tag + g);
             const uint32_t x0 = (uint32_t)tg ^ tag4, x1 = (uint32_t)(tg >> 32) ^ tag4;
             uint32_t m = (((x0 - 0x01010101u) & ~x0 & 0x80808080u) >> 7) | (((x1 - 0x01010101u) & ~x1 & 0x80808080u) >> 3);
@@ -611,7 +611,11 @@ __global__ void __launch_bounds__(P2_NW * 32, P2_BLOCKS_PER_SM) agg_kernel(const
             while (m) {  // almost always one candidate
               const uint32_t bit = (uint32_t)__ffs(m) - 1u;
               m &= m - 1;
-              const uint32_t sl = g + (bit >> 3) + (bit & 4u);
+              const uint32_t j = (bit >> 3) + (bit & 4u);
+              // exact tag check first: a false positive may point at a slot whose insert is still in flight -- key
+              // already claimed, index not yet stored; only a published tag (written last) vouches for both
+              if ((uint32_t)((tg >> (8 * j)) & 0xFFull) != (tag4 & 0xFFu)) continue;
+              const uint32_t sl = g + j;
               if (lds64(a_hk + sl * 8) == (unsigned long long)key) {
                 idx = lds16(a_idx + sl * 2);
                 break;

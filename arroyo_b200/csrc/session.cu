@@ -628,6 +628,13 @@ class SessionOp final : public OpBase {
   // pools
   uint64_t node_cap_ = 0, row_cap_ = 0;
   DevBuf n_next_, n_start_, n_off_, n_len_, r_ts_, r_val_[SV];
+  // compaction copies the live nodes / rows into a second set of pools and swaps the sets; both sets and the scratch
+  // arrays persist (a cudaMalloc / cudaFree per step synchronises the device -- and, behind an NCCL edge, waits for the
+  // peers' progress: 145 ms per step at N = 2 before they were kept)
+  uint64_t sp_node_cap_ = 0, sp_row_cap_ = 0;
+  DevBuf sp_next_, sp_start_, sp_off_, sp_len_, sp_rts_, sp_rval_[SV];
+  DevBuf c_cn_, c_cr_, c_on_, c_orow_, c_tot_;
+  uint64_t c_cap_ = 0;
   DevBuf ctr_;
   PinnedBuf h_ctr_;
   // launch arena
@@ -1192,7 +1199,15 @@ void SessionOp::maybe_compact() {
   const uint64_t nodes = h[0], rows = h[1], dead_nodes = h[2], dead_rows = h[3];
   if (nodes < compact_min_ && rows < 4 * compact_min_) return;
   if (dead_nodes * 2 < nodes && dead_rows * 2 < rows) return;
-  DevBuf cn((size_t)n_keys_ * 4), cr((size_t)n_keys_ * 4), on((size_t)n_keys_ * 8), orow((size_t)n_keys_ * 8), tot(16);
+  if (c_cap_ < n_keys_) {
+    c_cap_ = std::max<uint64_t>(id_cap_, n_keys_);
+    c_cn_.alloc(c_cap_ * 4);
+    c_cr_.alloc(c_cap_ * 4);
+    c_on_.alloc(c_cap_ * 8);
+    c_orow_.alloc(c_cap_ * 8);
+    c_tot_.alloc(16);
+  }
+  DevBuf &cn = c_cn_, &cr = c_cr_, &on = c_on_, &orow = c_orow_, &tot = c_tot_;
   SessCtx c = ctx();
   live_count_kernel<<<grid_for(n_keys_, 128), 128, 0, stream_>>>(c, n_keys_, cn.as<unsigned int>(), cr.as<unsigned int>());
   AB_CUDA(cudaGetLastError());
@@ -1202,32 +1217,43 @@ void SessionOp::maybe_compact() {
   AB_CUDA(cudaMemcpyAsync(t, tot.p, 16, cudaMemcpyDeviceToHost, stream_));
   AB_CUDA(cudaStreamSynchronize(stream_));
   const uint64_t live_nodes = t[0], live_rows = t[1];
-  const uint64_t ncap = std::max<uint64_t>(2 * live_nodes + 16, 1 << 16), rcap = std::max<uint64_t>(2 * live_rows + 16, 1 << 16);
-  DevBuf nn(ncap * 4), ns(ncap * 8), no(ncap * 8), nl(ncap * 4), rt(rcap * 8), rv[SV];
-  CompactDst d{};
-  d.n_next = nn.as<int>();
-  d.n_start = ns.as<long long>();
-  d.n_off = no.as<long long>();
-  d.n_len = nl.as<int>();
-  d.r_ts = rt.as<long long>();
-  for (int v = 0; v < n_vals_; ++v) {
-    rv[v].alloc(rcap * 8);
-    d.r_val[v] = rv[v].as<long long>();
+  // the spare set takes the live entries; it is at least as large as the set in use, so a compaction allocates only
+  // when the live data itself has outgrown it
+  const uint64_t ncap = std::max<uint64_t>(std::max<uint64_t>(2 * live_nodes + 16, 1 << 16), node_cap_);
+  const uint64_t rcap = std::max<uint64_t>(std::max<uint64_t>(2 * live_rows + 16, 1 << 16), row_cap_);
+  if (sp_node_cap_ < ncap) {
+    sp_next_.alloc(ncap * 4);
+    sp_start_.alloc(ncap * 8);
+    sp_off_.alloc(ncap * 8);
+    sp_len_.alloc(ncap * 4);
+    sp_node_cap_ = ncap;
   }
+  if (sp_row_cap_ < rcap) {
+    sp_rts_.alloc(rcap * 8);
+    for (int v = 0; v < n_vals_; ++v) sp_rval_[v].alloc(rcap * 8);
+    sp_row_cap_ = rcap;
+  }
+  CompactDst d{};
+  d.n_next = sp_next_.as<int>();
+  d.n_start = sp_start_.as<long long>();
+  d.n_off = sp_off_.as<long long>();
+  d.n_len = sp_len_.as<int>();
+  d.r_ts = sp_rts_.as<long long>();
+  for (int v = 0; v < n_vals_; ++v) d.r_val[v] = sp_rval_[v].as<long long>();
   compact_copy_kernel<<<grid_for(n_keys_, 128), 128, 0, stream_>>>(c, d, n_keys_, on.as<unsigned long long>(),
                                                                   orow.as<unsigned long long>());
   AB_CUDA(cudaGetLastError());
   unsigned long long nc[4] = {live_nodes, live_rows, 0, 0};
   AB_CUDA(cudaMemcpyAsync(ctr_.p, nc, sizeof nc, cudaMemcpyHostToDevice, stream_));
   AB_CUDA(cudaStreamSynchronize(stream_));
-  n_next_ = std::move(nn);
-  n_start_ = std::move(ns);
-  n_off_ = std::move(no);
-  n_len_ = std::move(nl);
-  r_ts_ = std::move(rt);
-  for (int v = 0; v < n_vals_; ++v) r_val_[v] = std::move(rv[v]);
-  node_cap_ = ncap;
-  row_cap_ = rcap;
+  std::swap(n_next_, sp_next_);
+  std::swap(n_start_, sp_start_);
+  std::swap(n_off_, sp_off_);
+  std::swap(n_len_, sp_len_);
+  std::swap(r_ts_, sp_rts_);
+  for (int v = 0; v < n_vals_; ++v) std::swap(r_val_[v], sp_rval_[v]);
+  std::swap(node_cap_, sp_node_cap_);
+  std::swap(row_cap_, sp_row_cap_);
   st_.kernel_launches += 8;
 }
 
