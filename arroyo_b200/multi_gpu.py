@@ -549,7 +549,7 @@ def _e2e_partials(args, torch, dist, B, ab, native, rank, world, local, device, 
                     "-> host Arrow windows"}
 
 
-def _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, panes, W, K, collect=False):
+def _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, panes, W, K, collect=False, sampler=None):
     """One pass of the N-GPU plan over this rank's `panes`: W warm-up steps, K timed steps (CUDA events, max over
     ranks).  With `collect` every window this rank emits is reduced to checksums on the device (a verification pass;
     its time means nothing).  Returns a dict."""
@@ -662,9 +662,10 @@ def _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, pane
 
     step = step_partials if mode == "partials" else step_rows
     timed_op = local_op if mode == "partials" else owner_op
-    sampler = B.ClockSampler(local)
-    if rank == 0 and not collect:
-        sampler.start()
+    if sampler is None:
+        sampler = B.ClockSampler(local)
+        if rank == 0 and not collect:
+            sampler.start()
     for p in range(W):
         step(p)
     if pipe is not None:
@@ -782,9 +783,12 @@ def bench(args, torch, dist, rank, world, local, all_cpus=None):
     W, K = B.steady_warmup(args.warmup, extra=2), args.steps
     rows = args.rows_per_pane
     mode = args.shuffle
+    sampler = B.ClockSampler(local)  # started before the seconds of input generation: see bench.py::run_ours
+    if rank == 0:
+        sampler.start()
     gen_pane = B.make_generator(torch, device, rows, args.keys, args.dist, 42 + rank, args.keyspace)
     panes = [gen_pane(p) for p in range(W + K)]
-    res = _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, panes, W, K)
+    res = _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, panes, W, K, sampler=sampler)
     del panes
     ms, d = res["ms"], res["d"]
 
