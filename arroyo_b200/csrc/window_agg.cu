@@ -8,11 +8,16 @@
 //   K4 AggregateExec(Final)  K5 final projection (window struct, _timestamp)  K7 late-row filter
 //
 // Design:
-//   * one persistent key dictionary per operator: open addressing, 16-byte slots {key, dense id};
-//     keys recur in every pane, so after warm-up a row costs one read-only 16-byte probe (L2 hit).
+//   * one persistent key dictionary per operator (bdict.cuh): buckets of <= 1280 keys, open addressing inside the
+//     bucket, dense id = bucket * 1280 + index: a bucket's keys own a contiguous id range.  Keys recur in every
+//     pane, so after warm-up a row costs one read-only lookup.
 //   * one accumulator block per pane: dense SoA arrays indexed by id (rows, then one 64-bit
-//     accumulator per SUM / AVG / MIN / MAX).  A row = date_bin (one mulhi) + late test + probe +
-//     one RED per accumulator.  Nothing is sorted, gathered or materialised per batch.
+//     accumulator per SUM / AVG / MIN / MAX).  Nothing is sorted, gathered or materialised per batch.
+//   * ingest, large launches of COUNT / SUM / AVG plans (ingest_two_pass.cuh): rows are radix-partitioned by
+//     dictionary bucket (part_kernel), then each bucket is aggregated in shared memory against a lookup table of
+//     its keys, fed by per-warp TMA rings, and flushed to its contiguous id range of the pane (agg_kernel).
+//     Everything else (small launches, MIN / MAX / f64, partial-row inputs, hot-key streams, rows the two passes
+//     hand back): ingest_kernel, one pass -- date_bin (one mulhi) + late test + lookup + one RED per accumulator.
 //   * panes live in a ring indexed by (ts / slide) & (R - 1); the device table pane_bins[] says
 //     which bin a slot holds.  Rows whose pane is not resident (far future / before the ring) or
 //     whose key cannot get an id (dictionary full) are copied to a deferred buffer; the host grows

@@ -555,6 +555,7 @@ def _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, pane
     its time means nothing).  Returns a dict."""
     import pyarrow as pa
 
+    dog = _Watchdog(rank, f"the {world}-GPU plan (--shuffle {args.shuffle})")
     rows = panes[0][0].numel()
     nb = rows // B.BATCH_ROWS
     mins, maxs = [], []
@@ -610,6 +611,7 @@ def _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, pane
         gather()
         owner_op.handle_watermark_device_begin(eff)
         outstanding = True
+        dog.beat(f"owner stage emitted at watermark {eff}")
 
     native_ex = None
     if plan is not None and not args.sync_plan and getattr(args, "native_exchange", False):
@@ -660,7 +662,12 @@ def _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, pane
             else:
                 owner_op.flush()  # the receive buffers are reused by the next round
 
-    step = step_partials if mode == "partials" else step_rows
+    step_inner = step_partials if mode == "partials" else step_rows
+
+    def step(p):
+        step_inner(p)
+        dog.beat(f"local stage fed pane {p}")
+
     timed_op = local_op if mode == "partials" else owner_op
     if sampler is None:
         sampler = B.ClockSampler(local)
@@ -718,11 +725,47 @@ def _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, pane
         owner_op.close()
         part.close()
     torch.cuda.empty_cache()
+    dog.close()
     return {"ms": ms, "d": d, "launches": int(tot[0].item()), "rows_out": int(tot[1].item()), "sent": sent,
             "clocks": clocks, "sums": sums, "pipelined": pipe is not None, "rows_out_warm": rows_out_warm,
             "host_ms_per_step": host_ms,
             "owner_ms": {"ingest_ms": (so1["ingest_ms"] - so0["ingest_ms"]) / max(K, 1),
                          "emit_ms": (so1["emit_ms"] - so0["emit_ms"]) / max(K, 1)} if local_op is not None else None}
+
+
+class _Watchdog:
+    """Fail fast instead of hanging: a collective whose peer never arrives blocks for ever (and takes the other ranks
+    with it).  `beat()` is called from the step loop and the owner stage; if nothing beats for `limit_s` the process
+    says where it stood and exits -- the launcher then tears the job down."""
+
+    def __init__(self, rank, what, limit_s=240.0):
+        import threading
+        import time
+        self.rank, self.what, self.limit_s = rank, what, limit_s
+        self.last = time.monotonic()
+        self.note = "start"
+        self.stop = False
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def beat(self, note):
+        import time
+        self.last = time.monotonic()
+        self.note = note
+
+    def _run(self):
+        import os
+        import sys
+        import time
+        while not self.stop:
+            time.sleep(1.0)
+            if time.monotonic() - self.last > self.limit_s:
+                print(f"[arroyo_b200] rank {self.rank}: no progress for {self.limit_s:.0f} s in {self.what} "
+                      f"(last: {self.note}); giving up", file=sys.stderr, flush=True)
+                os._exit(124)
+
+    def close(self):
+        self.stop = True
 
 
 def _gather_window_sums(torch, dist, device, sums):
@@ -783,12 +826,9 @@ def bench(args, torch, dist, rank, world, local, all_cpus=None):
     W, K = B.steady_warmup(args.warmup, extra=2), args.steps
     rows = args.rows_per_pane
     mode = args.shuffle
-    sampler = B.ClockSampler(local)  # started before the seconds of input generation: see bench.py::run_ours
-    if rank == 0:
-        sampler.start()
     gen_pane = B.make_generator(torch, device, rows, args.keys, args.dist, 42 + rank, args.keyspace)
     panes = [gen_pane(p) for p in range(W + K)]
-    res = _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, panes, W, K, sampler=sampler)
+    res = _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, panes, W, K)
     del panes
     ms, d = res["ms"], res["d"]
 

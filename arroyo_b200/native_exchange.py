@@ -67,6 +67,17 @@ class NativeExchange:
         self._cols = (C.c_uint64 * (world * n_cols))()
         self._rows = (C.c_int64 * world)()
         self._wms = (C.c_int64 * world)()
+        # One throw-away round with a few rows for every destination, now, while the devices are quiet: NCCL sets its
+        # peer-to-peer connections up at the first send / receive between two ranks, and that set-up (allocations, IPC
+        # handles, a handshake per peer) should not run in the middle of the pipeline with every SM taken.  Nothing of
+        # it reaches an operator; no watermark is attached.
+        if world > 1:
+            n = int(min(max_rows, 64 * world))
+            dev = torch.device("cuda", device_index)
+            self._warm = [torch.arange(n, dtype=torch.int64, device=dev) * 0x1E3779B97F4A7C15 + rank for _ in range(n_cols)]
+            torch.cuda.synchronize(dev)
+            self.round_packed([t.data_ptr() for t in self._warm], None, n, None)
+            torch.cuda.synchronize(dev)
 
     def round_packed(self, col_ptrs, _counts, n_rows: int, watermark: Optional[int], more: bool = False):
         inp = (C.c_uint64 * self.n_cols)(*col_ptrs) if n_rows > 0 else None

@@ -13,16 +13,32 @@ one 10-s window (<= 1 Mi rows x 6 columns).
             handle_watermark_device of the C ABI); timed with CUDA events on the operator's stream
   e2e       the same through the reference-facing call with HOST buffers: pinned Arrow batches in via
             arroyo_b200_op_process_batch, emitted windows out as host Arrow batches
-  roofline  ingest kernel: 24 algorithmic bytes per input row / its CUDA-event time, against the
-            measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  roofline  the ingest (window-assign + partial aggregate: part_kernel + agg_kernel per launch): 24 algorithmic
+            bytes per input row / the CUDA-event time of the step's ingest launches, against the measured HBM
+            copy bandwidth (MEASURED_PEAKS.json); `traffic` = DRAM bytes from the committed ncu capture
+  verified  the windows of a second, identical pass over the panes the CPU baseline consumed equal the C
+            oracle's, checksum by checksum (rows out, sum COUNT, wrapping sum SUM bit-exact; sum AVG 1e-6);
+            a mismatch makes the script exit non-zero
   cpu_baseline / --impl reference
             the C restatement of the reference's algorithm (oracle/window_oracle.c, "port": the Rust
             reference cannot be built here) on all host cores, key-partitioned like the reference
 
 Multi-GPU (N > 1): one process per GPU; every rank ingests its own shard of the stream (seed 42 + rank),
-hash-partitions it on the device, exchanges the partitions with an NCCL all-to-all and aggregates the
-keys it owns (weak scaling: per-GPU input fixed).
+pre-aggregates it per pane, hash-partitions the partial rows on the device, exchanges them over NCCL (the
+library's own round: csrc/exchange.cu) and the owner of a key merges and emits (weak scaling: per-GPU
+input fixed; arroyo_b200/multi_gpu.py).  `--workload join | session`: BASELINE configs[3] / configs[4]
+(bench_workloads.py).
 """
+import os as _os
+
+if int(_os.environ.get("WORLD_SIZE", "1")) > 4:
+    # Two NCCL communicators live in every rank at N > 1 (torch.distributed's and the Shuffle edge's own,
+    # csrc/exchange.cu); all this job moves through collectives is an 80-byte control record per round, so NVLink SHARP
+    # (NVLS: multicast objects set up per communicator across the whole NVSwitch domain) buys nothing and is left out
+    # of the set-up on large boxes.  The one N = 8 attempt of round 2 did not get past its set-up within five minutes
+    # (cause not established: no GPU time was left to look); N <= 4 run with NCCL's defaults, as measured.
+    _os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+
 import argparse
 import ctypes as C
 import json
@@ -168,13 +184,20 @@ class ClockSampler:
         self.lines = []  # (arrival time, text)
         self.t0 = self.t1 = None
 
-    def start(self):
+    def start(self, wait_first_s=3.0):
+        """Starts the sampler and waits (bounded) for its first line: nvidia-smi needs ~0.1 s to print it -- longer than
+        the warm-up plus a 100-step timed region -- and from then on prints one every PERIOD_MS.  It is started right
+        before the warm-up, not earlier: polling through the job's set-up (allocations, NCCL initialisation) contends
+        with those calls for the driver."""
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                  "-lms", str(self.PERIOD_MS)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            deadline = time.perf_counter() + wait_first_s
+            while not self.lines and time.perf_counter() < deadline and self.proc.poll() is None:
+                time.sleep(0.005)
         except Exception:
             self.proc = None
 
@@ -575,13 +598,9 @@ def run_ours(args):
     W, K = steady_warmup(args.warmup), args.steps
     rows = args.rows_per_pane
     assert rows % BATCH_ROWS == 0
-    # nvidia-smi takes ~0.1 s to print its first sample -- longer than warm-up + a short timed region: started here,
-    # before the seconds of input generation, it is sampling every 5 ms by the time the timed region begins
-    sampler = ClockSampler(local)
-    sampler.start()
     gen_pane = make_generator(torch, device, rows, args.keys, args.dist, 42 + rank, args.keyspace)
     panes = [gen_pane(p) for p in range(W + K)]
-    ms, d, rows_out, clocks, _ = device_resident(args, torch, native, ffi, local, panes, W, K, rows, sampler=sampler)
+    ms, d, rows_out, clocks, _ = device_resident(args, torch, native, ffi, local, panes, W, K, rows)
     del panes
 
     value = K * rows / (ms * 1e-3)

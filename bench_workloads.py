@@ -95,7 +95,7 @@ def _join_inputs(torch, device, rank, world, n_p, n_a, seed):
     return pid, name, seller, auction, reserve
 
 
-def _run_join(torch, dist, rank, world, local, device, n_p, n_a, warm, steps, seed, collect=False):
+def _run_join(torch, dist, rank, world, local, device, n_p, n_a, warm, steps, seed, collect=False, sampler=None):
     import pyarrow as pa
 
     import arroyo_b200 as ab
@@ -149,6 +149,8 @@ def _run_join(torch, dist, rank, world, local, device, n_p, n_a, warm, steps, se
                 if collect:
                     sums.append(_checksum(torch, [outb[i].cols[c] for c in range(outb[i].n_cols)], outb[i].n_rows, device))
 
+    if sampler is not None:
+        sampler.start()  # after the set-up (operators, NCCL communicators), right before the warm-up
     for w in range(warm):
         step(w)
     torch.cuda.synchronize()
@@ -156,11 +158,15 @@ def _run_join(torch, dist, rank, world, local, device, n_p, n_a, warm, steps, se
         dist.barrier()
     rows_out = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler is not None:
+        sampler.begin()
     e0.record()
     for w in range(warm, warm + steps):
         step(w)
     e1.record()
     torch.cuda.synchronize()
+    if sampler is not None:
+        sampler.end()
     ms = e0.elapsed_time(e1) if steps else 0.0
     launches = jop.stats()["kernel_launches"]
     jop.close()
@@ -277,7 +283,7 @@ def _session_cfg(mod):
 
 
 def _run_session(torch, dist, rank, world, local, device, n_keys, srows, warm, steps, seed, collect=False, final=False,
-                 split=1):
+                 split=1, sampler=None):
     import pyarrow as pa
 
     import arroyo_b200 as ab
@@ -316,6 +322,8 @@ def _run_session(torch, dist, rank, world, local, device, n_keys, srows, warm, s
         if eff is not None:
             emit(eff)
 
+    if sampler is not None:
+        sampler.start()  # after the set-up (operator, NCCL communicator), right before the warm-up
     for p in range(warm):
         step(p)
     torch.cuda.synchronize()
@@ -323,11 +331,15 @@ def _run_session(torch, dist, rank, world, local, device, n_keys, srows, warm, s
         dist.barrier()
     rows_out = 0 if not collect else rows_out
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler is not None:
+        sampler.begin()
     e0.record()
     for p in range(warm, warm + steps):
         step(p)
     e1.record()
     torch.cuda.synchronize()
+    if sampler is not None:
+        sampler.end()
     ms = e0.elapsed_time(e1) if steps else 0.0
     if final:  # end of data: every open session leaves
         got, eff = edge.round(None, 0, ab.FINAL_WATERMARK)
@@ -458,15 +470,13 @@ def run(args, B):
         dist = dist_mod
     torch.cuda.set_stream(torch.cuda.Stream(device=device))
     steps = min(args.steps, 20)
-    sampler = B.ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler = B.ClockSampler(local) if rank == 0 else None
     if args.workload == "join":
         n_p, n_a, warm = 1 << args.join_persons_log2, 1 << args.join_auctions_log2, 3
-        sampler.begin()
-        ms, rows_out, _, launches = _run_join(torch, dist, rank, world, local, device, n_p, n_a, warm, steps, 1)
-        sampler.end()
+        ms, rows_out, _, launches = _run_join(torch, dist, rank, world, local, device, n_p, n_a, warm, steps, 1,
+                                              sampler=sampler)
         rows_step = n_p + n_a
+        clocks = sampler.stop() if sampler is not None else None  # (before the verification pass sets its own edges up)
         verify = verify_join(torch, dist, rank, world, local, device)
         metric = "input rows/sec windowed hash-join (Nexmark q8 shape)"
         workload = (f"BASELINE configs[3]: q8-shaped 30-s tumbling person x auction join on person id = seller; every GPU's "
@@ -474,11 +484,10 @@ def run(args, B):
         bytes_row = (24 * n_p + 32 * n_a) / rows_step
     else:
         n_keys, srows, warm = args.session_keys, 1 << args.session_rows_log2, 14
-        sampler.begin()
         ms, rows_out, _, launches = _run_session(torch, dist, rank, world, local, device, n_keys, srows, warm, steps, 1,
-                                                 split=args.session_split)
-        sampler.end()
+                                                 split=args.session_split, sampler=sampler)
         rows_step = srows
+        clocks = sampler.stop() if sampler is not None else None
         verify = verify_session(torch, dist, rank, world, local, device)
         metric = "rows/sec session-window aggregate (5 s gap)"
         workload = (f"BASELINE configs[4]: session windows, gap 5 s, SUM + COUNT, {n_keys} keys per GPU; every GPU's shard "
@@ -491,7 +500,6 @@ def run(args, B):
         dist.all_reduce(t)
         ms = float(mx[0].item())
         rows_out, launches = int(t[1].item()), int(t[2].item())
-    clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         os.sched_setaffinity(0, all_cpus)
         cpu = None
