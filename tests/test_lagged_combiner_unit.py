@@ -68,3 +68,27 @@ def test_owner_stage_failure_reaches_the_local_stage():
         for p in range(10):
             pipe.local_step(lambda: None, 100 + p)
         pipe.drain()
+
+
+def test_watchdog_ends_a_stalled_rank_and_leaves_a_progressing_one_alone():
+    """multi_gpu._Watchdog: a rank of the N > 1 plan that stops making progress (a collective whose peer never arrives)
+    says where it stood and exits with 124 instead of hanging until the launcher's limit."""
+    import os
+    import subprocess
+    import sys
+    import time
+
+    from arroyo_b200.multi_gpu import _Watchdog
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dog = _Watchdog(0, "a test", limit_s=1.5)
+    for i in range(4):
+        time.sleep(0.6)
+        dog.beat(f"step {i}")
+    dog.close()  # 2.4 s without firing: beats keep it quiet
+    code = ("import sys, time; sys.path.insert(0, %r)\n"
+            "from arroyo_b200.multi_gpu import _Watchdog\n"
+            "d = _Watchdog(3, 'the 8-GPU plan', limit_s=1.0); d.beat('local stage fed pane 7'); time.sleep(30)\n" % ROOT)
+    t0 = time.time()
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=25)
+    assert r.returncode == 124 and time.time() - t0 < 20
+    assert "rank 3" in r.stderr and "local stage fed pane 7" in r.stderr
