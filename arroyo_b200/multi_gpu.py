@@ -687,7 +687,8 @@ def _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, pane
         pipe.reset_times()
     rows_out_warm = rows_out
     rows_out = 0
-    sent0 = ex.bytes_sent
+    ex_used = native_ex if native_ex is not None else ex
+    sent0 = ex_used.bytes_sent
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.begin()
     e0.record()
@@ -713,7 +714,7 @@ def _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, pane
     launches = d["kernel_launches"] + (so1["kernel_launches"] - so0["kernel_launches"] if local_op is not None else 0)
     tot = torch.tensor([launches, rows_out, d["rows_in"]], dtype=torch.int64, device=device)
     dist.all_reduce(tot)
-    sent = ex.bytes_sent - sent0
+    sent = ex_used.bytes_sent - sent0
     host_ms = {k: round(1e3 * v / max(K, 1), 4) for k, v in pipe.times.items()} if pipe is not None else None
     if pipe is not None:
         pipe.close()

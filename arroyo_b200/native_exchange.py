@@ -44,7 +44,7 @@ class NativeExchange:
     def __init__(self, torch, dist, rank: int, world: int, device_index: int, stream: int, n_cols: int, key_col: int,
                  max_rows: int, max_recv_rows: int):
         self.lib = load()
-        self.world, self.n_cols = world, n_cols
+        self.world, self.n_cols, self.rank = world, n_cols, rank
         # the NCCL unique id travels over the process group that already exists
         uid = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
@@ -78,6 +78,7 @@ class NativeExchange:
             torch.cuda.synchronize(dev)
             self.round_packed([t.data_ptr() for t in self._warm], None, n, None)
             torch.cuda.synchronize(dev)
+            self.bytes_sent = 0
 
     def round_packed(self, col_ptrs, _counts, n_rows: int, watermark: Optional[int], more: bool = False):
         inp = (C.c_uint64 * self.n_cols)(*col_ptrs) if n_rows > 0 else None
@@ -88,6 +89,7 @@ class NativeExchange:
         if st != ffi.OK:
             raise ffi.ArroyoB200Error(st, (self.lib.arroyo_b200_xchg_last_error(self.h) or b"").decode())
         nc = self.n_cols
+        self.bytes_sent += (n_rows - int(self._rows[self.rank])) * nc * 8  # rows that left for another rank
         batches = [([self._cols[s * nc + c] for c in range(nc)], int(self._rows[s])) for s in range(self.world) if self._rows[s]]
         before = self.holder.last_present_watermark
         for s in range(self.world):
