@@ -762,7 +762,13 @@ class _Watchdog:
             time.sleep(1.0)
             if time.monotonic() - self.last > self.limit_s:
                 print(f"[arroyo_b200] rank {self.rank}: no progress for {self.limit_s:.0f} s in {self.what} "
-                      f"(last: {self.note}); giving up", file=sys.stderr, flush=True)
+                      f"(last: {self.note}); giving up.  Python stacks of every thread:", file=sys.stderr, flush=True)
+                try:
+                    import faulthandler
+                    faulthandler.dump_traceback(file=sys.stderr, all_threads=True)  # which call each thread sits in
+                except Exception:
+                    pass
+                sys.stderr.flush()
                 os._exit(124)
 
     def close(self):
