@@ -835,7 +835,11 @@ def bench(args, torch, dist, rank, world, local, all_cpus=None):
     mode = args.shuffle
     gen_pane = B.make_generator(torch, device, rows, args.keys, args.dist, 42 + rank, args.keyspace)
     panes = [gen_pane(p) for p in range(W + K)]
+    job = getattr(args, "_dog", None)
+    beat = job.beat if job is not None else (lambda note: None)
+    beat("input generated; timed plan")
     res = _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, panes, W, K)
+    beat("timed plan done")
     del panes
     ms, d = res["ms"], res["d"]
 
@@ -844,8 +848,10 @@ def bench(args, torch, dist, rank, world, local, all_cpus=None):
         # repeated like the single-GPU pass (the host links are shared with the box's other tenants): median reported
         Ke = args.e2e_steps or min(args.steps, 6)
         feed = B.host_feed(torch, gen_pane, range(13 + Ke), rows)
-        trials = [_e2e_partials(args, torch, dist, B, ab, native, rank, world, local, device, gen_pane, feed=feed)
-                  for _ in range(max(1, args.e2e_trials))]
+        trials = []
+        for i in range(max(1, args.e2e_trials)):
+            beat(f"end-to-end pass {i}")
+            trials.append(_e2e_partials(args, torch, dist, B, ab, native, rank, world, local, device, gen_pane, feed=feed))
         trials.sort(key=lambda r: r["value"])
         e2e = dict(trials[len(trials) // 2])
         e2e["trials"] = [round(r["value"]) for r in trials]
@@ -856,6 +862,7 @@ def bench(args, torch, dist, rank, world, local, all_cpus=None):
     verify = cpu = None
     if not args.skip_cpu:
         VP = B.WIDTH // B.SLIDE + 6
+        beat("CPU baseline on rank 0 (the other ranks wait for its sample size)")
         n_rows = torch.zeros(1, dtype=torch.int64, device=device)
         if rank == 0:
             if all_cpus:
@@ -865,6 +872,7 @@ def bench(args, torch, dist, rank, world, local, all_cpus=None):
             n_rows[0] = cpu["rows_per_step"]
         dist.broadcast(n_rows, src=0)
         vrows = int(n_rows.item())
+        beat("verification pass")
         vp = [B.sample_pane(torch, device, gen_pane(p), vrows) for p in range(VP)]
         vres = _run_plan(args, torch, dist, B, ab, native, rank, world, local, device, vp, VP, 0, collect=True)
         del vp
@@ -919,7 +927,10 @@ def bench(args, torch, dist, rank, world, local, all_cpus=None):
             out["verify"] = verify
             out["verified"] = verify["verified"]
         print(json.dumps(out), flush=True)
+    beat("done; final barrier")
     dist.barrier()
     dist.destroy_process_group()
+    if job is not None:
+        job.close()
     if rank == 0 and verify is not None and not verify["verified"]:
         sys.exit("bench.py: GPU windows differ from the oracle's -- see the verify block of the line above")

@@ -581,7 +581,13 @@ def run_ours(args):
     all_cpus = os.sched_getaffinity(0)
     args.numa = "not bound" if args.no_numa_bind else bind_to_gpu_numa_node(local)
     if world > 1:
+        # whole-job watchdog: a rank that sits in one phase (communicator set-up, a collective whose peer never
+        # arrives ...) for seven minutes says where, dumps its threads' stacks and exits, instead of hanging silently
+        from arroyo_b200.multi_gpu import _Watchdog
+        args._dog = _Watchdog(rank, f"bench.py at {world} GPUs", limit_s=420.0)
+        args._dog.beat("init_process_group")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        args._dog.beat("process group up")
     if ffi.load().arroyo_b200_device_count() < 1:
         raise RuntimeError("bench.py needs a CUDA device: arroyo_b200 has no CPU fallback")
     torch.cuda.set_device(local)
