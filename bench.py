@@ -35,8 +35,8 @@ if int(_os.environ.get("WORLD_SIZE", "1")) > 4:
     # Two NCCL communicators live in every rank at N > 1 (torch.distributed's and the Shuffle edge's own,
     # csrc/exchange.cu); all this job moves through collectives is an 80-byte control record per round, so NVLink SHARP
     # (NVLS: multicast objects set up per communicator across the whole NVSwitch domain) buys nothing and is left out
-    # of the set-up on large boxes.  The one N = 8 attempt of round 2 did not get past its set-up within five minutes
-    # (cause not established: no GPU time was left to look); N <= 4 run with NCCL's defaults, as measured.
+    # of the set-up on large boxes.  The one N = 8 attempt of round 2 printed nothing within five minutes (cause not
+    # established: no GPU time was left to look); N <= 4 run with NCCL's defaults, as measured.
     _os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
 
 import argparse
@@ -96,9 +96,12 @@ def parse():
     ap.add_argument("--python-exchange", action="store_true",
                     help="N>1, partials: the shuffle round through torch.distributed (device partitioner + all_gather + "
                          "all_to_all_single from Python) instead of the library's own round (csrc/exchange.cu: partition + "
-                         "control all-gather + grouped ncclSend / ncclRecv in one C call), which is the default: "
-                         "47.7 vs 32.7 G rows/s at N = 2 (profiles/r02_bench_n2_*.json)")
-    ap.add_argument("--native-exchange", action="store_true", help="accepted and ignored (it is the default since round 2)")
+                         "control all-gather + grouped ncclSend / ncclRecv in one C call): 56.7 vs 61.9 G rows/s at N = 2 "
+                         "(profiles/r02_bench_n2*.json)")
+    ap.add_argument("--native-exchange", action="store_true",
+                    help="N>1, partials: the library's own round (see --python-exchange).  It is the default up to 4 GPUs, "
+                         "where it was measured; above that the default is the torch.distributed round, the one that has "
+                         "run on eight GPUs (round 1) -- the library's round is selected with this flag")
     ap.add_argument("--sync-plan", action="store_true",
                     help="N>1, partials: run the local stage, the shuffle and the owner stage in sequence on one host "
                          "thread instead of as a two-stage pipeline")
@@ -116,7 +119,8 @@ def parse():
     ap.add_argument("--shuffle", default="partials", choices=["partials", "rows"],
                     help="N>1: what crosses the all-to-all (per-pane partial aggregates, or raw rows)")
     args = ap.parse_args()
-    args.native_exchange = not args.python_exchange
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.native_exchange = (not args.python_exchange) and (world <= 4 or args.native_exchange)
     return args
 
 
